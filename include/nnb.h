@@ -1,0 +1,213 @@
+/*
+ * nnb.h -- C ABI of libnnb.so: the B200-native (sm_100a) hot path of adammoss/nnest.
+ *
+ * The reference is pure Python and has no FFI; its boundary for this path is Python-level
+ * (SURVEY.md section 8b).  Each entry point below names the reference code it replaces.  A
+ * reference maintainer binds these with ctypes from nnest/trainer.py and nnest/sampler.py
+ * (stub shown in INTEGRATION.md); nnest_b200/_lib.py is exactly that binding.
+ *
+ * Conventions
+ *   - every function returns 0 (NNB_OK) or a negative error code; nnb_last_error() gives text.
+ *     Nothing throws across the ABI.  There is no CPU fallback: without a CUDA device
+ *     nnb_create fails with NNB_ERR_CUDA.
+ *   - pointers marked [dev] are device pointers owned by the caller (e.g. torch tensors);
+ *     pointers marked [host] are host memory read during the call.  The library owns only its
+ *     handle and a small device workspace.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     stream-ordered and asynchronous unless stated otherwise.  One handle per device; a handle is
+ *     not re-entrant.
+ *   - matrices of per-chain vectors are addressed as ptr[row * row_stride + col * col_stride]
+ *     (strides in elements): row-major (n,d) is (d,1); chain-minor "SoA" (d,n) is (1,n).
+ */
+#ifndef NNB_H_
+#define NNB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNB_ABI_VERSION 1
+#define NNB_MAX_DIM 128      /* x_dim */
+#define NNB_MAX_BLOCKS 16    /* num_blocks */
+#define NNB_MAX_LIKE_PARAMS 160
+
+enum {
+  NNB_OK = 0,
+  NNB_ERR_ARG = -1,          /* invalid argument / unsupported shape */
+  NNB_ERR_CUDA = -2,         /* CUDA runtime error (text in nnb_last_error) */
+  NNB_ERR_STATE = -3,        /* flow or target not set */
+  NNB_ERR_UNSUPPORTED = -4,  /* valid in the reference but not implemented on the device */
+  NNB_ERR_START = -5         /* 'Could not find starting value' (nnest/sampler.py:284) */
+};
+
+/* flags for nnb_set_flow (reference: `scale` kwarg of SingleSpeedNVP, nnest/networks.py:330-346) */
+enum { NNB_FLOW_TRANSLATE_ONLY = 1, NNB_FLOW_CONST_SCALE = 2 };
+
+/* likelihood ids (reference: nnest/likelihoods.py) */
+enum {
+  NNB_LIKE_ROSENBROCK = 0,     /* :48-51   params: none */
+  NNB_LIKE_HIMMELBLAU = 1,     /* :62-70   params: none, d == 2 */
+  NNB_LIKE_GAUSSIAN = 2,       /* :77-86   params: corr */
+  NNB_LIKE_EGGBOX = 3,         /* :97-106  params: none (product over all dims; reference has d == 2) */
+  NNB_LIKE_GAUSSIAN_MIX = 4,   /* :165-189 params: sep, sigma, ncomp, w[ncomp] */
+  NNB_LIKE_GAUSSIAN_SHELL = 5  /* :113-128 params: sigma, rshell, center[d] */
+};
+
+enum { NNB_PRIOR_NONE = 0, NNB_PRIOR_BOX_U = 1, NNB_PRIOR_BOX_V = 2 };
+enum { NNB_MODE_HARD = 0, NNB_MODE_MH = 1 };
+
+typedef struct nnb_handle nnb_handle;
+
+int nnb_abi_version(void);
+
+/* Create / destroy a per-device context. */
+int nnb_create(int device, nnb_handle** out);
+void nnb_destroy(nnb_handle* h);
+/* Text of the last error on this handle (or of the last failed nnb_create when h == NULL). */
+const char* nnb_last_error(nnb_handle* h);
+
+/*
+ * Install the weights of a SingleSpeedNVP (replaces holding an nn.Module: nnest/networks.py:328-347,
+ * built at nnest/trainer.py:90).  weights [host]: netG.state_dict() order -- for each block k,
+ * the scale net (omitted if NNB_FLOW_TRANSLATE_ONLY) then the translate net, each as
+ * Linear(d,H), [Linear(H,H)] x num_layers, Linear(H,d), every Linear as weight (out*in, row-major)
+ * followed by bias (out); then, if NNB_FLOW_CONST_SCALE, one float per block (ScaleLayer.scale).
+ * Coupling masks are not parameters: block k uses mask[i] = (i + k) % 2 (networks.py:333-346).
+ * Synchronous (small H2D copy).  hidden must be one of 16, 32, 64.
+ */
+int nnb_set_flow(nnb_handle* h, int d, int hidden, int num_layers, int num_blocks, int flags,
+                 const float* weights, size_t n_floats);
+
+/*
+ * Flow maps (replace Trainer.inverse / Trainer.forward, nnest/trainer.py:247-269 ->
+ * NormalizingFlow.inverse / forward nnest/networks.py:24-42 -> CouplingLayer nnest/networks.py:289-309).
+ * in/out [dev] float32 n x d with the given strides, logdet [dev] float32 n (may be NULL).
+ * in and out may alias when their strides are equal.
+ */
+int nnb_flow_inverse(nnb_handle* h, const float* z, int64_t z_rs, int64_t z_cs, float* x, int64_t x_rs,
+                     int64_t x_cs, float* logdet, int64_t n, void* stream);
+int nnb_flow_forward(nnb_handle* h, const float* x, int64_t x_rs, int64_t x_cs, float* z, int64_t z_rs,
+                     int64_t z_cs, float* logdet, int64_t n, void* stream);
+
+/*
+ * Likelihood o transform, and prior (replace safe_loglike / safe_prior / safe_transform,
+ * nnest/sampler.py:100-163, and the per-row loops of nnest/likelihoods.py:14-22, nnest/priors.py:39-43).
+ *   transform: v[i] = u[i] * t_scale[i] + t_shift[i]  (the affine maps of examples/nested/run.py:25-44
+ *              and nnest/mcmc.py:111); NULL arrays = identity.
+ *   compute_f64: 0 = arithmetic follows the float32 input as NumPy does in the reference;
+ *                1 = inputs are promoted to float64 before the transform (float64 live points,
+ *                    nnest/priors.py:46, or a float64 transform, nnest/mcmc.py:111).
+ *   prior_kind: NNB_PRIOR_BOX_U tests lo <= u <= hi (NestedSampler: transform_prior=False,
+ *               nnest/nested.py:76,84); NNB_PRIOR_BOX_V tests transform(u) (nnest/sampler.py:158-159).
+ * All arrays [host], d entries each (like_params: n_like_params entries).  Synchronous.
+ */
+typedef struct {
+  int like_id;
+  int n_like_params;
+  const double* like_params;
+  int compute_f64;
+  const double* t_scale;
+  const double* t_shift;
+  int prior_kind;
+  const double* prior_lo;
+  const double* prior_hi;
+} nnb_target;
+
+int nnb_set_target(nnb_handle* h, int d, const nnb_target* t);
+
+/*
+ * logl[r] = safe_loglike(u[r]) for n rows (nnest/sampler.py:110-133): non-finite values become
+ * -1e100 (-inf when the reference's result would be float32).  u [dev] n x d, float32 or float64
+ * (in_f64); logl [dev] float64 n.  logp (may be NULL) [dev] float64 n receives safe_prior: 0 or -inf.
+ */
+int nnb_loglike(nnb_handle* h, const void* u, int in_f64, int64_t u_rs, int64_t u_cs, double* logl,
+                double* logp, int64_t n, void* stream);
+
+/*
+ * The batched latent-space MCMC step (replaces Sampler._mcmc_sample, nnest/sampler.py:229-463):
+ * `steps` Metropolis steps of n_chains independent chains entirely on the device.
+ *
+ * Per-chain state lives in caller-owned chain-minor buffers (element (i, c) at [i * n_chains + c]):
+ *   z, x [dev] float32 d x n; logl [dev] float64 n; logdet [dev] float32 n; logp [dev] float64 n.
+ * nnb_mcmc_init fills them from start points; nnb_mcmc_run advances them in place.
+ */
+typedef struct {
+  int64_t n_chains;
+  /* state (in/out) */
+  float* z;
+  float* x;
+  double* logl;
+  float* logdet;
+  double* logp;
+  /* start: exactly one of init_u / init_z may be non-NULL, both NULL = draw z ~ N(0,I) from Philox
+   * (nnest/sampler.py:262-284).  Chain-minor d x n [dev] float32. */
+  const float* init_u;
+  const float* init_z;
+  const double* init_logl; /* [dev] n, NULL = evaluate the likelihood of the start points */
+  uint64_t seed;
+  uint64_t chain_offset; /* global id of chain 0 (multi-GPU sharding: results independent of the split) */
+  uint32_t start_try;    /* retry counter for Philox starts */
+  /* out [host] */
+  int64_t* n_bad_start;  /* chains whose start logl <= -1e30 (nnest/sampler.py:281) */
+  int64_t* ncall;        /* likelihood evaluations performed */
+} nnb_mcmc_init_args;
+
+int nnb_mcmc_init(nnb_handle* h, const nnb_mcmc_init_args* a, void* stream); /* synchronous */
+
+typedef struct {
+  int64_t n_chains;
+  int steps;
+  int mode;              /* NNB_MODE_HARD: accept iff Jacobian/prior test passes and logl > loglstar
+                            (sampler.py:299-370); NNB_MODE_MH: Metropolis ratio (sampler.py:372-416) */
+  double loglstar;
+  double step_size;      /* initial scale; <= 0 -> 2/sqrt(d) (sampler.py:248-249) */
+  int dynamic_step_size; /* sampler.py:422-430, one scale per call (= per rank, as under MPI) */
+  uint64_t seed;
+  uint64_t chain_offset;
+  uint32_t step_offset;  /* Philox step counter of the first step is step_offset + 1 */
+  /* state (in/out), as nnb_mcmc_init */
+  float* z;
+  float* x;
+  double* logl;
+  float* logdet;
+  double* logp;
+  /* optional full trace [dev]: row t (0..steps) of trace_x/trace_z is d x n chain-minor, i.e. element
+   * (t, i, c) at [(t * d + i) * n + c]; trace_logl (t, c) at [t * n + c].  Row 0 = the state at entry
+   * (samples.append before the loop, sampler.py:286-289).  NULL = not recorded. */
+  float* trace_x;
+  float* trace_z;
+  double* trace_logl;
+  /* optional replay noise [dev] (parity tests): normals (steps, n, d) row-major float32 in the
+   * reference's draw order torch.randn_like(z) (sampler.py:310/:377); uniforms (steps, n)
+   * (sampler.py:334/:412).  NULL = Philox4x32-10 keyed (seed; chain, step). */
+  const float* replay_normals;
+  const float* replay_uniforms;
+  /* optional dump of the noise actually used, same layouts [dev] */
+  float* dump_normals;
+  float* dump_uniforms;
+  /* out [host] */
+  double* scale_out;     /* final scale (sampler.py:463) */
+  int64_t* ncall_out;    /* likelihood calls (sampler.py:363,397) */
+  int64_t* naccept_out;  /* accepted proposals (total_accepted, sampler.py:418-420) */
+} nnb_mcmc_args;
+
+int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream); /* synchronous at return */
+
+/*
+ * Live-point replacement (replaces the consume loop of NestedSampler.run, nnest/nested.py:429-439,
+ * together with the selection of the worst point nnest/nested.py:272-276).  Host-side, exact:
+ * scans chains ib = *nb .. n_chains-1 (incrementing *nb for each inspected chain) for the first whose
+ * end point differs from its start point in EVERY coordinate and whose end loglike > loglstar.
+ * first/last [host] float32 row-major (n_chains, d); logl_last [host] float64 n_chains.
+ * Returns the chain index used, or -1 if the rest of the batch was exhausted without a usable chain.
+ */
+int64_t nnb_consume_scan(const float* first, const float* last, const double* logl_last, int64_t n_chains,
+                         int d, double loglstar, int64_t* nb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNB_H_ */

@@ -1,0 +1,348 @@
+// nnb_api.cu -- C ABI of libnnb.so (contract: include/nnb.h): handle management, weight packing,
+// dispatch to the per-hidden-size kernels, the likelihood kernel launch and the host-side
+// live-point scan.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nnb_host.h"
+
+using namespace nnb;
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+static std::string g_create_err;
+
+int nnb_fail(nnb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+static int fail(nnb_handle* h, int code, const std::string& msg) { return nnb_fail(h, code, msg); }
+
+extern "C" int nnb_abi_version(void) { return NNB_ABI_VERSION; }
+
+extern "C" const char* nnb_last_error(nnb_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int nnb_create(int device, nnb_handle** out) {
+  if (!out) return fail(nullptr, NNB_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, NNB_ERR_CUDA,
+                std::string("no CUDA device available (libnnb has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, NNB_ERR_ARG, "device index out of range");
+  nnb_handle* h = new nnb_handle();
+  h->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, NNB_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (prop.major < 10) {
+    delete h;
+    return fail(nullptr, NNB_ERR_CUDA, "libnnb is built for sm_100a (Blackwell B200) only");
+  }
+  h->sm_count = prop.multiProcessorCount;
+  h->max_smem = (int)prop.sharedMemPerBlockOptin;
+  if ((e = cudaMalloc(&h->d_ctrl, sizeof(Ctrl))) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_ctrl, sizeof(Ctrl))) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, NNB_ERR_CUDA, cudaGetErrorString(e));
+  }
+  *out = h;
+  return NNB_OK;
+}
+
+extern "C" void nnb_destroy(nnb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->d_weights) cudaFree(h->d_weights);
+  if (h->d_target) cudaFree(h->d_target);
+  if (h->d_ctrl) cudaFree(h->d_ctrl);
+  if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  delete h;
+}
+
+// Natural (state_dict) order -> packed device layout; see FlowDesc in nnb_device.cuh.
+static size_t natural_floats(int d, int H, int L, int B, int flags) {
+  size_t net = (size_t)H * d + H + (size_t)L * (H * H + H) + (size_t)d * H + d;
+  size_t nets = (flags & NNB_FLOW_TRANSLATE_ONLY) ? 1 : 2;
+  return B * nets * net + ((flags & NNB_FLOW_CONST_SCALE) ? B : 0);
+}
+
+static void pack_net(const float* src, int d, int H, int L, int k, float* dst) {
+  const int nin = blk_nin(d, k), i0 = blk_i0(k), nout = blk_nout(d, k), o0 = blk_o0(k);
+  const float* W1 = src;            // (H, d)
+  const float* b1 = W1 + (size_t)H * d;
+  float* o = dst;
+  for (int a = 0; a < nin; ++a)
+    for (int j = 0; j < H; ++j) *o++ = W1[(size_t)j * d + (i0 + 2 * a)];
+  for (int j = 0; j < H; ++j) *o++ = b1[j];
+  const float* p = b1 + H;
+  for (int l = 0; l < L; ++l) {
+    const float* W2 = p;            // (H, H) [j][k]
+    const float* b2 = W2 + (size_t)H * H;
+    for (int kk = 0; kk < H; ++kk)
+      for (int j = 0; j < H; ++j) *o++ = W2[(size_t)j * H + kk];
+    for (int j = 0; j < H; ++j) *o++ = b2[j];
+    p = b2 + H;
+  }
+  const float* W3 = p;              // (d, H)
+  const float* b3 = W3 + (size_t)d * H;
+  for (int q = 0; q < nout; ++q)
+    for (int j = 0; j < H; ++j) *o++ = W3[(size_t)(o0 + 2 * q) * H + j];
+  for (int q = 0; q < round4(nout); ++q) *o++ = q < nout ? b3[o0 + 2 * q] : 0.f;
+}
+
+extern "C" int nnb_set_flow(nnb_handle* h, int d, int hidden, int num_layers, int num_blocks, int flags,
+                            const float* weights, size_t n_floats) {
+  if (!h) return NNB_ERR_ARG;
+  if (d < 1 || d > NNB_MAX_DIM) return fail(h, NNB_ERR_ARG, "x_dim must be in [1, NNB_MAX_DIM]");
+  if (hidden != 16 && hidden != 32 && hidden != 64)
+    return fail(h, NNB_ERR_UNSUPPORTED, "hidden_dim must be 16, 32 or 64");
+  if (num_layers < 0 || num_layers > 8) return fail(h, NNB_ERR_ARG, "num_layers must be in [0, 8]");
+  if (num_blocks < 1 || num_blocks > NNB_MAX_BLOCKS) return fail(h, NNB_ERR_ARG, "num_blocks out of range");
+  if ((flags & NNB_FLOW_CONST_SCALE) && !(flags & NNB_FLOW_TRANSLATE_ONLY))
+    return fail(h, NNB_ERR_ARG, "NNB_FLOW_CONST_SCALE implies NNB_FLOW_TRANSLATE_ONLY (networks.py:331)");
+  if (!weights || n_floats != natural_floats(d, hidden, num_layers, num_blocks, flags))
+    return fail(h, NNB_ERR_ARG, "weight buffer size does not match (d, hidden, num_layers, num_blocks, flags)");
+  NNB_CUDA(h, cudaSetDevice(h->device));
+  FlowDesc f{};
+  f.d = d; f.H = hidden; f.L = num_layers; f.B = num_blocks; f.flags = flags;
+  const bool tonly = flags & NNB_FLOW_TRANSLATE_ONLY;
+  const size_t net_nat = (size_t)hidden * d + hidden + (size_t)num_layers * (hidden * hidden + hidden) +
+                         (size_t)d * hidden + d;
+  int off = 0;
+  for (int k = 0; k < num_blocks; ++k) {
+    const int nf = net_floats(d, hidden, num_layers, k);
+    if (tonly) {
+      f.off_s[k] = -1;
+    } else {
+      f.off_s[k] = off;
+      off += nf;
+    }
+    f.off_t[k] = off;
+    off += nf;
+  }
+  f.total_floats = off;
+  std::vector<float> packed((size_t)off, 0.f);
+  const float* src = weights;
+  for (int k = 0; k < num_blocks; ++k) {
+    if (!tonly) {
+      pack_net(src, d, hidden, num_layers, k, packed.data() + f.off_s[k]);
+      src += net_nat;
+    }
+    pack_net(src, d, hidden, num_layers, k, packed.data() + f.off_t[k]);
+    src += net_nat;
+  }
+  for (int k = 0; k < num_blocks; ++k) f.cscale[k] = (flags & NNB_FLOW_CONST_SCALE) ? src[k] : 0.f;
+  if (smem_bytes(f.total_floats, target_doubles(d, NNB_MAX_LIKE_PARAMS), d, 2) > (size_t)h->max_smem)
+    return fail(h, NNB_ERR_UNSUPPORTED, "flow too large for one CTA's shared memory (reduce x_dim / hidden_dim / blocks)");
+  if (h->d_weights) { cudaFree(h->d_weights); h->d_weights = nullptr; }
+  NNB_CUDA(h, cudaMalloc(&h->d_weights, packed.size() * sizeof(float)));
+  NNB_CUDA(h, cudaMemcpy(h->d_weights, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->flow = f;
+  h->has_flow = true;
+  return NNB_OK;
+}
+
+extern "C" int nnb_set_target(nnb_handle* h, int d, const nnb_target* t) {
+  if (!h || !t) return NNB_ERR_ARG;
+  if (d < 1 || d > NNB_MAX_DIM) return fail(h, NNB_ERR_ARG, "x_dim must be in [1, NNB_MAX_DIM]");
+  if (t->n_like_params < 0 || t->n_like_params > NNB_MAX_LIKE_PARAMS || (t->n_like_params && !t->like_params))
+    return fail(h, NNB_ERR_ARG, "bad likelihood parameter array");
+  int need = 0;
+  switch (t->like_id) {
+    case NNB_LIKE_ROSENBROCK: need = 0; break;
+    case NNB_LIKE_HIMMELBLAU: need = 0; if (d != 2) return fail(h, NNB_ERR_ARG, "Himmelblau needs x_dim == 2"); break;
+    case NNB_LIKE_GAUSSIAN: need = 1; break;
+    case NNB_LIKE_EGGBOX: need = 0; break;
+    case NNB_LIKE_GAUSSIAN_MIX:
+      need = 3;
+      if (d < 2) return fail(h, NNB_ERR_ARG, "GaussianMix needs x_dim >= 2");
+      if (t->n_like_params >= 3) {
+        int nc = (int)t->like_params[2];
+        if (nc < 2 || nc > 4) return fail(h, NNB_ERR_ARG, "GaussianMix needs 2, 3 or 4 components");
+        need = 3 + nc;
+      }
+      break;
+    case NNB_LIKE_GAUSSIAN_SHELL: need = 2 + d; break;
+    default: return fail(h, NNB_ERR_UNSUPPORTED, "unknown likelihood id (arbitrary Python likelihoods cannot run on the device)");
+  }
+  if (t->n_like_params != need) return fail(h, NNB_ERR_ARG, "wrong number of likelihood parameters");
+  if (t->prior_kind != NNB_PRIOR_NONE && (!t->prior_lo || !t->prior_hi))
+    return fail(h, NNB_ERR_ARG, "box prior needs prior_lo / prior_hi");
+  if ((t->t_scale == nullptr) != (t->t_shift == nullptr)) return fail(h, NNB_ERR_ARG, "t_scale and t_shift go together");
+  NNB_CUDA(h, cudaSetDevice(h->device));
+  TargetDesc td{};
+  td.like_id = t->like_id; td.n_params = t->n_like_params; td.compute_f64 = t->compute_f64 ? 1 : 0;
+  td.prior_kind = t->prior_kind; td.has_transform = t->t_scale ? 1 : 0; td.d = d;
+  std::vector<double> buf((size_t)target_doubles(d, td.n_params), 0.0);
+  for (int i = 0; i < td.n_params; ++i) buf[i] = t->like_params[i];
+  double* ts = buf.data() + td.n_params;
+  for (int i = 0; i < d; ++i) {
+    ts[i] = t->t_scale ? t->t_scale[i] : 1.0;
+    ts[d + i] = t->t_shift ? t->t_shift[i] : 0.0;
+    ts[2 * d + i] = t->prior_lo ? t->prior_lo[i] : -INFINITY;
+    ts[3 * d + i] = t->prior_hi ? t->prior_hi[i] : INFINITY;
+  }
+  if (h->d_target) { cudaFree(h->d_target); h->d_target = nullptr; }
+  NNB_CUDA(h, cudaMalloc(&h->d_target, buf.size() * sizeof(double)));
+  NNB_CUDA(h, cudaMemcpy(h->d_target, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+  h->tdesc = td;
+  h->has_target = true;
+  return NNB_OK;
+}
+
+template <bool INV>
+static int flow_dispatch(nnb_handle* h, const float* in, int64_t irs, int64_t ics, float* out, int64_t ors,
+                         int64_t ocs, float* logdet, int64_t n, void* stream) {
+  if (!h) return NNB_ERR_ARG;
+  if (!h->has_flow) return fail(h, NNB_ERR_STATE, "nnb_set_flow has not been called");
+  if (n < 0 || (n > 0 && (!in || !out))) return fail(h, NNB_ERR_ARG, "bad buffer");
+  if (n == 0) return NNB_OK;
+  NNB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (h->flow.H) {
+    case 16: return LaunchH<16>::flow(h, INV, in, irs, ics, out, ors, ocs, logdet, n, st);
+    case 32: return LaunchH<32>::flow(h, INV, in, irs, ics, out, ors, ocs, logdet, n, st);
+    case 64: return LaunchH<64>::flow(h, INV, in, irs, ics, out, ors, ocs, logdet, n, st);
+  }
+  return fail(h, NNB_ERR_UNSUPPORTED, "hidden_dim");
+}
+
+extern "C" int nnb_flow_inverse(nnb_handle* h, const float* z, int64_t z_rs, int64_t z_cs, float* x, int64_t x_rs,
+                                int64_t x_cs, float* logdet, int64_t n, void* stream) {
+  return flow_dispatch<true>(h, z, z_rs, z_cs, x, x_rs, x_cs, logdet, n, stream);
+}
+
+extern "C" int nnb_flow_forward(nnb_handle* h, const float* x, int64_t x_rs, int64_t x_cs, float* z, int64_t z_rs,
+                                int64_t z_cs, float* logdet, int64_t n, void* stream) {
+  return flow_dispatch<false>(h, x, x_rs, x_cs, z, z_rs, z_cs, logdet, n, stream);
+}
+
+extern "C" int nnb_loglike(nnb_handle* h, const void* u, int in_f64, int64_t u_rs, int64_t u_cs, double* logl,
+                           double* logp, int64_t n, void* stream) {
+  if (!h) return NNB_ERR_ARG;
+  if (!h->has_target) return fail(h, NNB_ERR_STATE, "nnb_set_target has not been called");
+  if (n < 0 || (n > 0 && !u)) return fail(h, NNB_ERR_ARG, "bad buffer");
+  if (n == 0) return NNB_OK;
+  NNB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t sm = smem_bytes(0, target_doubles(h->tdesc.d, h->tdesc.n_params), h->tdesc.d, 0);
+  int grid = nnb_grid_for(h, n, 8);
+  if (in_f64)
+    loglike_kernel<double><<<grid, kBlockThreads, sm, st>>>(h->tdesc, h->d_target, (const double*)u, u_rs, u_cs, logl,
+                                                             logp, n);
+  else
+    loglike_kernel<float><<<grid, kBlockThreads, sm, st>>>(h->tdesc, h->d_target, (const float*)u, u_rs, u_cs, logl,
+                                                            logp, n);
+  NNB_CUDA(h, cudaGetLastError());
+  return NNB_OK;
+}
+
+static int check_mcmc_ready(nnb_handle* h) {
+  if (!h->has_flow) return fail(h, NNB_ERR_STATE, "nnb_set_flow has not been called");
+  if (!h->has_target) return fail(h, NNB_ERR_STATE, "nnb_set_target has not been called");
+  if (h->tdesc.d != h->flow.d) return fail(h, NNB_ERR_STATE, "flow and target have different x_dim");
+  return NNB_OK;
+}
+
+extern "C" int nnb_mcmc_init(nnb_handle* h, const nnb_mcmc_init_args* a, void* stream) {
+  if (!h || !a) return NNB_ERR_ARG;
+  int rc = check_mcmc_ready(h);
+  if (rc) return rc;
+  if (a->n_chains <= 0 || !a->z || !a->x || !a->logl || !a->logdet || !a->logp)
+    return fail(h, NNB_ERR_ARG, "state buffers missing");
+  if (a->init_u && a->init_z) return fail(h, NNB_ERR_ARG, "give at most one of init_u / init_z");
+  NNB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  std::memset(h->h_ctrl, 0, sizeof(Ctrl));
+  NNB_CUDA(h, cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
+  InitParams p{};
+  p.n = a->n_chains; p.z = a->z; p.x = a->x; p.logl = a->logl; p.logdet = a->logdet; p.logp = a->logp;
+  p.init_u = a->init_u; p.init_z = a->init_z; p.init_logl = a->init_logl;
+  p.seed_lo = (unsigned int)(a->seed & 0xffffffffu); p.seed_hi = (unsigned int)(a->seed >> 32);
+  p.chain_offset = a->chain_offset; p.start_try = a->start_try; p.ctrl = h->d_ctrl;
+  switch (h->flow.H) {
+    case 16: rc = LaunchH<16>::init(h, p, st); break;
+    case 32: rc = LaunchH<32>::init(h, p, st); break;
+    case 64: rc = LaunchH<64>::init(h, p, st); break;
+    default: rc = fail(h, NNB_ERR_UNSUPPORTED, "hidden_dim");
+  }
+  if (rc) return rc;
+  NNB_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  NNB_CUDA(h, cudaStreamSynchronize(st));
+  if (a->n_bad_start) *a->n_bad_start = (int64_t)h->h_ctrl->nbad;
+  if (a->ncall) *a->ncall = (int64_t)h->h_ctrl->ncall;
+  return NNB_OK;
+}
+
+extern "C" int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream) {
+  if (!h || !a) return NNB_ERR_ARG;
+  int rc = check_mcmc_ready(h);
+  if (rc) return rc;
+  if (a->n_chains <= 0 || a->steps < 0 || !a->z || !a->x || !a->logl || !a->logdet || !a->logp)
+    return fail(h, NNB_ERR_ARG, "state buffers missing");
+  if (a->mode != NNB_MODE_HARD && a->mode != NNB_MODE_MH) return fail(h, NNB_ERR_ARG, "mode");
+  if ((a->trace_x != nullptr) != (a->trace_z != nullptr) || (a->trace_x != nullptr) != (a->trace_logl != nullptr))
+    return fail(h, NNB_ERR_ARG, "trace_x, trace_z and trace_logl go together");
+  if ((a->replay_normals != nullptr) != (a->replay_uniforms != nullptr))
+    return fail(h, NNB_ERR_ARG, "replay_normals and replay_uniforms go together");
+  NNB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = h->flow.d;
+  const long long n = a->n_chains;
+  std::memset(h->h_ctrl, 0, sizeof(Ctrl));
+  h->h_ctrl->scale = a->step_size > 0.0 ? a->step_size : 2.0 / std::sqrt((double)d);  // sampler.py:248-249
+  NNB_CUDA(h, cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
+  if (a->trace_x) {  // row 0 = state at entry (sampler.py:286-289)
+    NNB_CUDA(h, cudaMemcpyAsync(a->trace_x, a->x, sizeof(float) * d * n, cudaMemcpyDeviceToDevice, st));
+    NNB_CUDA(h, cudaMemcpyAsync(a->trace_z, a->z, sizeof(float) * d * n, cudaMemcpyDeviceToDevice, st));
+    NNB_CUDA(h, cudaMemcpyAsync(a->trace_logl, a->logl, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  }
+  McmcParams p{};
+  p.n = n; p.mode = a->mode; p.dynamic = a->dynamic_step_size ? 1 : 0; p.loglstar = a->loglstar;
+  p.seed_lo = (unsigned int)(a->seed & 0xffffffffu); p.seed_hi = (unsigned int)(a->seed >> 32);
+  p.chain_offset = a->chain_offset; p.step_offset = a->step_offset;
+  p.z = a->z; p.x = a->x; p.logl = a->logl; p.logdet = a->logdet; p.logp = a->logp;
+  p.trace_x = a->trace_x; p.trace_z = a->trace_z; p.trace_logl = a->trace_logl;
+  p.replay_normals = a->replay_normals; p.replay_uniforms = a->replay_uniforms;
+  p.dump_normals = a->dump_normals; p.dump_uniforms = a->dump_uniforms;
+  p.ctrl = h->d_ctrl;
+  if (a->steps > 0) {
+    switch (h->flow.H) {
+      case 16: rc = LaunchH<16>::mcmc(h, p, a->steps, st); break;
+      case 32: rc = LaunchH<32>::mcmc(h, p, a->steps, st); break;
+      case 64: rc = LaunchH<64>::mcmc(h, p, a->steps, st); break;
+      default: rc = fail(h, NNB_ERR_UNSUPPORTED, "hidden_dim");
+    }
+    if (rc) return rc;
+  }
+  NNB_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  NNB_CUDA(h, cudaStreamSynchronize(st));
+  if (a->scale_out) *a->scale_out = h->h_ctrl->scale;
+  if (a->ncall_out) *a->ncall_out = (int64_t)h->h_ctrl->ncall;
+  if (a->naccept_out) *a->naccept_out = (int64_t)h->h_ctrl->naccept;
+  return NNB_OK;
+}
+
+extern "C" int64_t nnb_consume_scan(const float* first, const float* last, const double* logl_last, int64_t n_chains,
+                                    int d, double loglstar, int64_t* nb) {
+  if (!first || !last || !logl_last || !nb) return -1;
+  for (int64_t ib = *nb; ib < n_chains; ++ib) {
+    *nb = ib + 1;
+    const float* a = first + ib * d;
+    const float* b = last + ib * d;
+    bool all_differ = true;
+    for (int i = 0; i < d; ++i) all_differ &= (a[i] != b[i]);   // np.all(samples[ib,0,:] != samples[ib,-1,:])
+    if (all_differ && logl_last[ib] > loglstar) return ib;
+  }
+  return -1;
+}

@@ -1,0 +1,53 @@
+// nnb_host.h -- host-side handle and the per-hidden-size launchers of libnnb.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "nnb_kernels.cuh"
+
+struct nnb_handle {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem = 0;
+  bool has_flow = false, has_target = false;
+  nnb::FlowDesc flow{};
+  float* d_weights = nullptr;
+  nnb::TargetDesc tdesc{};
+  double* d_target = nullptr;
+  Ctrl* d_ctrl = nullptr;
+  Ctrl* h_ctrl = nullptr;  // pinned
+  std::string err;
+};
+
+int nnb_fail(nnb_handle* h, int code, const std::string& msg);
+
+#define NNB_CUDA(h, call)                                                                        \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return nnb_fail((h), NNB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+  } while (0)
+
+template <typename K>
+static inline cudaError_t nnb_set_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static inline int nnb_grid_for(nnb_handle* h, long long n, int ctas_per_sm) {
+  long long tiles = (n + nnb::kBlockThreads - 1) / nnb::kBlockThreads;
+  long long cap = (long long)h->sm_count * ctas_per_sm;
+  return (int)(tiles < cap ? tiles : cap);
+}
+
+// One translation unit per hidden size (nnb_h16.cu, nnb_h32.cu, nnb_h64.cu) so they compile in parallel.
+template <int H>
+struct LaunchH {
+  static int flow(nnb_handle* h, bool inverse, const float* in, int64_t irs, int64_t ics, float* out, int64_t ors,
+                  int64_t ocs, float* logdet, int64_t n, cudaStream_t st);
+  static int init(nnb_handle* h, const InitParams& p, cudaStream_t st);
+  static int mcmc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st);
+};
+extern template struct LaunchH<16>;
+extern template struct LaunchH<32>;
+extern template struct LaunchH<64>;

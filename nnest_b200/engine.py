@@ -1,0 +1,224 @@
+"""Thin torch-tensor front end of the C ABI (include/nnb.h).
+
+PyTorch is used for device memory and streams only; all arithmetic of the hot path happens in
+libnnb.so.  One Engine = one nnb_handle = one CUDA device.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _darr(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def flatten_state_dict(sd, scale=''):
+    """netG.state_dict() of a SingleSpeedNVP -> (flat float32 array in nnb_set_flow order, d, H, L, B, flags).
+    Key layout: flow.flows.<i>.{scale_net,translate_net}.<2j>.{weight,bias} (+ flow.flows.<i>.scale for
+    ScaleLayer), reference nnest/networks.py:262-282,312-347."""
+    get = lambda k: np.asarray(sd[k].detach().cpu().numpy() if hasattr(sd[k], 'detach') else sd[k], dtype=np.float32)
+    translate_only = scale in ('translate', 'constant')
+    stride = 2 if scale == 'constant' else 1
+    idx = sorted({int(k.split('.')[2]) for k in sd if k.startswith('flow.flows.')})
+    if not idx:
+        raise ValueError('not a SingleSpeedNVP state_dict')
+    num_blocks = (max(idx) + stride) // stride
+    parts = []
+    nlin = None
+    for k in range(num_blocks):
+        fi = k * stride
+        for net in ('scale_net', 'translate_net'):
+            if net == 'scale_net' and translate_only:
+                continue
+            j = 0
+            while 'flow.flows.%d.%s.%d.weight' % (fi, net, 2 * j) in sd:
+                w = get('flow.flows.%d.%s.%d.weight' % (fi, net, 2 * j))
+                if j == 0:
+                    hidden, d = w.shape
+                parts.append(w.ravel())
+                parts.append(get('flow.flows.%d.%s.%d.bias' % (fi, net, 2 * j)).ravel())
+                j += 1
+            if j < 2:
+                raise ValueError('state_dict is missing %s of block %d' % (net, k))
+            nlin = j
+    flags = 0
+    if translate_only:
+        flags |= L.NNB_FLOW_TRANSLATE_ONLY
+    if scale == 'constant':
+        flags |= L.NNB_FLOW_CONST_SCALE
+        parts.append(np.array([get('flow.flows.%d.scale' % (k * stride + 1)) for k in range(num_blocks)],
+                              dtype=np.float32).ravel())
+    return np.concatenate(parts), int(d), int(hidden), int(nlin - 2), int(num_blocks), flags
+
+
+class ChainState(object):
+    """Per-chain state in chain-minor layout (element (i, c) at [i * n + c])."""
+
+    def __init__(self, n, d, device):
+        self.n, self.d = n, d
+        self.z = torch.empty((d, n), dtype=torch.float32, device=device)
+        self.x = torch.empty((d, n), dtype=torch.float32, device=device)
+        self.logl = torch.empty((n,), dtype=torch.float64, device=device)
+        self.logdet = torch.empty((n,), dtype=torch.float32, device=device)
+        self.logp = torch.empty((n,), dtype=torch.float64, device=device)
+
+
+class Engine(object):
+
+    def __init__(self, device=None):
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError('nnest_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
+        h = C.c_void_p()
+        rc = self.lib.nnb_create(self.device.index, C.byref(h))
+        if rc != 0:
+            raise L.NNBError(rc, (self.lib.nnb_last_error(None) or b'').decode())
+        self.h = h
+        self.d = None
+        self.gpu_launches = 0     # kernels launched through this engine (bench.py reports it)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None):
+                self.lib.nnb_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        L.check(self.h, rc)
+
+    # ---- flow -------------------------------------------------------------------------------
+    def set_flow(self, flat, d, hidden, num_layers, num_blocks, flags=0):
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        self._check(self.lib.nnb_set_flow(self.h, d, hidden, num_layers, num_blocks, flags,
+                                          flat.ctypes.data_as(C.POINTER(C.c_float)), flat.size))
+        self.d = d
+        self.flow_shape = (d, hidden, num_layers, num_blocks, flags)
+
+    def set_flow_from_state_dict(self, sd, scale=''):
+        flat, d, hidden, nl, nb, flags = flatten_state_dict(sd, scale)
+        self.set_flow(flat, d, hidden, nl, nb, flags)
+
+    def _flow(self, fn, a):
+        assert a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[1] == self.d
+        n = a.shape[0]
+        out = torch.empty((n, self.d), dtype=torch.float32, device=a.device)
+        ld = torch.empty((n,), dtype=torch.float32, device=a.device)
+        if n:
+            self._check(fn(self.h, _ptr(a), a.stride(0), a.stride(1), _ptr(out), out.stride(0), out.stride(1),
+                           _ptr(ld), n, _stream()))
+            self.gpu_launches += 1
+        return out, ld
+
+    def flow_inverse(self, z):
+        """z (n,d) float32 cuda (any strides) -> x (n,d), log|det dx/dz| (n,)"""
+        return self._flow(self.lib.nnb_flow_inverse, z)
+
+    def flow_forward(self, x):
+        return self._flow(self.lib.nnb_flow_forward, x)
+
+    # ---- target -----------------------------------------------------------------------------
+    def set_target(self, d, like_id, like_params=(), t_scale=None, t_shift=None, compute_f64=False,
+                   prior_kind=L.NNB_PRIOR_NONE, prior_lo=None, prior_hi=None):
+        t = L.nnb_target()
+        keep = []
+        t.like_id = like_id
+        t.n_like_params = len(like_params)
+        a, p = _darr(like_params if len(like_params) else [0.0])
+        keep.append(a)
+        t.like_params = p
+        t.compute_f64 = 1 if compute_f64 else 0
+        if t_scale is not None:
+            a, t.t_scale = _darr(np.broadcast_to(t_scale, (d,)))
+            keep.append(a)
+            a, t.t_shift = _darr(np.broadcast_to(0.0 if t_shift is None else t_shift, (d,)))
+            keep.append(a)
+        t.prior_kind = prior_kind
+        if prior_kind != L.NNB_PRIOR_NONE:
+            a, t.prior_lo = _darr(np.broadcast_to(prior_lo, (d,)))
+            keep.append(a)
+            a, t.prior_hi = _darr(np.broadcast_to(prior_hi, (d,)))
+            keep.append(a)
+        self._check(self.lib.nnb_set_target(self.h, d, C.byref(t)))
+        self.target_d = d
+
+    def loglike(self, u, want_prior=False):
+        """u (n,d) float32 or float64 cuda -> logl float64 (n,) [, logp float64 (n,)]"""
+        assert u.is_cuda and u.dim() == 2 and u.shape[1] == self.target_d
+        assert u.dtype in (torch.float32, torch.float64)
+        n = u.shape[0]
+        logl = torch.empty((n,), dtype=torch.float64, device=u.device)
+        logp = torch.empty((n,), dtype=torch.float64, device=u.device) if want_prior else None
+        if n:
+            self._check(self.lib.nnb_loglike(self.h, _ptr(u), 1 if u.dtype == torch.float64 else 0, u.stride(0),
+                                             u.stride(1), _ptr(logl), _ptr(logp), n, _stream()))
+            self.gpu_launches += 1
+        return (logl, logp) if want_prior else logl
+
+    # ---- MCMC -------------------------------------------------------------------------------
+    def mcmc_init(self, n, init_u=None, init_z=None, init_logl=None, seed=0, chain_offset=0, start_try=0):
+        """init_u / init_z: chain-minor (d,n) float32 cuda tensors.  Returns (ChainState, n_bad_start, ncall)."""
+        st = ChainState(n, self.d, self.device)
+        a = L.nnb_mcmc_init_args()
+        a.n_chains = n
+        a.z, a.x, a.logl, a.logdet, a.logp = [t.data_ptr() for t in (st.z, st.x, st.logl, st.logdet, st.logp)]
+        for name, t, dt in (('init_u', init_u, torch.float32), ('init_z', init_z, torch.float32),
+                            ('init_logl', init_logl, torch.float64)):
+            if t is not None:
+                assert t.is_cuda and t.dtype == dt and t.is_contiguous()
+                setattr(a, name, t.data_ptr())
+        a.seed, a.chain_offset, a.start_try = seed, chain_offset, start_try
+        nbad, ncall = C.c_int64(0), C.c_int64(0)
+        a.n_bad_start, a.ncall = C.pointer(nbad), C.pointer(ncall)
+        self._check(self.lib.nnb_mcmc_init(self.h, C.byref(a), _stream()))
+        self.gpu_launches += 1
+        return st, nbad.value, ncall.value
+
+    def mcmc_run(self, st, steps, mode=L.NNB_MODE_HARD, loglstar=0.0, step_size=0.0, dynamic_step_size=False,
+                 seed=0, chain_offset=0, step_offset=0, trace=False, replay=None, dump_noise=False):
+        """Advances `st` in place by `steps` steps.  Returns a dict with scale, ncall, naccept and, if
+        requested, the trace tensors (steps+1, d, n) / (steps+1, n) and the dumped noise."""
+        n, d = st.n, st.d
+        a = L.nnb_mcmc_args()
+        a.n_chains, a.steps, a.mode = n, steps, mode
+        a.loglstar = 0.0 if loglstar is None else float(loglstar)
+        a.step_size, a.dynamic_step_size = float(step_size), 1 if dynamic_step_size else 0
+        a.seed, a.chain_offset, a.step_offset = seed, chain_offset, step_offset
+        a.z, a.x, a.logl, a.logdet, a.logp = [t.data_ptr() for t in (st.z, st.x, st.logl, st.logdet, st.logp)]
+        out = {}
+        if trace:
+            out['trace_x'] = torch.empty((steps + 1, d, n), dtype=torch.float32, device=self.device)
+            out['trace_z'] = torch.empty((steps + 1, d, n), dtype=torch.float32, device=self.device)
+            out['trace_logl'] = torch.empty((steps + 1, n), dtype=torch.float64, device=self.device)
+            a.trace_x, a.trace_z, a.trace_logl = [out[k].data_ptr() for k in ('trace_x', 'trace_z', 'trace_logl')]
+        if replay is not None:
+            nrm, uni = replay
+            assert nrm.is_cuda and nrm.dtype == torch.float32 and nrm.is_contiguous() and tuple(nrm.shape) == (steps, n, d)
+            assert uni.is_cuda and uni.dtype == torch.float32 and uni.is_contiguous() and tuple(uni.shape) == (steps, n)
+            a.replay_normals, a.replay_uniforms = nrm.data_ptr(), uni.data_ptr()
+        if dump_noise:
+            out['normals'] = torch.empty((steps, n, d), dtype=torch.float32, device=self.device)
+            out['uniforms'] = torch.empty((steps, n), dtype=torch.float32, device=self.device)
+            a.dump_normals, a.dump_uniforms = out['normals'].data_ptr(), out['uniforms'].data_ptr()
+        scale, ncall, nacc = C.c_double(0), C.c_int64(0), C.c_int64(0)
+        a.scale_out, a.ncall_out, a.naccept_out = C.pointer(scale), C.pointer(ncall), C.pointer(nacc)
+        self._check(self.lib.nnb_mcmc_run(self.h, C.byref(a), _stream()))
+        self.gpu_launches += (steps if dynamic_step_size else (1 if steps else 0))
+        out.update(scale=scale.value, ncall=ncall.value, naccept=nacc.value)
+        return out

@@ -1,0 +1,86 @@
+"""CPU-side checks of the C-ABI library: it builds/loads and exports exactly what include/nnb.h declares.
+No compute call is made (there is no GPU here; the library has no CPU fallback by design)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from nnest_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, 'include', 'nnb.h')).read()
+    txt = re.sub(r'/\*.*?\*/', '', txt, flags=re.S)
+    return sorted(set(re.findall(r'\b(nnb_[a-z_0-9]+)\s*\(', txt)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from nnest_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), 'libnnb.so does not export %s' % n
+        assert n in _lib.SYMBOLS, 'ctypes binding lacks %s' % n
+    assert sorted(_lib.SYMBOLS) == names
+    assert lib.nnb_abi_version() == _lib.NNB_ABI_VERSION
+
+
+def test_struct_layout_matches_header(lib, tmp_path):
+    """sizeof / offsetof of every ABI struct, as gcc sees include/nnb.h, equal the ctypes mirror."""
+    import subprocess
+    from nnest_b200 import _lib
+    structs = {'nnb_target': _lib.nnb_target, 'nnb_mcmc_init_args': _lib.nnb_mcmc_init_args,
+               'nnb_mcmc_args': _lib.nnb_mcmc_args}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nnb.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for f, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, f, name, f))
+    lines += ['return 0; }']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == ctypes.sizeof(cls)
+        for f, _ in cls._fields_:
+            assert int(got['%s.%s' % (name, f)]) == getattr(cls, f).offset, (name, f)
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    h = ctypes.c_void_p()
+    rc = lib.nnb_create(0, ctypes.byref(h))
+    assert rc != 0 and not h.value
+    assert b'no CUDA device' in lib.nnb_last_error(None)
+    from nnest_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine(0)
+
+
+def test_consume_scan_semantics(lib):
+    """nested.py:429-439 : first chain from nb on whose end point differs from its start in EVERY coordinate
+    and whose end loglike beats loglstar; nb advances past every inspected chain."""
+    import numpy as np
+    first = np.array([[0, 0], [0, 0], [0, 0], [0, 0]], dtype=np.float32)
+    last = np.array([[0, 1], [1, 1], [2, 2], [3, 3]], dtype=np.float32)
+    logl = np.array([9.0, 0.5, 2.0, 3.0])
+    fp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    nb = ctypes.c_int64(0)
+    r = lib.nnb_consume_scan(fp(first), fp(last), logl.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 4, 2, 1.0,
+                             ctypes.byref(nb))
+    assert (r, nb.value) == (2, 3)        # chain 0 moved in one coordinate only, chain 1 fails the constraint
+    r = lib.nnb_consume_scan(fp(first), fp(last), logl.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 4, 2, 5.0,
+                             ctypes.byref(nb))
+    assert (r, nb.value) == (-1, 4)
