@@ -1,0 +1,65 @@
+"""One-process-per-GPU plumbing (torch.distributed; NCCL over NVLink on the GPU box, gloo in CPU tests).
+
+Replaces the reference's mpi4py pickle collectives (nnest/sampler.py:165-177; nnest/nested.py:199-226,416-427):
+  * chains are sharded by rank -- rank r owns global chain ids [r*n, (r+1)*n), which key the Philox streams, so a
+    chain's trajectory does not depend on how many GPUs the batch is split over;
+  * after a refill only the end states (start point, end point, end loglike: all that nested.py:432-437 reads)
+    are all-gathered, in rank order = the reference's np.concatenate order;
+  * flow weights are broadcast from rank 0 as one flat buffer after every (re)training.
+There is no data-path collective inside the MCMC steps themselves.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def is_distributed():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def rank_world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def chain_offset(n_chains_per_rank):
+    return rank_world()[0] * n_chains_per_rank
+
+
+def allgather_rows(t):
+    """Concatenate every rank's tensor along dim 0 in rank order (same shape on every rank)."""
+    if not is_distributed():
+        return t
+    t = t.contiguous()
+    parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, t)
+    return torch.cat(parts, dim=0)
+
+
+def broadcast_array(a, device, src=0):
+    """Broadcast a numpy array from `src`; every rank passes an array of the right shape/dtype."""
+    if not is_distributed():
+        return a
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    dist.broadcast(t, src=src)
+    return t.cpu().numpy()
+
+
+def broadcast_parameters(module, src=0):
+    """Replicate `module`'s parameters from `src` with ONE collective on a flat buffer."""
+    if not is_distributed():
+        return
+    params = list(module.parameters())
+    flat = torch.nn.utils.parameters_to_vector(params).detach().clone()
+    dist.broadcast(flat, src=src)
+    with torch.no_grad():
+        torch.nn.utils.vector_to_parameters(flat, params)
+
+
+def allreduce_sum_int(v, device):
+    if not is_distributed():
+        return int(v)
+    t = torch.tensor([int(v)], dtype=torch.int64, device=device)
+    dist.all_reduce(t)
+    return int(t.item())

@@ -1,0 +1,372 @@
+"""NestedSampler with the reference's interface (nnest/nested.py:24-510).
+
+The MCMC refill (nested.py:398-427) runs in the fused CUDA kernels (Sampler._mcmc_refill); live-point
+replacement (nested.py:429-439) uses the exact host scan exported by the C ABI (nnb_consume_scan); evidence
+bookkeeping (nested.py:272-293,458-464,487-500) is the reference's float64 arithmetic, kept verbatim on the
+host so that logZ, H and the posterior arrays are bit-identical given identical likelihood values.  The
+per-iteration O(it) rebuild of self.samples/weights/loglikes (nested.py:469-471) is deferred to the points
+where they are read (checkpoints, end of run): same values, linear instead of quadratic cost.
+
+Multi-GPU: one process per GPU under torchrun; every rank runs its own shard of chains, the end states are
+all-gathered over NCCL in rank order (the reference's gather + bcast + concatenate, nested.py:416-427) and
+every rank replays the identical bookkeeping.
+"""
+from __future__ import division, print_function
+
+import csv
+import ctypes
+import glob
+import json
+import logging
+import os
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import dist
+from .priors import UniformPrior
+from .sampler import Sampler
+
+
+class NestedSampler(Sampler):
+
+    def __init__(self,
+                 x_dim,
+                 loglike,
+                 transform=None,
+                 append_run_num=True,
+                 hidden_dim=16,
+                 num_slow=0,
+                 num_derived=0,
+                 batch_size=100,
+                 flow='spline',
+                 num_blocks=3,
+                 num_layers=1,
+                 learning_rate=0.001,
+                 log_dir='logs/test',
+                 resume=True,
+                 base_dist=None,
+                 scale='',
+                 use_gpu=True,
+                 trainer=None,
+                 oversample_rate=-1,
+                 log_level=logging.INFO,
+                 param_names=None,
+                 num_live_points=1000,
+                 seed=0):
+
+        prior = UniformPrior(x_dim, -1, 1)      # nested.py:76 : the flow lives on the unit hyper-cube [-1, 1]^d
+
+        super(NestedSampler, self).__init__(x_dim, loglike, transform=transform, append_run_num=append_run_num,
+                                            hidden_dim=hidden_dim, num_slow=num_slow, num_derived=num_derived,
+                                            batch_size=batch_size, flow=flow, num_blocks=num_blocks,
+                                            num_layers=num_layers, learning_rate=learning_rate,
+                                            log_dir=log_dir, resume=resume,
+                                            use_gpu=use_gpu, base_dist=base_dist, scale=scale, trainer=trainer,
+                                            prior=prior, transform_prior=False, log_level=log_level,
+                                            param_names=param_names, oversample_rate=oversample_rate, seed=seed)
+
+        self.num_live_points = num_live_points
+        self.sampler = 'nested'
+
+        if self.single_or_primary_process:
+            self.logger.info('Num live points [%d]' % self.num_live_points)
+            with open(os.path.join(self.logs['results'], 'results.csv'), 'w') as f:
+                writer = csv.writer(f)
+                writer.writerow(['step', 'acceptance', 'min_ess',
+                                 'max_ess', 'jump_distance', 'scale', 'loglstar', 'logz', 'fraction_remain', 'ncall'])
+
+    # ---- multi-GPU helpers -----------------------------------------------------------------------
+    def _allgather_batch(self, batch):
+        """Rank-order concatenation of every rank's end states (NCCL all_gather over NVLink)."""
+        if not self.use_mpi:
+            return batch, self.total_calls
+        out = {key: dist.allgather_rows(batch[key]) for key in ('first', 'last', 'logl_last')}
+        out.update(scale=batch['scale'], ncall=batch['ncall'], trace_x=batch.get('trace_x'))
+        return out, dist.allreduce_sum_int(self.total_calls, self.device)
+
+    def _bcast_array(self, a):
+        return dist.broadcast_array(a, self.device)
+
+    # ---------------------------------------------------------------------------------------------
+    def run(
+            self,
+            strategy=None,
+            mcmc_steps=0,
+            mcmc_num_chains=10,
+            mcmc_dynamic_step_size=True,
+            max_iters=1000000,
+            update_interval=None,
+            log_interval=None,
+            dlogz=0.5,
+            train_iters=500,
+            volume_switch=-1.0,
+            step_size=0.0,
+            jitter=-1.0,
+            rejection_cache_interval=10,
+            rejection_enlargement_factor=1.1,
+            rejection_trials=None,
+            chain_stats=True):
+
+        if strategy is None or len(strategy) == 0:
+            strategy = ['rejection_prior', 'mcmc']
+        for method in strategy:
+            if method not in ('rejection_prior', 'mcmc'):
+                raise NotImplementedError("strategy %r is not implemented on the accelerated path" % method)
+        expired_strategies = []
+        current_method = ''
+
+        if update_interval is None:
+            update_interval = max(1, round(0.5 * self.num_live_points))
+        else:
+            update_interval = round(update_interval)
+            if update_interval < 1:
+                raise ValueError("update_interval must be >= 1")
+
+        if log_interval is None:
+            log_interval = max(1, round(0.2 * self.num_live_points))
+        else:
+            log_interval = round(log_interval)
+            if log_interval < 1:
+                raise ValueError("log_interval must be >= 1")
+
+        if mcmc_steps <= 0:
+            mcmc_steps = 5 * self.x_dim
+        if step_size <= 0.0:
+            step_size = 1 / self.x_dim ** 0.5
+
+        primary = self.single_or_primary_process
+        if primary:
+            self.logger.info('MCMC steps [%d]' % mcmc_steps)
+            self.logger.info('Initial scale [%5.4f]' % step_size)
+            self.logger.info('Volume switch [%5.4f]' % volume_switch)
+
+        nlive = self.num_live_points
+        it = -1
+        if self.resume and self.logs is not None and not self.logs['created']:
+            for f in glob.glob(os.path.join(self.logs['checkpoint'], 'checkpoint_*.txt')):
+                it = max(it, int(f.split('/checkpoint_')[1].split('.txt')[0]))
+
+        if it >= 0:
+            if primary:
+                self.logger.info('Using checkpoint [%d]' % it)
+            with open(os.path.join(self.logs['checkpoint'], 'checkpoint_%s.txt' % it), 'r') as f:
+                data = json.load(f)
+            logz, h, logvol = data['logz'], data['h'], data['logvol']
+            self.total_calls = int(data['ncall'] / self.mpi_size)
+            fraction_remain = data['fraction_remain']
+            strategy = data['strategy']
+            expired_strategies = data['expired_strategies']
+            ckpt = self.logs['checkpoint']
+            active_u = np.load(os.path.join(ckpt, 'active_u_%s.npy' % it))
+            active_v = self.transform(active_u)
+            active_logl = np.load(os.path.join(ckpt, 'active_logl_%s.npy' % it))
+            active_derived = np.load(os.path.join(ckpt, 'active_derived_%s.npy' % it))
+            saved_v = np.load(os.path.join(ckpt, 'saved_v.npy')).tolist()
+            saved_logl = np.load(os.path.join(ckpt, 'saved_logl.npy')).tolist()
+            saved_logwt = np.load(os.path.join(ckpt, 'saved_logwt.npy')).tolist()
+            assert it == len(saved_logl)
+            total_calls = data['ncall']
+        else:
+            active_u = self.sample_prior(nlive) if primary else np.empty((nlive, self.x_dim), dtype=np.float64)
+            active_u = self._bcast_array(active_u)
+            active_v = self.transform(active_u)
+            # float64 live points -> float64 likelihood (nested.py:228 with priors.py:46)
+            active_logl, active_derived = self.loglike(active_u)
+            total_calls = self.total_calls
+            if primary:
+                self.logger.info('Step [0] max logl [%5.4e] vol [1.0] ncalls [%d]' % (np.max(active_logl), total_calls))
+            saved_v, saved_logl, saved_logwt = [], [], []
+            h = 0.0
+            logz = -1e300
+            logvol = np.log(1.0 - np.exp(-1.0 / nlive))
+            fraction_remain = 1.0
+            it = 0
+            if primary:
+                self._write_checkpoint(it, active_u, active_v, active_logl, active_derived, saved_v, saved_logl,
+                                       saved_logwt, logz, h, logvol, total_calls, fraction_remain, strategy,
+                                       expired_strategies)
+
+        lib = L.load()
+        first_time = True
+        get_samples = True
+        nb = 0
+        ncs = []
+        mean_calls = 0
+        accept_point = True
+        scale = step_size
+        batch = None
+        samples = loglikes = None
+        max_logl = np.max(active_logl)
+
+        while fraction_remain > dlogz and it <= max_iters:
+
+            worst = int(np.argmin(active_logl))               # nested.py:272 (first index on ties)
+            logwt = logvol + active_logl[worst]
+            loglstar = active_logl[worst]
+            expected_vol = np.exp(-it / nlive)
+
+            if accept_point:                                   # nested.py:280-293
+                logz_new = np.logaddexp(logz, logwt)
+                h = (np.exp(logwt - logz_new) * active_logl[worst] + np.exp(logz - logz_new) * (h + logz) - logz_new)
+                logz = logz_new
+                saved_v.append(np.array(active_v[worst], copy=True))
+                saved_logwt.append(logwt)
+                saved_logl.append(active_logl[worst])
+                accept_point = False
+
+            old_method = current_method
+            for method in strategy:
+                if method not in expired_strategies:
+                    current_method = method
+                    break
+            if current_method != old_method:
+                get_samples = True
+
+            if not current_method == 'rejection_prior' and (first_time or it % update_interval == 0):
+                self.trainer.train(active_u, max_iters=train_iters, jitter=jitter)     # nested.py:311-314
+                first_time = False
+
+            if current_method == 'rejection_prior':
+
+                if get_samples:
+                    nb = 0
+                    samples, loglikes, _, nc = self._rejection_prior_sample(loglstar, num_trials=rejection_trials)
+                    ncs.append(nc)
+                    mean_calls = np.mean(ncs[-20:]) if len(ncs) > 20 else 0
+                    if expected_vol < volume_switch >= 0 or \
+                            (volume_switch < 0 and mean_calls > mcmc_steps and 'mcmc' in strategy
+                             and 'mcmc' not in expired_strategies):
+                        self.logger.info('Rejection prior no longer efficient, switching sampling method')
+                        expired_strategies.append('rejection_prior')
+                        ncs = []
+
+                for ib in range(nb, samples.shape[0]):          # nested.py:375-385
+                    nb += 1
+                    get_samples = nb == samples.shape[0]
+                    if loglikes[ib] > loglstar:
+                        active_u[worst] = samples[nb - 1, :]
+                        active_v[worst] = self.transform(active_u[worst])
+                        active_logl[worst] = loglikes[nb - 1]
+                        accept_point = True
+                        break
+
+                total_calls = self.total_calls
+                if accept_point and it > 0 and (it + 1) % log_interval == 0 and primary:
+                    self.logger.info(
+                        'Step [%d] loglstar [%5.4e] max logl [%5.4e] logz [%5.4e] vol [%6.5e] ncalls [%d] mean '
+                        'calls [%5.4f]' % (it + 1, loglstar, np.max(active_logl), logz, expected_vol, total_calls,
+                                           mean_calls))
+
+            elif current_method == 'mcmc':
+
+                if get_samples:                                 # nested.py:402-427
+                    nb = 0
+                    idx = np.random.randint(low=0, high=nlive, size=mcmc_num_chains)
+                    batch = self._mcmc_refill(mcmc_steps, active_u[idx, :], active_logl[idx], loglstar, step_size,
+                                              mcmc_dynamic_step_size, keep_trace=chain_stats)
+                    batch, total_calls = self._allgather_batch(batch)
+                    scale = batch['scale']
+                    b_first = np.ascontiguousarray(batch['first'].cpu().numpy())
+                    b_last = np.ascontiguousarray(batch['last'].cpu().numpy())
+                    b_logl = np.ascontiguousarray(batch['logl_last'].cpu().numpy())
+                    fp = ctypes.POINTER(ctypes.c_float)
+                    p_first, p_last = b_first.ctypes.data_as(fp), b_last.ctypes.data_as(fp)
+                    p_logl = b_logl.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+                    n_batch = b_first.shape[0]
+
+                c_nb = ctypes.c_int64(nb)                       # nested.py:429-439
+                ib = lib.nnb_consume_scan(p_first, p_last, p_logl, n_batch, self.x_dim, float(loglstar),
+                                          ctypes.byref(c_nb))
+                nb = c_nb.value
+                get_samples = nb == n_batch
+                if ib >= 0:
+                    active_u[worst] = b_last[ib, :]
+                    active_v[worst] = self.transform(active_u[worst])
+                    active_logl[worst] = b_logl[ib]
+                    accept_point = True
+
+                if accept_point and it > 0 and it % log_interval == 0 and primary:
+                    if chain_stats and batch.get('trace_x') is not None:
+                        acceptance, ess, jump_distance = self._chain_stats(
+                            batch['trace_x'].permute(2, 0, 1), mean=np.mean(active_u, axis=0),
+                            std=np.std(active_u, axis=0))
+                    else:
+                        acceptance, ess, jump_distance = np.nan, np.array([np.nan]), np.nan
+                    self.logger.info(
+                        'Step [%d] loglstar [%5.4e] maxlogl [%5.4e] logz [%5.4e] vol [%6.5e] ncalls [%d] '
+                        'scale [%5.4f]' % (it, loglstar, np.max(active_logl), logz, expected_vol, total_calls, scale))
+                    with open(os.path.join(self.logs['results'], 'results.csv'), 'a') as f:
+                        writer = csv.writer(f)
+                        writer.writerow([it, acceptance, np.min(ess), np.max(ess),
+                                         jump_distance, scale, loglstar, logz, fraction_remain, total_calls])
+
+            if accept_point:                                    # nested.py:458-485
+                # np.max(active_logl) without the O(nlive) pass: the maximum only changes when the new point
+                # beats it (the replaced point is the minimum; if min == max every point was equal)
+                new_logl = active_logl[worst]
+                if loglstar == max_logl:
+                    max_logl = np.max(active_logl)
+                elif new_logl > max_logl:
+                    max_logl = new_logl
+                logvol -= 1.0 / nlive
+                logz_remain = max_logl - it / nlive
+                fraction_remain = np.logaddexp(logz, logz_remain) - logz
+                it += 1
+
+                if primary and self.trainer.writer is not None:
+                    self.trainer.writer.add_scalar('logz', logz, it)
+
+                if it > 0 and it % log_interval == 0 and primary:
+                    self._write_checkpoint(it, active_u, active_v, active_logl, active_derived, saved_v, saved_logl,
+                                           saved_logwt, logz, h, logvol, total_calls, fraction_remain, strategy,
+                                           expired_strategies)
+                    self.samples = np.array(saved_v)
+                    self.weights = np.exp(np.array(saved_logwt) - logz)
+                    self.loglikes = np.array(saved_logl)
+                    self._save_samples(self.samples, self.loglikes, weights=self.weights)
+
+        logvol = -len(saved_v) / nlive - np.log(nlive)         # nested.py:487-500
+        for i in range(nlive):
+            logwt = logvol + active_logl[i]
+            logz_new = np.logaddexp(logz, logwt)
+            h = (np.exp(logwt - logz_new) * active_logl[i] + np.exp(logz - logz_new) * (h + logz) - logz_new)
+            logz = logz_new
+            saved_v.append(np.array(active_v[i]))
+            saved_logwt.append(logwt)
+            saved_logl.append(active_logl[i])
+
+        self.logz = logz
+        self.h = h
+        self.logzerr = np.sqrt(h / nlive)
+        self.niter = it + 1
+        self.samples = np.array(saved_v)
+        self.weights = np.exp(np.array(saved_logwt) - logz)
+        self.loglikes = np.array(saved_logl)
+        self.active_u, self.active_logl = active_u, active_logl
+
+        if primary:
+            with open(os.path.join(self.logs['results'], 'final.csv'), 'w') as f:
+                writer = csv.writer(f)
+                writer.writerow(['niter', 'ncall', 'logz', 'logzerr', 'h'])
+                writer.writerow([it + 1, total_calls, logz, np.sqrt(h / nlive), h])
+            self._save_samples(self.samples, self.loglikes, weights=self.weights)
+            self.logger.info("niter: {:d}\n ncall: {:d}\n nsamples: {:d}\n logz: {:6.3f} +/- {:6.3f}\n h: {:6.3f}"
+                             .format(it + 1, int(total_calls), len(saved_v), logz, np.sqrt(h / nlive), h))
+
+    def _write_checkpoint(self, it, active_u, active_v, active_logl, active_derived, saved_v, saved_logl,
+                          saved_logwt, logz, h, logvol, total_calls, fraction_remain, strategy, expired_strategies):
+        """Checkpoint files of the reference (nested.py:249-260,473-484)."""
+        ckpt = self.logs['checkpoint']
+        np.save(os.path.join(ckpt, 'active_u_%s.npy' % it), active_u)
+        np.save(os.path.join(ckpt, 'active_v_%s.npy' % it), active_v)
+        np.save(os.path.join(ckpt, 'active_logl_%s.npy' % it), active_logl)
+        np.save(os.path.join(ckpt, 'active_derived_%s.npy' % it), active_derived)
+        np.save(os.path.join(ckpt, 'saved_v.npy'), saved_v)
+        np.save(os.path.join(ckpt, 'saved_logl.npy'), saved_logl)
+        np.save(os.path.join(ckpt, 'saved_logwt.npy'), saved_logwt)
+        with open(os.path.join(ckpt, 'checkpoint_%s.txt' % it), 'w') as f:
+            json.dump({'logz': float(logz), 'h': float(h), 'logvol': float(logvol), 'ncall': int(total_calls),
+                       'fraction_remain': float(fraction_remain), 'strategy': strategy,
+                       'expired_strategies': expired_strategies}, f)

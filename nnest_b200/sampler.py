@@ -1,0 +1,381 @@
+"""Sampler base class with the reference's interface (nnest/sampler.py:29-527) whose MCMC loop runs in the
+fused CUDA chain-step kernels.
+
+What is kept from the reference's contract:
+  * constructor kwargs and their defaults; `loglike`, `transform`, `prior` wrappers with the reference's
+    counting semantics (`total_calls`, `total_accepted`, `total_rejected`, `total_fast_calls`);
+  * `_mcmc_sample(...)` signature and 6-tuple return (arrays shaped (chain, iteration, dim));
+  * run-directory layout, `info/params.txt`, chain files written by `_save_samples` ("%.5E").
+What differs, by design (north_star: no CPU fallback):
+  * `loglike` must be one of nnest_b200.likelihoods (the batched CUDA likelihood library) and `transform`
+    must be a per-dimension affine map (probed numerically: the maps of examples/nested/run.py:25-44 and
+    nnest/mcmc.py:111 all are); anything else raises NotImplementedError;
+  * random numbers come from a per-chain Philox stream (seed = `seed` kwarg), not torch's global generator.
+"""
+from __future__ import division, print_function
+
+import json
+import logging
+import os
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import dist
+from .likelihoods import Likelihood
+from .priors import UniformPrior
+from .trainer import Trainer
+from .utils.evaluation import acceptance_rate, effective_sample_size, mean_jump_distance
+from .utils.logger import create_logger, get_or_create_run_dir
+
+
+def probe_affine_transform(transform, d):
+    """Recover (scale, shift, promotes_to_f64) of a per-dimension affine transform by evaluating it, and
+    verify it on random points.  Raises NotImplementedError for anything that is not diagonal-affine."""
+    if transform is None:
+        return None, None, False
+    zero = np.zeros((1, d), dtype=np.float32)
+    out0 = np.asarray(transform(zero))
+    promotes = out0.dtype == np.float64
+    z64 = np.zeros((1, d))
+    shift = np.asarray(transform(z64), dtype=np.float64).reshape(d)
+    scale = np.asarray(transform(np.ones((1, d))), dtype=np.float64).reshape(d) - shift
+    rng = np.random.RandomState(12345)
+    pts = rng.uniform(-1, 1, size=(16, d))
+    want = np.asarray(transform(pts), dtype=np.float64)
+    got = pts * scale + shift
+    tol = 1e-9 * (1.0 + np.abs(want).max())
+    if want.shape != pts.shape or np.abs(want - got).max() > tol:
+        raise NotImplementedError('transform is not a per-dimension affine map; arbitrary Python transforms '
+                                  'cannot run inside the CUDA step kernel (no CPU fallback)')
+    return scale, shift, promotes
+
+
+class Sampler(object):
+
+    def __init__(self,
+                 x_dim,
+                 loglike,
+                 transform=None,
+                 prior=None,
+                 append_run_num=True,
+                 hidden_dim=16,
+                 num_slow=0,
+                 num_derived=0,
+                 batch_size=100,
+                 flow='spline',
+                 num_blocks=3,
+                 num_layers=1,
+                 learning_rate=0.001,
+                 log_dir='logs/test',
+                 resume=True,
+                 use_gpu=True,
+                 base_dist=None,
+                 scale='',
+                 trainer=None,
+                 transform_prior=True,
+                 oversample_rate=-1,
+                 log_level=logging.INFO,
+                 param_names=None,
+                 seed=0,
+                 ):
+        self.x_dim = x_dim
+        self.num_derived = num_derived
+        self.num_params = x_dim + num_derived
+        assert x_dim > num_slow
+        if num_slow != 0:
+            raise NotImplementedError('fast/slow hierarchies (num_slow > 0) are not on the accelerated path')
+        if num_derived != 0:
+            raise NotImplementedError('derived parameters need a Python likelihood; the device likelihoods have none')
+        self.num_slow = num_slow
+        self.num_fast = x_dim - num_slow
+        self.param_names = param_names
+        if self.param_names is not None:
+            assert len(param_names) == self.num_params
+        self.oversample_rate = oversample_rate if oversample_rate > 0 else self.num_fast / self.x_dim
+
+        if not isinstance(loglike, Likelihood):
+            raise NotImplementedError(
+                'loglike must be an instance of nnest_b200.likelihoods.* (Rosenbrock, Himmelblau, Gaussian, Eggbox, '
+                'GaussianMix, GaussianShell): arbitrary Python callables cannot run in the CUDA kernels and there is '
+                'no CPU fallback')
+        self._like = loglike
+        self._user_transform = transform
+        self._prior_obj = prior
+        self._transform_prior = transform_prior
+        if prior is not None and not isinstance(prior, UniformPrior):
+            raise NotImplementedError('only UniformPrior (box) priors are implemented on the device')
+
+        sample_prior = getattr(prior, 'sample', None)
+        self.sample_prior = sample_prior if callable(sample_prior) else None
+
+        # distributed context: one process per GPU (torch.distributed), replaces the reference's mpi4py probe
+        self.mpi_rank, self.mpi_size = dist.rank_world()
+        self.use_mpi = self.mpi_size > 1
+        self.single_or_primary_process = self.mpi_rank == 0
+
+        args = locals()
+        args.update(vars(self))
+
+        if self.single_or_primary_process or os.path.isdir(os.path.join(log_dir, 'info')):
+            self.logs = get_or_create_run_dir(log_dir, append_run_num=append_run_num)
+            self.log_dir = self.logs['run_dir']
+        else:
+            self.logs = None
+            self.log_dir = None
+        if self.single_or_primary_process:
+            self._save_params(args)
+
+        self.resume = resume
+        self.logger = create_logger(__name__, level=log_level)
+
+        if trainer is None:
+            self.trainer = Trainer(
+                x_dim, hidden_dim=hidden_dim, num_slow=num_slow, batch_size=batch_size, flow=flow,
+                num_blocks=num_blocks, num_layers=num_layers, learning_rate=learning_rate, log_dir=self.log_dir,
+                log=self.single_or_primary_process, use_gpu=use_gpu, base_dist=base_dist, scale=scale,
+                log_level=log_level)
+        else:
+            self.trainer = trainer
+        self.engine = self.trainer.engine
+        self.device = self.engine.device
+
+        if self.single_or_primary_process:
+            self.logger.info('Num base params [%d]' % (self.x_dim))
+            self.logger.info('Num derived params [%d]' % (self.num_derived))
+            self.logger.info('Total params [%d]' % (self.num_params))
+
+        self.total_accepted = 0
+        self.total_rejected = 0
+        self.total_calls = 0
+        self.total_fast_calls = 0
+        self.seed = int(seed)
+        self._step_counter = 0        # Philox step offset: every MCMC step of the run uses fresh counters
+        self._start_counter = 0
+        self.transform = transform    # property: (re)installs the device target
+
+    # ---- target plumbing ------------------------------------------------------------------------
+    @property
+    def transform(self):
+        return self._transform_fn
+
+    @transform.setter
+    def transform(self, fn):
+        """Assigning `sampler.transform = ...` (as MCMCSampler.run does, nnest/mcmc.py:111) re-probes the map and
+        re-installs likelihood + transform + prior on the device."""
+        self._user_transform = fn
+        scale, shift, promotes = probe_affine_transform(fn, self.x_dim)
+        self._t_scale, self._t_shift, self._t_f64 = scale, shift, promotes
+
+        if fn is None:
+            self._transform_fn = lambda x: x
+        else:
+            def safe_transform(x):
+                if isinstance(x, list):
+                    x = np.array(x)
+                if len(x.shape) == 1:
+                    assert x.shape[0] == self.x_dim
+                    x = np.expand_dims(x, 0)
+                return fn(x)
+            self._transform_fn = safe_transform
+        self._install_target()
+
+    def _install_target(self):
+        prior = self._prior_obj
+        if prior is None:
+            kind, lo, hi = L.NNB_PRIOR_NONE, None, None
+        else:
+            kind = L.NNB_PRIOR_BOX_V if (self._transform_prior and self._user_transform is not None) \
+                else L.NNB_PRIOR_BOX_U
+            lo, hi = prior.minimum.astype(np.float64), prior.maximum.astype(np.float64)
+        self.engine.set_target(self.x_dim, self._like.like_id, self._like.device_params(), t_scale=self._t_scale,
+                               t_shift=self._t_shift, compute_f64=self._t_f64, prior_kind=kind, prior_lo=lo,
+                               prior_hi=hi)
+
+    def _to_device_rows(self, x):
+        if isinstance(x, list):
+            x = np.array(x)
+        x = np.asarray(x)
+        if x.ndim == 1:
+            assert x.shape[0] == self.x_dim
+            x = x[None, :]
+        if x.dtype not in (np.float32, np.float64):
+            x = x.astype(np.float64)
+        return x, torch.from_numpy(np.ascontiguousarray(x)).to(self.device)
+
+    def loglike(self, x):
+        """safe_loglike (nnest/sampler.py:110-133): loglike(transform(x)) for a batch of points in the flow's
+        coordinates, non-finite -> -1e100, call counter updated.  Returns (logl, derived (n, 0))."""
+        x, xd = self._to_device_rows(x)
+        logl = self.engine.loglike(xd).cpu().numpy()
+        self.total_calls += x.shape[0]
+        if self._like.follows_input_dtype and x.dtype == np.float32 and not self._t_f64:
+            logl = logl.astype(np.float32)
+        return logl, np.empty((x.shape[0], 0))
+
+    def prior(self, x):
+        """safe_prior (nnest/sampler.py:143-163): 0 inside the box, -inf outside."""
+        x, xd = self._to_device_rows(x)
+        if self._prior_obj is None:
+            return np.array([0 for _ in x])
+        _, logp = self.engine.loglike(xd, want_prior=True)
+        return logp.cpu().numpy()
+
+    def _save_params(self, my_dict):
+        my_dict = {k: str(v) for k, v in my_dict.items()}
+        with open(os.path.join(self.logs['info'], 'params.txt'), 'w') as f:
+            json.dump(my_dict, f, indent=4)
+
+    # ---- the hot path -----------------------------------------------------------------------------
+    def _start_chains(self, num_chains, init_samples, init_loglikes, max_start_tries):
+        """Chain start (nnest/sampler.py:262-284) on the device.  Returns (ChainState, ncall)."""
+        offset = self.mpi_rank * num_chains
+        if init_samples is not None:
+            u = torch.from_numpy(np.ascontiguousarray(np.asarray(init_samples, dtype=np.float32))).to(self.device)
+            logl = None
+            if init_loglikes is not None:
+                logl = torch.from_numpy(np.ascontiguousarray(np.asarray(init_loglikes, dtype=np.float64))
+                                        ).to(self.device)
+            st, nbad, ncall = self.engine.mcmc_init(u.shape[0], init_u=u.t().contiguous(), init_logl=logl,
+                                                    seed=self.seed, chain_offset=offset)
+            return st, ncall
+        ncall = 0
+        for i in range(max_start_tries):
+            self._start_counter += 1
+            st, nbad, nc = self.engine.mcmc_init(num_chains, seed=self.seed, chain_offset=offset,
+                                                 start_try=self._start_counter)
+            ncall += nc
+            if nbad == 0:
+                return st, ncall
+        raise Exception('Could not find starting value')
+
+    def _mcmc_device(self, mcmc_steps, step_size, dynamic_step_size, num_chains, init_samples, init_loglikes,
+                     loglstar, max_start_tries, trace):
+        """Runs the fused kernels; returns (state, result dict, ncall)."""
+        if step_size <= 0.0:
+            step_size = 2 / self.x_dim ** 0.5
+        st, ncall = self._start_chains(num_chains, init_samples, init_loglikes, max_start_tries)
+        self.total_calls += ncall
+        mode = L.NNB_MODE_MH if loglstar is None else L.NNB_MODE_HARD
+        first_x = st.x.clone()
+        out = self.engine.mcmc_run(st, mcmc_steps, mode=mode, loglstar=loglstar, step_size=step_size,
+                                   dynamic_step_size=dynamic_step_size, seed=self.seed,
+                                   chain_offset=self.mpi_rank * st.n, step_offset=self._step_counter, trace=trace)
+        self._step_counter += mcmc_steps
+        n = st.n
+        self.total_calls += out['ncall']
+        self.total_accepted += out['naccept']
+        self.total_rejected += n * mcmc_steps - out['naccept']
+        out['first_x'] = first_x
+        return st, out, ncall + out['ncall']
+
+    def _mcmc_sample(
+            self,
+            mcmc_steps,
+            step_size=0.0,
+            dynamic_step_size=False,
+            num_chains=1,
+            init_samples=None,
+            init_loglikes=None,
+            init_derived=None,
+            loglstar=None,
+            show_progress=False,
+            max_start_tries=100,
+            output_interval=None,
+            stats_interval=None,
+            plot_trace=True,
+            prior_volume_steps=1):
+        """Same contract as the reference (nnest/sampler.py:229-463): returns
+        (samples (N,S+1,d) f32, latent_samples (N,S+1,d) f32, derived (N,S+1,0), loglikes (N,S+1) f64, scale, ncall).
+        The arrays are host views of the chain-minor device trace (no extra transposition pass)."""
+        if prior_volume_steps != 1:
+            raise NotImplementedError('prior_volume_steps != 1')
+        st, out, ncall = self._mcmc_device(mcmc_steps, step_size, dynamic_step_size, num_chains, init_samples,
+                                           init_loglikes, loglstar, max_start_tries, trace=True)
+        samples = out['trace_x'].cpu().numpy().transpose(2, 0, 1)        # (S+1, d, N) -> (N, S+1, d) view
+        latent_samples = out['trace_z'].cpu().numpy().transpose(2, 0, 1)
+        loglikes = out['trace_logl'].cpu().numpy().transpose(1, 0)
+        derived_samples = np.empty((st.n, mcmc_steps + 1, 0))
+        for it in range(1, mcmc_steps + 1):
+            if output_interval is not None and it % output_interval == 0:
+                self._save_samples(self.transform(samples[:, :it + 1].reshape(-1, self.x_dim)).reshape(
+                    st.n, it + 1, self.x_dim), loglikes[:, :it + 1])
+            if stats_interval is not None and it % stats_interval == 0:
+                self._chain_stats(self.transform(samples[:, :it + 1].reshape(-1, self.x_dim)).reshape(
+                    st.n, it + 1, self.x_dim), step=it)
+        return samples, latent_samples, derived_samples, loglikes, out['scale'], ncall
+
+    def _mcmc_refill(self, mcmc_steps, init_samples, init_loglikes, loglstar, step_size, dynamic_step_size,
+                     keep_trace=False):
+        """What NestedSampler.run needs from a batch (nested.py:429-439): start point, end point and end
+        loglike of every chain, on the host; the trace stays on the device (optional, for chain statistics)."""
+        st, out, ncall = self._mcmc_device(mcmc_steps, step_size, dynamic_step_size, init_samples.shape[0],
+                                           init_samples, init_loglikes, loglstar, 0, trace=keep_trace)
+        first = out['first_x'].t().contiguous()
+        last = st.x.t().contiguous()
+        return dict(first=first, last=last, logl_last=st.logl, scale=out['scale'], ncall=ncall,
+                    trace_x=out.get('trace_x'))
+
+    def _plot_trace(self, samples, latent_samples):
+        pass    # plotting is outside the accelerated path
+
+    def _chain_stats(self, samples, mean=None, std=None, step=None):
+        """Acceptance, ESS and jump distance with the reference's definitions (sampler.py:474-492); `samples` may be
+        a numpy array or a device tensor of shape (chains, steps, dim)."""
+        acceptance = acceptance_rate(samples)
+        flat = samples.reshape(-1, samples.shape[2])
+        if mean is None:
+            mean = flat.mean(0) if isinstance(flat, np.ndarray) else flat.double().mean(0).cpu().numpy()
+        if std is None:
+            std = flat.std(0) if isinstance(flat, np.ndarray) else flat.double().std(0, unbiased=False).cpu().numpy()
+        ess = effective_sample_size(samples, mean, std)
+        jump_distance = mean_jump_distance(samples)
+        if step is None:
+            self.logger.info('Acceptance [%5.4f] min ESS [%5.4f] max ESS [%5.4f] average jump [%5.4f]' %
+                             (acceptance, np.min(ess), np.max(ess), jump_distance))
+        else:
+            self.logger.info('Step [%d] acceptance [%5.4f] min ESS [%5.4f] max ESS [%5.4f] average jump [%5.4f]' %
+                             (step, acceptance, np.min(ess), np.max(ess), jump_distance))
+        return acceptance, ess, jump_distance
+
+    def _save_samples(self, samples, loglikes, weights=None, derived_samples=None, min_weight=1e-30,
+                      outfile='chain'):
+        """Chain files in the reference's text format (sampler.py:494-527): weight, -loglike, parameters,
+        every number '%.5E'."""
+        if weights is None:
+            weights = np.ones_like(loglikes)
+
+        def write(path, smp, lgl, wts, der):
+            cols = [np.maximum(wts, min_weight)[:, None], -np.asarray(lgl)[:, None], smp]
+            if der is not None:
+                cols.append(der)
+            table = np.concatenate([np.asarray(c, dtype=np.float64) for c in cols], axis=1)
+            with open(path, 'w') as f:
+                if self.param_names is not None:
+                    f.write('#weight minusloglike ' + ' '.join(self.param_names) + '\n')
+                for row in table:
+                    f.write(' '.join('%.5E' % v for v in row) + '\n')
+
+        if len(samples.shape) == 2:
+            write(os.path.join(self.logs['chains'], outfile + '.txt'), samples, loglikes, weights, derived_samples)
+        elif len(samples.shape) == 3:
+            for ib in range(samples.shape[0]):
+                write(os.path.join(self.logs['chains'], outfile + '_%s.txt' % (ib + 1)), samples[ib], loglikes[ib],
+                      weights[ib], None if derived_samples is None else derived_samples[ib])
+
+    # ---- rejection samplers used before the switch to MCMC (nnest/sampler.py:529-543) -------------------
+    def _rejection_prior_sample(self, loglstar, num_trials=None):
+        if num_trials is None:
+            ncall = 0
+            while True:
+                x = self.sample_prior(1)
+                logl, derived = self.loglike(x)
+                ncall += 1
+                if logl > loglstar:
+                    break
+        else:
+            x = self.sample_prior(num_trials)
+            logl, derived = self.loglike(x)
+            ncall = num_trials / np.sum(logl > loglstar)
+        return x, logl, derived, ncall

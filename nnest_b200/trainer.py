@@ -1,0 +1,243 @@
+"""Flow facade + fitting with the reference's Trainer interface (nnest/trainer.py:28-301).
+
+The facade methods the MCMC loop calls -- forward / inverse / get_samples / get_latent_samples /
+get_prior_samples / get_synthetic_samples / log_probs (trainer.py:247-301) -- run on the hand-written
+CUDA flow kernels through the C ABI (nnb_flow_forward / nnb_flow_inverse); there is no ATen path for
+them.  Fitting (train / _train / _validate, trainer.py:134-245,384-418) keeps the reference's procedure
+(k-d tree jitter, 90/10 split, Adam, early stopping with patience, best-model restore, netG.pt /
+originals.npy / tensorboard artefacts) on PyTorch autograd; after every change of the weights they are
+re-exported to the device (`_sync_device`), and broadcast to all ranks when running multi-GPU.
+
+Only flow='nvp' with num_slow=0 is implemented on the device (the hot path north_star
+names); other flows raise NotImplementedError.
+"""
+import copy
+import logging
+import math
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import dist
+from .engine import Engine
+from .networks import SingleSpeedNVP
+from .utils.logger import create_logger
+
+
+class Trainer(object):
+    best_validation_epoch = None
+    best_validation_loss = None
+
+    def __init__(self,
+                 x_dim,
+                 hidden_dim=16,
+                 num_slow=0,
+                 batch_size=100,
+                 flow='spline',
+                 scale='',
+                 num_blocks=3,
+                 num_layers=1,
+                 base_dist=None,
+                 load_model='',
+                 log_dir='logs/test',
+                 use_gpu=True,
+                 log=True,
+                 learning_rate=0.0001,
+                 weight_decay=1e-6,
+                 log_level=logging.INFO,
+                 engine=None):
+        if flow.lower() != 'nvp':
+            raise NotImplementedError("nnest_b200 accelerates flow='nvp' (RealNVP); got flow=%r" % flow)
+        if num_slow != 0:
+            raise NotImplementedError('fast/slow flows (num_slow > 0) are not on the accelerated path')
+        if base_dist is not None:
+            raise NotImplementedError('only the default N(0, I) base distribution is supported')
+        if not torch.cuda.is_available():
+            raise RuntimeError('nnest_b200 needs a CUDA device (B200); there is no CPU fallback')
+
+        self.engine = engine if engine is not None else Engine()
+        self.device = self.engine.device
+        self.x_dim = x_dim
+        self.z_dim = x_dim
+        self.batch_size = batch_size
+        self.total_iters = 0
+        self.num_slow = 0
+        self.scale = scale
+
+        self.netG = SingleSpeedNVP(x_dim, hidden_dim, num_blocks, num_layers, scale=scale, device=self.device)
+
+        if load_model:
+            self.path = os.path.join(log_dir, load_model)
+            self.netG.load_state_dict(torch.load(os.path.join(self.path, 'models', 'netG.pt'),
+                                                 map_location=self.device))
+        elif log_dir is not None:
+            self.path = log_dir
+            for sub in ('models', 'data', 'chains', 'plots'):
+                os.makedirs(os.path.join(self.path, sub), exist_ok=True)
+        else:
+            self.path = None
+
+        self.optimizer = torch.optim.Adam(self.netG.parameters(), lr=learning_rate, weight_decay=weight_decay)
+        self.logger = create_logger(__name__, level=log_level)
+        self.log = log
+        self.writer = None
+        if self.path is not None:
+            from torch.utils.tensorboard import SummaryWriter
+            self.logger.info(self.netG)
+            self.writer = SummaryWriter(self.path)
+        self.logger.info('Number of network params: [%s]' % sum(p.numel() for p in self.netG.parameters()))
+        self.logger.info('Device [%s]' % self.device)
+        self._sync_device()
+
+    # ------------------------------------------------------------------------------------------
+    def _sync_device(self, broadcast=True):
+        """Export the current weights to the CUDA kernels (and to every rank, rank 0's weights win)."""
+        if broadcast:
+            dist.broadcast_parameters(self.netG, src=0)       # NCCL over NVLink, one flat buffer
+        self.engine.set_flow_from_state_dict(self.netG.state_dict(), scale=self.scale)
+
+    def load_state_dict(self, sd):
+        self.netG.load_state_dict(sd)
+        self._sync_device()
+
+    # ------------------------------------------------------------------------------------------
+    def train(self,
+              samples,
+              max_iters=10000,
+              log_interval=100,
+              save_interval=100,
+              jitter=0.0,
+              validation_fraction=0.1,
+              patience=50,
+              l2_norm=0.0):
+        start_time = time.time()
+        samples = np.asarray(samples)
+
+        if self.path:
+            np.save(os.path.join(self.path, 'data', 'originals.npy'), samples)
+
+        if jitter < 0:
+            import scipy.spatial
+            dists, _ = scipy.spatial.cKDTree(samples).query(samples, 2)
+            training_jitter = .2 * np.mean(dists)
+        else:
+            training_jitter = jitter
+
+        if self.log:
+            self.logger.info('Number of training samples [%d]' % samples.shape[0])
+            self.logger.info('Training jitter [%5.4f]' % training_jitter)
+
+        n = samples.shape[0]
+        n_valid = int(math.ceil(validation_fraction * n))      # sklearn train_test_split rounding
+        perm = np.random.permutation(n)
+        x_valid = torch.from_numpy(samples[perm[:n_valid]].astype(np.float32)).to(self.device)
+        x_train = torch.from_numpy(samples[perm[n_valid:]].astype(np.float32)).to(self.device)
+
+        best_validation_loss = float('inf')
+        best_validation_epoch = 0
+        best_state = copy.deepcopy(self.netG.state_dict())
+        counter = 0
+
+        for epoch in range(1, max_iters + 1):
+            self.total_iters += 1
+            train_loss = self._train(epoch, x_train, jitter=training_jitter, l2_norm=l2_norm)
+            validation_loss = self._validate(epoch, x_valid)
+
+            if validation_loss < best_validation_loss:
+                best_validation_epoch = epoch
+                best_validation_loss = validation_loss
+                best_state = copy.deepcopy(self.netG.state_dict())
+                counter = 0
+
+            if epoch == 1 or epoch % log_interval == 0:
+                self.logger.info('Epoch [%i] train loss [%5.4f] validation loss [%5.4f]' % (
+                    epoch, train_loss, validation_loss))
+
+            if self.path:
+                self.writer.add_scalar('loss', validation_loss, self.total_iters)
+                if epoch % save_interval == 0:
+                    torch.save(self.netG.state_dict(), os.path.join(self.path, 'models', 'netG.pt'))
+
+            counter += 1
+            if counter > patience:
+                self.logger.info('Epoch [%i] ran out of patience' % (epoch))
+                if self.path:
+                    torch.save(self.netG.state_dict(), os.path.join(self.path, 'models', 'netG.pt'))
+                break
+
+        self.logger.info('Best epoch [%i] validation loss [%5.4f] train time (s) [%5.4f]]'
+                         % (best_validation_epoch, best_validation_loss, time.time() - start_time))
+        self.best_validation_epoch = best_validation_epoch
+        self.best_validation_loss = best_validation_loss
+        self.netG.load_state_dict(best_state)
+        self._sync_device()
+
+    def _train(self, epoch, x_train, jitter=0.0, l2_norm=0.0):
+        self.netG.train()
+        n = x_train.shape[0]
+        order = torch.randperm(n, device=x_train.device)
+        total = 0.0
+        for s in range(0, n, self.batch_size):
+            data = x_train[order[s:s + self.batch_size]]
+            data = data + jitter * torch.randn_like(data)
+            self.optimizer.zero_grad(set_to_none=True)
+            loss = -self.netG.log_probs(data).mean()
+            total += loss.item()
+            if l2_norm:
+                loss = loss + l2_norm * sum((p ** 2).sum() for p in self.netG.parameters())
+            loss.backward()
+            self.optimizer.step()
+        return total / n      # the reference divides by the dataset size (trainer.py:403)
+
+    def _validate(self, epoch, x_valid):
+        self.netG.eval()
+        if x_valid.shape[0] == 0:
+            return 0.0
+        with torch.no_grad():
+            val = -self.netG.log_probs(x_valid).mean().item()
+        return val / x_valid.shape[0]     # trainer.py:418
+
+    # ------------------------------------------------------------------------------------------
+    def _as_device(self, a):
+        if isinstance(a, np.ndarray):
+            return torch.from_numpy(a).float().to(self.device)
+        return a.to(self.device, dtype=torch.float32)
+
+    def forward(self, x, to_numpy=False):
+        z, log_det_J = self.engine.flow_forward(self._as_device(x))
+        if to_numpy:
+            return z.cpu().numpy(), log_det_J.cpu().numpy()
+        return z, log_det_J
+
+    def inverse(self, z, to_numpy=False):
+        x, log_det_J = self.engine.flow_inverse(self._as_device(z))
+        if to_numpy:
+            return x.cpu().numpy(), log_det_J.cpu().numpy()
+        return x, log_det_J
+
+    def get_prior_samples(self, num_samples, to_numpy=False):
+        z = torch.randn((num_samples, self.x_dim), device=self.device)
+        return z.cpu().numpy() if to_numpy else z
+
+    def get_latent_samples(self, x, to_numpy=False):
+        return self.forward(x, to_numpy=to_numpy)[0]
+
+    def get_samples(self, z, to_numpy=False):
+        return self.inverse(z, to_numpy=to_numpy)[0]
+
+    def get_synthetic_samples(self, num_samples, to_numpy=False):
+        return self.get_samples(self.get_prior_samples(num_samples), to_numpy=to_numpy)
+
+    def log_probs(self, x, to_numpy=False):
+        z, log_det_J = self.forward(x)
+        lp = -0.5 * (z * z).sum(-1) - 0.5 * self.x_dim * math.log(2 * math.pi) + log_det_J
+        return lp.cpu().numpy() if to_numpy else lp
+
+    def plot_samples(self, samples, outfile=None, plot_synthetic=True):
+        """Plotting is outside the accelerated path (matplotlib is optional)."""
+        try:
+            import matplotlib  # noqa: F401
+        except ImportError:
+            return

@@ -42,7 +42,7 @@ def _box_muller(ra, rb):
     u1 = ((ra >> np.uint32(8)).astype(np.float32) + np.float32(1.0)) * TWO_M24       # (0, 1]
     u2 = (rb >> np.uint32(8)).astype(np.float32) * TWO_M24                            # [0, 1)
     rad = np.sqrt(np.float32(-2.0) * np.log(u1)).astype(np.float32)
-    ang = (np.float32(6.283185307179586) * u2).astype(np.float32)
+    ang = ((u2 - np.float32(0.5)) * np.float32(6.283185307179586)).astype(np.float32)      # [-pi, pi)
     return (rad * np.cos(ang)).astype(np.float32), (rad * np.sin(ang)).astype(np.float32)
 
 

@@ -1,0 +1,196 @@
+"""GPU tests of the reference-facing Python API (NestedSampler / MCMCSampler / Trainer mirrors): drop-in
+behaviour, bit-exact bookkeeping against the oracle, on-disk layout, and the reference's own evidence test."""
+import csv
+import json
+import logging
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+from oracle import flow as oflow
+from oracle import nested as onested
+from helpers import load, state_dict_of, weights_of, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_trainer_facade_matches_reference_flow(tmp_path):
+    """Trainer.forward/inverse/log_probs (trainer.py:247-301) through the CUDA kernels vs golden reference outputs,
+    and the properties of tests/test_flows.py:56-72."""
+    from nnest_b200 import Trainer
+    g = load('flow_d5.npz')
+    t = Trainer(5, flow='nvp', log_dir=str(tmp_path), log_level=logging.WARNING)
+    t.load_state_dict({k: torch.from_numpy(v) for k, v in state_dict_of(g).items()})
+    z, ld = t.forward(g['x'])
+    assert z.shape == torch.Size([64, 5]) and ld.shape == torch.Size([64]) and z.is_cuda
+    assert rel_err(z.cpu().numpy(), g['fwd_z']) < 1e-5
+    x, ldx = t.inverse(z)
+    assert np.abs(x.cpu().numpy() - g['x']).max() <= 1e-5
+    assert np.abs((ld + ldx).cpu().numpy()).max() <= 1e-5
+    xn, ldn = t.inverse(g['zin'], to_numpy=True)
+    assert isinstance(xn, np.ndarray) and rel_err(xn, g['inv_x']) < 1e-5
+    assert t.get_synthetic_samples(10).shape == torch.Size([10, 5])
+    lp = t.log_probs(g['x'], to_numpy=True)
+    zz, ll = oflow.flow_forward(weights_of(g), g['x'])
+    ref = -0.5 * (zz.astype(np.float64) ** 2).sum(-1) - 2.5 * np.log(2 * np.pi) + ll
+    assert np.allclose(lp, ref, rtol=1e-5, atol=1e-5)
+    # device kernels and the autograd module hold the same weights
+    zt, ldt = t.netG.forward(torch.from_numpy(g['x']).cuda())
+    assert rel_err(zt.detach().cpu().numpy(), g['fwd_z']) < 1e-5
+
+
+def test_training_reduces_loss_and_updates_device_weights(tmp_path):
+    from nnest_b200 import Trainer
+    torch.manual_seed(0)
+    np.random.seed(0)
+    t = Trainer(2, flow='nvp', log_dir=str(tmp_path), learning_rate=0.001, log_level=logging.WARNING)
+    x = np.random.normal(size=(600, 2)) * np.array([0.2, 0.05]) + np.array([0.3, -0.2])
+    before = -t.log_probs(x.astype(np.float32)).mean().item()
+    t.train(x, max_iters=60, jitter=-1.0)
+    after = -t.log_probs(x.astype(np.float32)).mean().item()
+    assert after < before - 0.5
+    assert os.path.exists(os.path.join(str(tmp_path), 'data', 'originals.npy'))
+    # kernels see the trained weights: device log_probs == autograd log_probs
+    with torch.no_grad():
+        ref = t.netG.log_probs(torch.from_numpy(x.astype(np.float32)).cuda()).cpu().numpy()
+    assert np.allclose(t.log_probs(x.astype(np.float32), to_numpy=True), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_mcmc_sample_contract(tmp_path):
+    """_mcmc_sample keeps the reference's signature and return contract (sampler.py:229-244,454-463)."""
+    from nnest_b200 import NestedSampler
+    from nnest_b200.likelihoods import Rosenbrock
+    s = NestedSampler(2, Rosenbrock(2), transform=lambda x: 5 * x, flow='nvp', num_live_points=100,
+                      log_dir=str(tmp_path), log_level=logging.WARNING)
+    u = s.sample_prior(64)
+    logl, der = s.loglike(u)
+    assert logl.shape == (64,) and der.shape == (64, 0) and s.total_calls == 64
+    out = s._mcmc_sample(7, init_samples=u, init_loglikes=logl, init_derived=der, loglstar=np.median(logl),
+                         step_size=0.5, dynamic_step_size=True)
+    samples, latent, derived, loglikes, scale, ncall = out
+    assert samples.shape == (64, 8, 2) and samples.dtype == np.float32
+    assert latent.shape == (64, 8, 2) and derived.shape == (64, 8, 0)
+    assert loglikes.shape == (64, 8) and loglikes.dtype == np.float64
+    assert np.abs(samples[:, 0] - u).max() < 1e-5            # start row = inverse(forward(u))
+    assert np.array_equal(loglikes[:, 0], logl)
+    moved = np.any(samples[:, 1:] != samples[:, :-1], axis=2)
+    assert (loglikes[:, 1:][moved] > np.median(logl)).all()     # hard constraint on every accepted move
+    assert s.total_accepted == moved.sum() and s.total_accepted + s.total_rejected == 64 * 7
+    assert s.total_calls == 64 + ncall
+    # python callables cannot be dropped in: no CPU fallback
+    with pytest.raises(NotImplementedError):
+        NestedSampler(2, lambda x: -np.sum(x ** 2, axis=1), flow='nvp', log_dir=str(tmp_path))
+    with pytest.raises(NotImplementedError):
+        NestedSampler(2, Rosenbrock(2), transform=lambda x: x ** 3, flow='nvp', log_dir=str(tmp_path))
+
+
+def test_nested_run_bookkeeping_bit_exact_and_layout(tmp_path):
+    """A full NestedSampler.run; every MCMC batch it consumed is recorded and replayed through the CPU oracle of
+    nested.py:269-500: evidence, information, posterior samples/weights must agree bit for bit."""
+    from nnest_b200 import NestedSampler
+    from nnest_b200.likelihoods import Rosenbrock
+    np.random.seed(3)
+    torch.manual_seed(3)
+    tr = lambda x: 5 * x
+    s = NestedSampler(2, Rosenbrock(2), transform=tr, flow='nvp', num_live_points=200, log_dir=str(tmp_path),
+                      log_level=logging.WARNING, seed=5)
+    rec = {'batches': [], 'idx': []}
+    orig_refill = s._mcmc_refill
+    orig_prior = s.sample_prior
+    orig_randint = np.random.randint
+
+    def refill(mcmc_steps, init_samples, init_loglikes, loglstar, *a, **k):
+        b = orig_refill(mcmc_steps, init_samples, init_loglikes, loglstar, *a, **k)
+        rec['batches'].append((b['first'].cpu().numpy(), b['last'].cpu().numpy(), b['logl_last'].cpu().numpy(),
+                               loglstar))
+        return b
+
+    def prior_sample(n):
+        rec['u0'] = orig_prior(n)
+        return rec['u0']
+
+    s._mcmc_refill = refill
+    s.sample_prior = prior_sample
+    s.run(strategy=['mcmc'], mcmc_num_chains=64, mcmc_steps=10, train_iters=30, mcmc_dynamic_step_size=True)
+
+    it_b = iter(rec['batches'])
+    cur = {}
+
+    def randint(n, size):
+        cur['b'] = next(it_b)
+        return np.zeros(size, dtype=np.int64)
+
+    def batch_fn(init_samples, init_loglikes, loglstar):
+        first, last, logl, lstar = cur['b']
+        assert loglstar == lstar
+        return np.stack([first, last], axis=1), np.stack([np.zeros_like(logl), logl], axis=1)
+
+    logl0 = s._like(tr(rec['u0']))                         # float64 live-point likelihoods (device kernel)
+    st, au, av, al, trace = onested.run_mcmc_strategy(rec['u0'], logl0, tr, batch_fn, mcmc_num_chains=64,
+                                                      randint=randint)
+    logz, h, samples, weights, loglikes, logzerr = onested.finalize(st, av, al)
+    assert s.logz == logz and s.h == h and s.niter == st.it + 1
+    assert np.array_equal(s.samples, samples) and np.array_equal(s.weights, weights)
+    assert np.array_equal(s.loglikes, loglikes)
+    # analytic evidence of Rosenbrock-2D on [-5,5]^2 is -5.804
+    assert abs(s.logz + 5.804) < 0.35 + 3 * s.logzerr
+
+    # on-disk layout (sampler.py:182-190,494-511 ; nested.py:92-95,249-260,473-485,503-507)
+    run_dir = s.log_dir
+    for sub in ('info', 'results', 'chains', 'checkpoint', 'plots', 'models', 'data'):
+        assert os.path.isdir(os.path.join(run_dir, sub)), sub
+    params = json.load(open(os.path.join(run_dir, 'info', 'params.txt')))
+    assert params['x_dim'] == '2' and all(isinstance(v, str) for v in params.values())
+    rows = list(csv.reader(open(os.path.join(run_dir, 'results', 'final.csv'))))
+    assert rows[0] == ['niter', 'ncall', 'logz', 'logzerr', 'h'] and float(rows[1][2]) == s.logz
+    hdr = next(csv.reader(open(os.path.join(run_dir, 'results', 'results.csv'))))
+    assert hdr == ['step', 'acceptance', 'min_ess', 'max_ess', 'jump_distance', 'scale', 'loglstar', 'logz',
+                   'fraction_remain', 'ncall']
+    lines = open(os.path.join(run_dir, 'chains', 'chain.txt')).read().splitlines()
+    assert len(lines) == s.samples.shape[0]
+    first = lines[0].split(' ')
+    assert len(first) == 4 and all(len(tok.split('E')) == 2 and len(tok.split('E')[0].lstrip('-')) == 7 for tok in first)
+    assert float(first[1]) == float('%.5E' % -s.loglikes[0])
+    assert os.path.exists(os.path.join(run_dir, 'checkpoint', 'checkpoint_0.txt'))
+    ck = json.load(open(os.path.join(run_dir, 'checkpoint', 'checkpoint_0.txt')))
+    assert sorted(ck) == ['expired_strategies', 'fraction_remain', 'h', 'logvol', 'logz', 'ncall', 'strategy']
+
+
+def test_reference_evidence_test_rosenbrock(tmp_path):
+    """The reference's only integration test (tests/test_nested.py:10-19): Rosenbrock-2D, 1000 live points,
+    |logz + 5.80| <= 0.2 -- here with flow='nvp' (the accelerated flow), default strategy, 1000 GPU chains."""
+    from nnest_b200 import NestedSampler
+    from nnest_b200.likelihoods import Rosenbrock
+    np.random.seed(0)
+    torch.manual_seed(0)
+    sampler = NestedSampler(2, Rosenbrock(2), transform=lambda x: 5 * x, num_live_points=1000, hidden_dim=16,
+                            num_layers=1, num_blocks=3, num_slow=0, flow='nvp', log_dir=str(tmp_path),
+                            log_level=logging.WARNING)
+    sampler.run(mcmc_num_chains=1000, mcmc_dynamic_step_size=False, train_iters=200)
+    assert np.abs(sampler.logz + 5.80) <= 0.2 + 2 * sampler.logzerr
+
+
+def test_mcmc_sampler_gaussian_posterior(tmp_path):
+    """MCMCSampler.run (mcmc.py:79-126) on a correlated Gaussian: chains reproduce the target moments."""
+    from nnest_b200 import MCMCSampler
+    from nnest_b200.likelihoods import Gaussian
+    from nnest_b200.priors import UniformPrior
+    np.random.seed(1)
+    torch.manual_seed(1)
+    d, rho = 4, 0.5
+    cov = np.eye(d) + rho * (1 - np.eye(d))
+    training = np.random.multivariate_normal(np.zeros(d), cov, size=2000)
+    s = MCMCSampler(d, Gaussian(d, rho), prior=UniformPrior(d, -8, 8), flow='nvp', log_dir=str(tmp_path),
+                    log_level=logging.WARNING)
+    s.run(300, 512, training, stats_interval=None, train_iters=150)
+    assert s.samples.shape == (512, 301, d) and s.latent_samples.shape == (512, 301, d)
+    assert s.loglikes.shape == (512, 301)
+    tail = s.samples[:, 100:, :].reshape(-1, d)
+    assert np.abs(tail.mean(0)).max() < 0.1
+    assert np.abs(np.cov(tail.T) - cov).max() < 0.15
+    # the recorded loglikes are the float64 likelihood of the recorded (transformed) samples
+    chk = s._like(s.samples[:4, -1, :].astype(np.float64))
+    assert np.allclose(chk, s.loglikes[:4, -1], rtol=1e-5, atol=1e-5)
