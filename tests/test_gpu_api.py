@@ -109,8 +109,9 @@ def test_nested_run_bookkeeping_bit_exact_and_layout(tmp_path):
         return b
 
     def prior_sample(n):
-        rec['u0'] = orig_prior(n)
-        return rec['u0']
+        u = orig_prior(n)
+        rec['u0'] = u.copy()          # run() updates the live set in place
+        return u
 
     s._mcmc_refill = refill
     s.sample_prior = prior_sample

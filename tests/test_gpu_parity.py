@@ -141,7 +141,7 @@ def test_philox_stream_matches_oracle(engine):
         nrm = ophilox.normals(99, 7 + s + 1, 1000 + np.arange(n), d)
         uni = ophilox.uniforms(99, 7 + s + 1, 1000 + np.arange(n))
         assert np.array_equal(out['uniforms'][s].cpu().numpy(), uni)          # integer path: bit exact
-        assert np.abs(out['normals'][s].cpu().numpy() - nrm).max() < 2e-6      # log/sin/cos: few ulp
+        assert np.abs(out['normals'][s].cpu().numpy() - nrm).max() < 1e-5      # __logf/__sincosf: abs err 2^-21.4 x radius
 
 
 HARD = {
