@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 1
+#define NNB_ABI_VERSION 2
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -58,6 +58,9 @@ enum {
 
 enum { NNB_PRIOR_NONE = 0, NNB_PRIOR_BOX_U = 1, NNB_PRIOR_BOX_V = 2 };
 enum { NNB_MODE_HARD = 0, NNB_MODE_MH = 1 };
+/* kernel variant of nnb_mcmc_run: AUTO picks the tcgen05 (tensor-core, 3xTF32) kernel when the flow shape allows
+ * it (hidden_dim == 16, 2 <= x_dim <= 63, scale == ''), else the FP32-FMA kernel */
+enum { NNB_IMPL_AUTO = 0, NNB_IMPL_FFMA = 1, NNB_IMPL_TCGEN05 = 2 };
 
 typedef struct nnb_handle nnb_handle;
 
@@ -192,6 +195,7 @@ typedef struct {
   double* scale_out;     /* final scale (sampler.py:463) */
   int64_t* ncall_out;    /* likelihood calls (sampler.py:363,397) */
   int64_t* naccept_out;  /* accepted proposals (total_accepted, sampler.py:418-420) */
+  int impl;              /* NNB_IMPL_* */
 } nnb_mcmc_args;
 
 int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream); /* synchronous at return */

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libnnb.so')
 
-NNB_ABI_VERSION = 1
+NNB_ABI_VERSION = 2
 NNB_MAX_DIM = 128
 NNB_MAX_BLOCKS = 16
 
@@ -19,6 +19,7 @@ NNB_FLOW_TRANSLATE_ONLY, NNB_FLOW_CONST_SCALE = 1, 2
  NNB_LIKE_GAUSSIAN_SHELL) = range(6)
 NNB_PRIOR_NONE, NNB_PRIOR_BOX_U, NNB_PRIOR_BOX_V = 0, 1, 2
 NNB_MODE_HARD, NNB_MODE_MH = 0, 1
+NNB_IMPL_AUTO, NNB_IMPL_FFMA, NNB_IMPL_TCGEN05 = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -44,7 +45,8 @@ class nnb_mcmc_args(C.Structure):
                 ('z', C.c_void_p), ('x', C.c_void_p), ('logl', C.c_void_p), ('logdet', C.c_void_p),
                 ('logp', C.c_void_p), ('trace_x', C.c_void_p), ('trace_z', C.c_void_p), ('trace_logl', C.c_void_p),
                 ('replay_normals', C.c_void_p), ('replay_uniforms', C.c_void_p), ('dump_normals', C.c_void_p),
-                ('dump_uniforms', C.c_void_p), ('scale_out', _dp), ('ncall_out', _ip), ('naccept_out', _ip)]
+                ('dump_uniforms', C.c_void_p), ('scale_out', _dp), ('ncall_out', _ip), ('naccept_out', _ip),
+                ('impl', C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/nnb.h declares

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 OBJDIR = os.path.join(LIBDIR, 'obj')
 LIB = os.path.join(LIBDIR, 'libnnb.so')
-UNITS = ['nnb_api.cu', 'nnb_h16.cu', 'nnb_h32.cu', 'nnb_h64.cu']
+UNITS = ['nnb_api.cu', 'nnb_tc.cu', 'nnb_h16.cu', 'nnb_h32.cu', 'nnb_h64.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 NVCC_FLAGS = ARCH + ['-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
@@ -28,21 +28,40 @@ def _nvcc():
     return exe
 
 
-def _sources():
-    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    out.append(os.path.join(HERE, '..', 'include', 'nnb.h'))
-    return out
+def _deps(path, seen=None):
+    """The file plus every local header it (transitively) includes."""
+    import re
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    for inc in re.findall(r'#include\s+"([^"]+)"', open(path).read()):
+        _deps(os.path.join(os.path.dirname(path), inc), seen)
+    return seen
+
+
+def _obj(unit):
+    return os.path.join(OBJDIR, unit.replace('.cu', '.o'))
+
+
+def _unit_stale(unit):
+    obj = _obj(unit)
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(d) > t for d in _deps(os.path.join(CSRC, unit)))
 
 
 def up_to_date():
     if not os.path.exists(LIB):
         return False
     t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(s) <= t for s in _sources())
+    return not any(_unit_stale(u) for u in UNITS) and all(os.path.getmtime(_obj(u)) <= t for u in UNITS)
 
 
 def _compile(unit):
-    obj = os.path.join(OBJDIR, unit.replace('.cu', '.o'))
+    obj = _obj(unit)
     cmd = [_nvcc()] + NVCC_FLAGS + ['-c', os.path.join(CSRC, unit), '-o', obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return unit, obj, r.returncode, r.stdout + r.stderr
@@ -52,21 +71,20 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
     os.makedirs(OBJDIR, exist_ok=True)
-    with concurrent.futures.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
-        results = list(ex.map(_compile, UNITS))
-    log = []
+    todo = [u for u in UNITS if force or _unit_stale(u)]
+    with concurrent.futures.ThreadPoolExecutor(max_workers=max(1, len(todo))) as ex:
+        results = list(ex.map(_compile, todo))
     for unit, obj, rc, out in results:
-        log.append('== %s ==\n%s' % (unit, out))
+        with open(os.path.join(LIBDIR, 'ptxas_%s.log' % unit.replace('.cu', '')), 'w') as f:
+            f.write(out)
         if rc != 0:
             raise RuntimeError('nvcc failed for %s:\n%s' % (unit, out))
-    with open(os.path.join(LIBDIR, 'ptxas.log'), 'w') as f:
-        f.write('\n'.join(log))
-    cmd = [_nvcc()] + ARCH + ['-shared', '-o', LIB] + [r[1] for r in results]
+        if verbose:
+            print('== %s ==\n%s' % (unit, out))
+    cmd = [_nvcc()] + ARCH + ['-shared', '-o', LIB] + [_obj(u) for u in UNITS]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
-    if verbose:
-        print('\n'.join(log))
     return LIB
 
 

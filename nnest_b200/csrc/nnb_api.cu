@@ -63,6 +63,7 @@ extern "C" void nnb_destroy(nnb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->d_weights) cudaFree(h->d_weights);
+  if (h->d_weights_tc) cudaFree(h->d_weights_tc);
   if (h->d_target) cudaFree(h->d_target);
   if (h->d_ctrl) cudaFree(h->d_ctrl);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -149,7 +150,7 @@ extern "C" int nnb_set_flow(nnb_handle* h, int d, int hidden, int num_layers, in
   NNB_CUDA(h, cudaMemcpy(h->d_weights, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
   h->flow = f;
   h->has_flow = true;
-  return NNB_OK;
+  return nnb_tc_pack(h, weights);
 }
 
 extern "C" int nnb_set_target(nnb_handle* h, int d, const nnb_target* t) {
@@ -191,6 +192,18 @@ extern "C" int nnb_set_target(nnb_handle* h, int d, const nnb_target* t) {
     ts[d + i] = t->t_shift ? t->t_shift[i] : 0.0;
     ts[2 * d + i] = t->prior_lo ? t->prior_lo[i] : -INFINITY;
     ts[3 * d + i] = t->prior_hi ? t->prior_hi[i] : INFINITY;
+  }
+  {  // float32 mirrors behind the doubles (see TargetSmem)
+    float* ff = reinterpret_cast<float*>(ts + 4 * d);
+    for (int i = 0; i < d; ++i) {
+      ff[i] = (float)ts[i];
+      ff[d + i] = (float)ts[d + i];
+      float lo = (float)ts[2 * d + i], hi = (float)ts[3 * d + i];
+      if ((double)lo < ts[2 * d + i]) lo = std::nextafterf(lo, INFINITY);     // smallest float >= lo
+      if ((double)hi > ts[3 * d + i]) hi = std::nextafterf(hi, -INFINITY);    // largest float <= hi
+      ff[2 * d + i] = lo;
+      ff[3 * d + i] = hi;
+    }
   }
   if (h->d_target) { cudaFree(h->d_target); h->d_target = nullptr; }
   NNB_CUDA(h, cudaMalloc(&h->d_target, buf.size() * sizeof(double)));
@@ -316,7 +329,14 @@ extern "C" int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream)
   p.replay_normals = a->replay_normals; p.replay_uniforms = a->replay_uniforms;
   p.dump_normals = a->dump_normals; p.dump_uniforms = a->dump_uniforms;
   p.ctrl = h->d_ctrl;
-  if (a->steps > 0) {
+  if (a->impl < NNB_IMPL_AUTO || a->impl > NNB_IMPL_TCGEN05) return fail(h, NNB_ERR_ARG, "impl");
+  if (a->impl == NNB_IMPL_TCGEN05 && !h->tc_ok)
+    return fail(h, NNB_ERR_UNSUPPORTED, "tcgen05 path needs hidden_dim == 16, 2 <= x_dim <= 63 and scale == ''");
+  const bool use_tc = h->tc_ok && a->impl != NNB_IMPL_FFMA;
+  if (a->steps > 0 && use_tc) {
+    rc = nnb_launch_mcmc_tc(h, p, a->steps, st);
+    if (rc) return rc;
+  } else if (a->steps > 0) {
     switch (h->flow.H) {
       case 16: rc = LaunchH<16>::mcmc(h, p, a->steps, st); break;
       case 32: rc = LaunchH<32>::mcmc(h, p, a->steps, st); break;

@@ -39,6 +39,13 @@ struct FlowDesc {
   float cscale[NNB_MAX_BLOCKS];    // ScaleLayer parameter (networks.py:312-325) when NNB_FLOW_CONST_SCALE
 };
 
+// Packed weights of the tensor-core variant (layout: nnb_tc_kernels.cuh)
+struct TcFlowDesc {
+  int d, L, B;
+  int total_floats;
+  int off[NNB_MAX_BLOCKS];   // float offset of block k in the packed TC buffer
+};
+
 __host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
 __host__ __device__ inline int blk_i0(int k) { return (k + 1) & 1; }
 __host__ __device__ inline int blk_o0(int k) { return k & 1; }
@@ -59,8 +66,27 @@ struct TargetSmem {
   const double* tb;      // [d] transform shift
   const double* lo;      // [d]
   const double* hi;      // [d]
+  // float32 mirrors (4*d floats stored behind the doubles): transform scale/shift rounded to float32 (what NumPy
+  // uses for float32 rows) and box bounds rounded so that (double)u < lo  <=>  u < lo_f and (double)u > hi  <=>  u > hi_f
+  const float* tsf;
+  const float* tbf;
+  const float* lof;
+  const float* hif;
 };
-__host__ __device__ inline int target_doubles(int d, int n_params) { return n_params + 4 * d; }
+__host__ __device__ inline int target_doubles(int d, int n_params) { return n_params + 4 * d + 2 * d; }
+
+__device__ __forceinline__ void target_bind(TargetSmem& tg, const TargetDesc& td, const double* td_s) {
+  tg.desc = td;
+  tg.params = td_s;
+  tg.ts = td_s + td.n_params;
+  tg.tb = tg.ts + td.d;
+  tg.lo = tg.tb + td.d;
+  tg.hi = tg.lo + td.d;
+  tg.tsf = reinterpret_cast<const float*>(tg.hi + td.d);
+  tg.tbf = tg.tsf + td.d;
+  tg.lof = tg.tbf + td.d;
+  tg.hif = tg.lof + td.d;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011).  Stream specification: oracle/philox.py.
@@ -86,7 +112,7 @@ __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& n0, 
   const float k2m24 = 1.0f / 16777216.0f;
   float u1 = __fmul_rn(__fadd_rn((float)(ra >> 8), 1.0f), k2m24);
   float u2 = __fmul_rn((float)(rb >> 8), k2m24);
-  float rad = sqrtf(__fmul_rn(-2.0f, __logf(u1)));
+  float rad = __fsqrt_rn(__fmul_rn(-2.0f, __logf(u1)));
   float ang = __fmul_rn(__fsub_rn(u2, 0.5f), 6.283185307179586f);
   float s, c;
   __sincosf(ang, &s, &c);
@@ -274,6 +300,7 @@ struct Transformed {
   __device__ __forceinline__ T operator()(int i) const {
     T u = (T)xg(i);
     if (!tg.desc.has_transform) return u;
+    if (sizeof(T) == 4) return Ar<T>::add(Ar<T>::mul(u, (T)tg.tsf[i]), (T)tg.tbf[i]);
     return Ar<T>::add(Ar<T>::mul(u, (T)tg.ts[i]), (T)tg.tb[i]);
   }
 };
@@ -403,9 +430,16 @@ __device__ __forceinline__ double prior_T(const TargetSmem& tg, const XG& xg) {
   if (tg.desc.prior_kind == NNB_PRIOR_NONE) return 0.0;
   bool bad = false;
   if (tg.desc.prior_kind == NNB_PRIOR_BOX_U) {
-    for (int i = 0; i < d; ++i) {
-      double u = (double)xg(i);
-      bad |= (u < tg.lo[i]) | (u > tg.hi[i]);
+    if (sizeof(xg(0)) == 4) {   // float32 point against pre-rounded float32 bounds: same truth value, no FP64
+      for (int i = 0; i < d; ++i) {
+        float u = (float)xg(i);
+        bad |= (u < tg.lof[i]) | (u > tg.hif[i]);
+      }
+    } else {
+      for (int i = 0; i < d; ++i) {
+        double u = (double)xg(i);
+        bad |= (u < tg.lo[i]) | (u > tg.hi[i]);
+      }
     }
   } else {
     Transformed<T, XG> v{tg, xg};
@@ -431,6 +465,8 @@ __device__ __forceinline__ double prior_any(const TargetSmem& tg, const XG& xg, 
 // ---------------------------------------------------------------------------------------------
 // CTA-wide helpers
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int block_count(bool pred) { return (unsigned int)__syncthreads_count(pred); }
+
 __device__ __forceinline__ unsigned int block_sum_u32(unsigned int v, unsigned int* red /* >= 32 words smem */) {
   v = __reduce_add_sync(0xffffffffu, v);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

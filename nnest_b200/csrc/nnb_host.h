@@ -15,12 +15,18 @@ struct nnb_handle {
   float* d_weights = nullptr;
   nnb::TargetDesc tdesc{};
   double* d_target = nullptr;
+  // tensor-core (tcgen05) variant of the MCMC kernel: weights pre-split hi/lo in the UMMA layout
+  bool tc_ok = false;
+  nnb::TcFlowDesc tcflow{};
+  float* d_weights_tc = nullptr;
   Ctrl* d_ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;  // pinned
   std::string err;
 };
 
 int nnb_fail(nnb_handle* h, int code, const std::string& msg);
+int nnb_tc_pack(nnb_handle* h, const float* weights_natural);                         // nnb_tc.cu
+int nnb_launch_mcmc_tc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st);      // nnb_tc.cu
 
 #define NNB_CUDA(h, call)                                                                        \
   do {                                                                                           \

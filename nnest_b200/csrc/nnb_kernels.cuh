@@ -74,12 +74,7 @@ __device__ __forceinline__ SmemView carve(unsigned char* base, int total_floats,
   double* td_s = reinterpret_cast<double*>(base + (size_t)total_floats * 4);
   const int nd = tgt_g ? target_doubles(td.d, td.n_params) : 0;
   for (int i = threadIdx.x; i < nd; i += blockDim.x) td_s[i] = tgt_g[i];
-  v.tg.desc = td;
-  v.tg.params = td_s;
-  v.tg.ts = td_s + td.n_params;
-  v.tg.tb = v.tg.ts + td.d;
-  v.tg.lo = v.tg.tb + td.d;
-  v.tg.hi = v.tg.lo + td.d;
+  target_bind(v.tg, td, td_s);
   v.y = reinterpret_cast<float*>(td_s + nd);
   v.zp = v.y + (size_t)d * kBlockThreads;
   v.red = reinterpret_cast<unsigned int*>(v.y + (size_t)nvec * d * kBlockThreads);
@@ -357,7 +352,7 @@ mcmc_kernel(FlowDesc f, const float* __restrict__ wg, TargetDesc td, const doubl
     if (p.dynamic) {
       // global accept count of this step -> scale adaptation (sampler.py:418-430).  The host issues one
       // launch per step in this mode, so "the last CTA to finish" owns the update.
-      unsigned int blk = block_sum_u32(accept ? 1u : 0u, sv.red);
+      unsigned int blk = block_count(accept);
       if (threadIdx.x == 0) {
         if (blk) atomicAdd(&p.ctrl->step_acc, blk);
         __threadfence();

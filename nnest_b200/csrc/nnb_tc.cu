@@ -1,0 +1,95 @@
+// nnb_tc.cu -- host side of the tensor-core MCMC kernel: weight packing into the UMMA layout and launch.
+#include <cstring>
+#include <vector>
+
+#include "nnb_host.h"
+#include "nnb_tc_kernels.cuh"
+
+using namespace nnb;
+
+// natural (state_dict) order -> per block { B1 | bias1 | L x (B2s B2t bias2) | B3s B3t bias3 }, see nnb_tc_kernels.cuh
+int nnb_tc_pack(nnb_handle* h, const float* weights) {
+  const FlowDesc& f = h->flow;
+  h->tc_ok = false;
+  if (!tc_supported(f)) return NNB_OK;
+  const int d = f.d, H = 16, L = f.L, B = f.B;
+  TcFlowDesc t{};
+  t.d = d; t.L = L; t.B = B;
+  int off = 0;
+  for (int k = 0; k < B; ++k) { t.off[k] = off; off += tc_block_floats(d, L, k); }
+  t.total_floats = off;
+  std::vector<float> buf((size_t)off, 0.f);
+  const size_t net_nat = (size_t)H * d + H + (size_t)L * (H * H + H) + (size_t)d * H + d;
+  for (int k = 0; k < B; ++k) {
+    const int nin = blk_nin(d, k), i0 = blk_i0(k), nout = blk_nout(d, k), o0 = blk_o0(k);
+    const int K1 = round8(nin), N3 = round16(nout);
+    const float* net[2] = {weights + (size_t)(2 * k) * net_nat, weights + (size_t)(2 * k + 1) * net_nat};
+    float* dst = buf.data() + t.off[k];
+    // layer 1: rows 0-15 scale net, 16-31 translate net; columns = masked inputs
+    std::vector<float> w1((size_t)32 * K1, 0.f);
+    for (int s = 0; s < 2; ++s)
+      for (int j = 0; j < H; ++j)
+        for (int a = 0; a < nin; ++a) w1[(size_t)(16 * s + j) * K1 + a] = net[s][(size_t)j * d + (i0 + 2 * a)];
+    tc::host_pack_b(w1.data(), 32, K1, K1, 32, K1, dst, dst + 32 * K1);
+    float* bias1 = dst + 64 * K1;
+    for (int s = 0; s < 2; ++s)
+      for (int j = 0; j < H; ++j) bias1[16 * s + j] = net[s][(size_t)H * d + j];
+    float* o = bias1 + 32;
+    size_t nat_off = (size_t)H * d + H;
+    for (int l = 0; l < L; ++l) {
+      for (int s = 0; s < 2; ++s) tc::host_pack_b(net[s] + nat_off, 16, 16, 16, 16, 16, o + 512 * s, o + 512 * s + 256);
+      for (int s = 0; s < 2; ++s)
+        for (int j = 0; j < H; ++j) o[1024 + 16 * s + j] = net[s][nat_off + (size_t)H * H + j];
+      o += 1056;
+      nat_off += (size_t)H * H + H;
+    }
+    std::vector<float> w3((size_t)N3 * 16, 0.f);
+    for (int s = 0; s < 2; ++s) {
+      std::fill(w3.begin(), w3.end(), 0.f);
+      for (int q = 0; q < nout; ++q)
+        for (int j = 0; j < H; ++j) w3[(size_t)q * 16 + j] = net[s][nat_off + (size_t)(o0 + 2 * q) * H + j];
+      tc::host_pack_b(w3.data(), N3, 16, 16, N3, 16, o + (size_t)32 * N3 * s, o + (size_t)32 * N3 * s + 16 * N3);
+    }
+    float* bias3 = o + 64 * N3;
+    for (int s = 0; s < 2; ++s)
+      for (int q = 0; q < nout; ++q) bias3[N3 * s + q] = net[s][nat_off + (size_t)d * H + (o0 + 2 * q)];
+  }
+  if (tc_smem_bytes(t, target_doubles(d, NNB_MAX_LIKE_PARAMS), 1) > (size_t)h->max_smem) return NNB_OK;
+  if (h->d_weights_tc) { cudaFree(h->d_weights_tc); h->d_weights_tc = nullptr; }
+  NNB_CUDA(h, cudaMalloc(&h->d_weights_tc, buf.size() * sizeof(float)));
+  NNB_CUDA(h, cudaMemcpy(h->d_weights_tc, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->tcflow = t;
+  h->tc_ok = true;
+  return NNB_OK;
+}
+
+template <int MODE>
+static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t st) {
+  const int tdoubles = target_doubles(h->tdesc.d, h->tdesc.n_params);
+  const long long tiles_total = (p.n + 127) / 128;
+  int ntiles = (int)((tiles_total + h->sm_count - 1) / h->sm_count);   // fill every SM before stacking tiles
+  if (ntiles > kTcMaxTiles) ntiles = kTcMaxTiles;
+  if (ntiles < 1) ntiles = 1;
+  while (ntiles > 1 && tc_smem_bytes(h->tcflow, tdoubles, ntiles) > (size_t)h->max_smem) --ntiles;
+  size_t sm = tc_smem_bytes(h->tcflow, tdoubles, ntiles);
+  const size_t one_cta_per_sm = 116 * 1024;   // TMEM is allocated per CTA: keep a single CTA resident per SM
+  if (sm < one_cta_per_sm) sm = one_cta_per_sm;
+  NNB_CUDA(h, nnb_set_smem(mcmc_tc_kernel<MODE>, sm));
+  const int grid = (int)((tiles_total + ntiles - 1) / ntiles);
+  if (p.dynamic) {
+    for (int s = 0; s < steps; ++s) {
+      p.s0 = s; p.nsteps = 1;
+      mcmc_tc_kernel<MODE><<<grid, ntiles * 128, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p);
+    }
+  } else {
+    p.s0 = 0; p.nsteps = steps;
+    mcmc_tc_kernel<MODE><<<grid, ntiles * 128, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p);
+  }
+  NNB_CUDA(h, cudaGetLastError());
+  return NNB_OK;
+}
+
+int nnb_launch_mcmc_tc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st) {
+  return p.mode == NNB_MODE_MH ? launch_tc_mode<NNB_MODE_MH>(h, p, steps, st)
+                               : launch_tc_mode<NNB_MODE_HARD>(h, p, steps, st);
+}

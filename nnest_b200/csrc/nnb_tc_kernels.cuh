@@ -1,0 +1,438 @@
+// nnb_tc_kernels.cuh -- tensor-core (tcgen05 / TMEM, 3xTF32) variant of the fused MCMC step kernel.
+//
+// Same contract as mcmc_kernel<16, MODE> (nnb_kernels.cuh; reference nnest/sampler.py:291-444); the six
+// small GEMMs of every coupling block -- s/t MLPs Linear(d,16) -> [Linear(16,16)] x L -> Linear(16,d),
+// nnest/networks.py:262-282 -- run on the 5th-generation tensor cores:
+//   * a warpgroup (128 threads) owns a tile of 128 chains = the M dimension of one tcgen05.mma; thread t owns
+//     chain t and TMEM lane t, so activations never leave the chain's own thread: D row -> registers
+//     (tcgen05.ld) -> bias + tanh/relu -> hi/lo split -> A row of the next layer (tcgen05.st);
+//   * weights (B operands) are pre-split into tf32 hi/lo halves on the host and staged once per CTA in shared
+//     memory in the canonical K-major core-matrix layout (nnb_tc.cuh);
+//   * layer 1 of both nets shares its input, so it is ONE N=32 MMA group; the hidden and output layers are
+//     block diagonal and issued as two N=16 (N=round16(nout)) groups.
+// Everything else of the step (Philox noise, box test, likelihood, accept/reject, state/trace update) is the
+// same per-thread code as the FFMA kernel.
+#pragma once
+#include "nnb_kernels.cuh"
+#include "nnb_tc.cuh"
+
+namespace nnb {
+
+constexpr int kTcMaxTiles = 4;          // warpgroups per CTA
+constexpr int kTcColsPerTile = 128;     // TMEM columns per tile: A hi [0,32) lo [32,64); D [64,128)
+
+__host__ __device__ inline int round8(int v) { return (v + 7) & ~7; }
+__host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
+// per-block packed layout (floats):
+//   B1_hi [K1*32] B1_lo [K1*32] bias1 [32]
+//   L x { B2s_hi [256] B2s_lo [256] B2t_hi [256] B2t_lo [256] bias2 [32] }
+//   B3s_hi [16*N3] B3s_lo B3t_hi B3t_lo   bias3s [N3] bias3t [N3]
+__host__ __device__ inline int tc_block_floats(int d, int L, int k) {
+  const int K1 = round8(blk_nin(d, k)), N3 = round16(blk_nout(d, k));
+  return 64 * K1 + 32 + L * 1056 + 64 * N3 + 2 * N3;
+}
+__host__ __device__ inline bool tc_supported(const FlowDesc& f) {
+  return f.H == 16 && f.d >= 2 && blk_nin(f.d, 0) <= 32 && blk_nin(f.d, 1) <= 32 && blk_nout(f.d, 0) <= 32 &&
+         blk_nout(f.d, 1) <= 32 && !(f.flags & (NNB_FLOW_TRANSLATE_ONLY | NNB_FLOW_CONST_SCALE));
+}
+
+#ifndef NNB_TC_FAST_TANH
+#define NNB_TC_FAST_TANH 0
+#endif
+// tanh of the s-net.  Default: libdevice tanhf (<= 2 ulp).  NNB_TC_FAST_TANH: 1 - 2/(exp2(2x log2 e) + 1) with the
+// MUFU ex2/rcp approximations and an odd polynomial below 0.25 (<= ~1e-6 relative).
+__device__ __forceinline__ float tc_tanh(float x) {
+#if NNB_TC_FAST_TANH
+  const float ax = fabsf(x);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.885390081777927f));
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(e + 1.0f));
+  const float big = copysignf(fmaf(-2.0f, rc, 1.0f), x);
+  const float x2 = x * x;
+  float pl = fmaf(x2, 0.021869488536155203f, -0.05396825396825397f);
+  pl = fmaf(pl, x2, 0.13333333333333333f);
+  pl = fmaf(pl, x2, -0.3333333333333333f);
+  const float small = fmaf(pl * x2, x, x);
+  return ax < 0.25f ? small : big;
+#else
+  return tanhf(x);
+#endif
+}
+
+#ifndef NNB_TC_FAST_EXP
+#define NNB_TC_FAST_EXP 0
+#endif
+// exp of the coupling scale.  NNB_TC_FAST_EXP: ex2.approx(x * log2 e) (2 ulp + |x| * 2^-24)
+__device__ __forceinline__ float tc_exp(float x) {
+#if NNB_TC_FAST_EXP
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return e;
+#else
+  return expf(x);
+#endif
+}
+
+struct TcTile {
+  uint32_t tmem;      // TMEM address of the tile's column 0 (lane 0)
+  uint32_t lane_tmem; // + this warp's lane quarter
+  uint64_t* mbar;
+  uint32_t phase;
+  uint32_t bar_id;
+  bool issuer_warp;   // warp 0 of the warpgroup; its lane 0 issues the MMAs
+};
+
+// hand the freshly written A operands to the tensor core, run `issue`, wait for completion
+template <typename F>
+__device__ __forceinline__ void tc_round_trip(TcTile& t, F issue) {
+  tc::wait_st();
+  tc::fence_before_sync();
+  tc::named_bar_sync(t.bar_id, 128);
+  if (t.issuer_warp) {   // the whole warp takes the branch so that no lane spins next to the issuing lane
+    tc::fence_after_sync();
+    if ((threadIdx.x & 31) == 0) {
+      issue();
+      tc::mma_commit(t.mbar);
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(t.mbar, t.phase);
+  t.phase ^= 1u;
+  __syncwarp();
+  tc::fence_after_sync();
+}
+
+// bias + activation + hi/lo split of the 32 hidden pre-activations (s-net 16 tanh | t-net 16 relu):
+// D cols [64,96) -> A hi cols [0,32), lo cols [32,64).  A rolled loop over 8-column chunks keeps the code small
+// (the instruction cache matters: the step kernel is large).
+__device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float* __restrict__ bias) {
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[8], hi[8], lo[8];
+    tc::tmem_ld8(t.lane_tmem + 64 + 8 * c, r);
+    tc::wait_ld();
+    const float4* b4 = reinterpret_cast<const float4*>(bias + 8 * c);
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float4 b = b4[q];
+      v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b.x;
+      v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b.y;
+      v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
+      v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
+    }
+    if (c < 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = tc_tanh(v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tc::split_tf32(v[j], hi[j], lo[j]);
+    tc::tmem_st8(t.lane_tmem + 8 * c, hi);
+    tc::tmem_st8(t.lane_tmem + 32 + 8 * c, lo);
+  }
+}
+
+// Flow inverse of one tile, in place on y (shared memory, stride ys).  Returns log|det dx/dz| of the chain.
+// wsm_u32: shared-memory byte address of the packed TC weights; wsm: the same as a pointer (biases).
+__device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const float* __restrict__ wsm, uint32_t wsm_u32,
+                                                 TcTile& t, float* y, int ys) {
+  const int d = f.d, L = f.L;
+  float ld = 0.f;
+  for (int k = f.B - 1; k >= 0; --k) {
+    const int nin = blk_nin(d, k), i0 = blk_i0(k), nout = blk_nout(d, k), o0 = blk_o0(k);
+    const int K1 = round8(nin), N3 = round16(nout);
+    const int base = f.off[k];
+    // ---- layer 1: A = masked inputs (dims with mask == 1), zero padded to K1 --------------------------
+    for (int c0 = 0; c0 < K1; c0 += 8) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int a = c0 + j;
+        float v = a < nin ? y[(i0 + 2 * a) * ys] : 0.f;
+        tc::split_tf32(v, hi[j], lo[j]);
+      }
+      tc::tmem_st8(t.lane_tmem + c0, hi);
+      tc::tmem_st8(t.lane_tmem + 32 + c0, lo);
+    }
+    {
+      const uint32_t b_hi = wsm_u32 + 4u * base, b_lo = b_hi + 4u * 32u * K1;
+      tc_round_trip(t, [&] { tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, b_hi, b_lo, K1 / 8, 32, false); });
+    }
+    int off = base + 64 * K1;   // -> bias1
+    tc_hidden_epilogue(t, wsm + off);
+    off += 32;
+    // ---- hidden layers: block diagonal, s-net cols [0,16), t-net cols [16,32) --------------------------------
+    for (int l = 0; l < L; ++l) {
+      const uint32_t bs_hi = wsm_u32 + 4u * off, bs_lo = bs_hi + 1024u, bt_hi = bs_hi + 2048u, bt_lo = bs_hi + 3072u;
+      tc_round_trip(t, [&] {
+        tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, bs_hi, bs_lo, 2, 16, false);
+        tc::mma_3xtf32(t.tmem + 80, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, 16, false);
+      });
+      tc_hidden_epilogue(t, wsm + off + 1024);
+      off += 1056;
+    }
+    // ---- output layer: log_s -> D cols [64, 64+N3), t -> D cols [96, 96+N3) ------------------------------------
+    {
+      const uint32_t sz = 4u * 16u * N3;
+      const uint32_t bs_hi = wsm_u32 + 4u * off, bs_lo = bs_hi + sz, bt_hi = bs_hi + 2 * sz, bt_lo = bs_hi + 3 * sz;
+      tc_round_trip(t, [&] {
+        tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, bs_hi, bs_lo, 2, N3, false);
+        tc::mma_3xtf32(t.tmem + 96, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, N3, false);
+      });
+    }
+    const float* b3s = wsm + off + 64 * N3;
+    const float* b3t = b3s + N3;
+    // x = (z - t) * exp(-log_s), ld -= log_s on the dims with mask == 0   (networks.py:300-309)
+    for (int c0 = 0; c0 < nout; c0 += 8) {
+      uint32_t rs[8], rt[8];
+      tc::tmem_ld8(t.lane_tmem + 64 + c0, rs);
+      tc::tmem_ld8(t.lane_tmem + 96 + c0, rt);
+      tc::wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int o = c0 + j;
+        if (o < nout) {
+          const float ls = __uint_as_float(rs[j]) + b3s[o];
+          const float tt = __uint_as_float(rt[j]) + b3t[o];
+          float* yp = y + (o0 + 2 * o) * ys;
+          *yp = (*yp - tt) * tc_exp(-ls);
+          ld -= ls;
+        }
+      }
+    }
+  }
+  return ld;
+}
+
+// one out-of-line copy of the likelihood / prior switch per kernel (code size)
+static __device__ __noinline__ double tc_loglike(const TargetSmem& tg, const float* y) {
+  SmemRow row{y};
+  return loglike_any(tg, row, false);
+}
+static __device__ __noinline__ double tc_prior(const TargetSmem& tg, const float* y) {
+  SmemRow row{y};
+  return prior_any(tg, row, false);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcMaxTiles * 128, 1)
+mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, const double* __restrict__ tgt_g,
+               McmcParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int d = f.d;
+  const int ntiles = blockDim.x >> 7;
+  // carve: [tc weights][target doubles][y: ntiles*d*128][zp: ntiles*d*128][mbar: 4 x 8B][tmem base][red 32]
+  float* wsm = reinterpret_cast<float*>(smem_raw);
+  double* td_s = reinterpret_cast<double*>(smem_raw + (size_t)f.total_floats * 4);
+  const int nd = target_doubles(td.d, td.n_params);
+  float* y_all = reinterpret_cast<float*>(td_s + nd);
+  float* zp_all = y_all + (size_t)ntiles * d * 128;
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(zp_all + (size_t)ntiles * d * 128);
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(mbars + kTcMaxTiles);
+  unsigned int* red = tmem_base_s + 2;
+
+  {
+    const float4* s4 = reinterpret_cast<const float4*>(wglob);
+    float4* d4 = reinterpret_cast<float4*>(wsm);
+    for (int i = threadIdx.x; i < f.total_floats / 4; i += blockDim.x) d4[i] = s4[i];
+    for (int i = threadIdx.x; i < nd; i += blockDim.x) td_s[i] = tgt_g[i];
+  }
+  TargetSmem tg;
+  target_bind(tg, td, td_s);
+
+  const int warp = threadIdx.x >> 5;
+  const int wg = warp >> 2;
+  const int wg_tid = threadIdx.x & 127;
+  const uint32_t tmem_cols = ntiles <= 1 ? 128u : (ntiles == 2 ? 256u : 512u);
+  if (warp == 0) tc::tmem_alloc(tmem_base_s, tmem_cols);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTcMaxTiles; ++i) tc::mbar_init(&mbars[i], 1);
+    tc::mbar_fence_init();
+  }
+  // weights were written through the generic proxy; the tensor core reads them through the async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+
+  TcTile t;
+  t.tmem = *tmem_base_s + (uint32_t)wg * kTcColsPerTile;
+  t.lane_tmem = t.tmem + (((uint32_t)(warp & 3) * 32u) << 16);
+  t.mbar = &mbars[wg];
+  t.phase = 0;
+  t.bar_id = 1 + wg;
+  t.issuer_warp = (warp & 3) == 0;
+  const uint32_t wsm_u32 = tc::smem_u32(wsm);
+
+  const long long n = p.n;
+  const long long tile_base = ((long long)blockIdx.x * ntiles + wg) * 128;
+  const bool tile_active = tile_base < n;          // uniform over the warpgroup
+  const long long c = tile_base + wg_tid;
+  const bool active = c < n;
+  float* y = y_all + (size_t)wg * d * 128 + wg_tid;
+  float* zp = zp_all + (size_t)wg * d * 128 + wg_tid;
+  const unsigned int chain = (unsigned int)(p.chain_offset + (unsigned long long)c);
+  unsigned int acc_total = 0, ncall_total = 0;
+  float ld_cur = 0.f;
+  double logl_cur = 0.0, logp_cur = 0.0;
+  if (active) {
+    ld_cur = p.logdet[c];
+    logl_cur = p.logl[c];
+    logp_cur = p.logp[c];
+  }
+
+  for (int s = p.s0 + 1; s <= p.s0 + p.nsteps; ++s) {
+    const float scale_f = (float)(*reinterpret_cast<volatile double*>(&p.ctrl->scale));
+    const unsigned int step_abs = p.step_offset + (unsigned int)s;
+    bool accept = false;
+    unsigned int ncall = 0;
+    if (tile_active) {
+      // ---- proposal ------------------------------------------------------------------------------------
+      if (active) {
+        // all loads of the current latent first (their latency overlaps), then the noise
+        for (int i = 0; i < d; ++i) y[i * 128] = p.z[(long long)i * n + c];
+        if (p.replay_normals) {
+          const float* nr = p.replay_normals + ((long long)(s - 1) * n + c) * d;
+          for (int i = 0; i < d; ++i) {
+            float v = __fadd_rn(y[i * 128], __fmul_rn(nr[i], scale_f));
+            y[i * 128] = v;
+            zp[i * 128] = v;
+          }
+        } else {
+          const int nj = (d + 3) / 4;
+          for (int j = 0; j < nj; j += 2) {   // two Philox blocks per iteration: independent chains for ILP
+            float nrm[8];
+            uint4 r0 = philox4x32_10(j, step_abs, chain, kTagNormal, p.seed_lo, p.seed_hi);
+            uint4 r1 = philox4x32_10(j + 1, step_abs, chain, kTagNormal, p.seed_lo, p.seed_hi);
+            box_muller(r0.x, r0.y, nrm[0], nrm[1]);
+            box_muller(r0.z, r0.w, nrm[2], nrm[3]);
+            box_muller(r1.x, r1.y, nrm[4], nrm[5]);
+            box_muller(r1.z, r1.w, nrm[6], nrm[7]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int i = 4 * j + q;
+              if (i < d) {
+                float v = __fadd_rn(y[i * 128], __fmul_rn(nrm[q], scale_f));
+                y[i * 128] = v;
+                zp[i * 128] = v;
+                if (p.dump_normals) p.dump_normals[((long long)(s - 1) * n + c) * d + i] = nrm[q];
+              }
+            }
+          }
+        }
+      } else {
+        for (int i = 0; i < d; ++i) y[i * 128] = 0.f;
+      }
+      __syncwarp();
+      // ---- flow inverse on the tensor cores (all 128 threads of the tile, converged) -------------------------
+      const float ld_prop = tc_flow_inverse(f, wsm, wsm_u32, t, y, 128);
+      if (active) {
+        float u01;
+        if (p.replay_uniforms) {
+          u01 = p.replay_uniforms[(long long)(s - 1) * n + c];
+        } else {
+          uint4 r = philox4x32_10(0u, step_abs, chain, kTagUniform, p.seed_lo, p.seed_hi);
+          u01 = uniform01(r.x);
+          if (p.dump_uniforms) p.dump_uniforms[(long long)(s - 1) * n + c] = u01;
+        }
+        double lp = 0.0, logp_prop = 0.0;
+        if (MODE == NNB_MODE_HARD) {
+          float lr = __fsub_rn(ld_prop, ld_cur);
+          logp_prop = tc_prior(tg, y);
+          if (logp_prop < -1e30) lr = -INFINITY;
+          float ratio = expf(lr);
+          if (ratio > 1.0f) ratio = 1.0f;
+          const bool m1 = u01 < ratio;
+          if (m1) {
+            lp = tc_loglike(tg, y);
+            ncall = 1;
+            accept = isfinite(lp) && (lp > p.loglstar);
+          }
+        } else {
+          lp = tc_loglike(tg, y);
+          ncall = 1;
+          logp_prop = tc_prior(tg, y);
+          double lr = (double)__fsub_rn(ld_prop, ld_cur) + (lp - logl_cur) + (logp_prop - logp_cur);
+          double ratio = exp(lr);
+          if (ratio > 1.0) ratio = 1.0;
+          accept = (double)u01 < ratio;
+        }
+        if (accept) {
+          for (int i = 0; i < d; ++i) {
+            p.z[(long long)i * n + c] = zp[i * 128];
+            p.x[(long long)i * n + c] = y[i * 128];
+          }
+          ld_cur = ld_prop;
+          logl_cur = lp;
+          logp_cur = logp_prop;
+        }
+        if (p.trace_z) {
+          float* tz = p.trace_z + (long long)s * d * n + c;
+          float* tx = p.trace_x + (long long)s * d * n + c;
+          if (accept) {
+            for (int i = 0; i < d; ++i) {
+              tz[(long long)i * n] = zp[i * 128];
+              tx[(long long)i * n] = y[i * 128];
+            }
+          } else {
+            for (int i = 0; i < d; ++i) {
+              tz[(long long)i * n] = p.z[(long long)i * n + c];
+              tx[(long long)i * n] = p.x[(long long)i * n + c];
+            }
+          }
+          p.trace_logl[(long long)s * n + c] = logl_cur;
+        }
+      }
+      __syncwarp();
+    }
+    acc_total += accept ? 1u : 0u;
+    ncall_total += ncall;
+
+    if (p.dynamic) {
+      unsigned int blk = block_count(accept);
+      if (threadIdx.x == 0) {
+        if (blk) atomicAdd(&p.ctrl->step_acc, blk);
+        __threadfence();
+        unsigned int tk = atomicAdd(&p.ctrl->ticket, 1u);
+        if (tk == gridDim.x - 1) {
+          __threadfence();
+          unsigned int na = atomicExch(&p.ctrl->step_acc, 0u);
+          p.ctrl->ticket = 0u;
+          int a = p.ctrl->accept, r = p.ctrl->reject;
+          if (2ull * na > (unsigned long long)n) a += 1; else r += 1;
+          double sc = p.ctrl->scale;
+          if (a > r) sc *= exp(1.0 / (1 + a));
+          if (a < r) sc /= exp(1.0 / (1 + r));
+          p.ctrl->accept = a;
+          p.ctrl->reject = r;
+          p.ctrl->scale = sc;
+        }
+      }
+    }
+  }
+  if (active) {
+    p.logdet[c] = ld_cur;
+    p.logl[c] = logl_cur;
+    p.logp[c] = logp_cur;
+  }
+  unsigned int ta = block_sum_u32(acc_total, red);
+  unsigned int tcall = block_sum_u32(ncall_total, red);
+  if (threadIdx.x == 0) {
+    if (ta) atomicAdd(&p.ctrl->naccept, (unsigned long long)ta);
+    if (tcall) atomicAdd(&p.ctrl->ncall, (unsigned long long)tcall);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(*tmem_base_s, tmem_cols);
+}
+
+__host__ inline size_t tc_smem_bytes(const TcFlowDesc& f, int tdoubles, int ntiles) {
+  return (size_t)f.total_floats * 4 + (size_t)tdoubles * 8 + 2 * (size_t)ntiles * f.d * 128 * 4 + kTcMaxTiles * 8 + 8 +
+         32 * 4;
+}
+
+}  // namespace nnb

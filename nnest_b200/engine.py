@@ -4,6 +4,7 @@ PyTorch is used for device memory and streams only; all arithmetic of the hot pa
 libnnb.so.  One Engine = one nnb_handle = one CUDA device.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -91,6 +92,7 @@ class Engine(object):
         self.h = h
         self.d = None
         self.gpu_launches = 0     # kernels launched through this engine (bench.py reports it)
+        self.default_impl = int(os.environ.get('NNB_IMPL', L.NNB_IMPL_AUTO))   # 0 auto, 1 ffma, 2 tcgen05
 
     def __del__(self):
         try:
@@ -191,7 +193,7 @@ class Engine(object):
         return st, nbad.value, ncall.value
 
     def mcmc_run(self, st, steps, mode=L.NNB_MODE_HARD, loglstar=0.0, step_size=0.0, dynamic_step_size=False,
-                 seed=0, chain_offset=0, step_offset=0, trace=False, replay=None, dump_noise=False):
+                 seed=0, chain_offset=0, step_offset=0, trace=False, replay=None, dump_noise=False, impl=None):
         """Advances `st` in place by `steps` steps.  Returns a dict with scale, ncall, naccept and, if
         requested, the trace tensors (steps+1, d, n) / (steps+1, n) and the dumped noise."""
         n, d = st.n, st.d
@@ -200,6 +202,7 @@ class Engine(object):
         a.loglstar = 0.0 if loglstar is None else float(loglstar)
         a.step_size, a.dynamic_step_size = float(step_size), 1 if dynamic_step_size else 0
         a.seed, a.chain_offset, a.step_offset = seed, chain_offset, step_offset
+        a.impl = self.default_impl if impl is None else impl
         a.z, a.x, a.logl, a.logdet, a.logp = [t.data_ptr() for t in (st.z, st.x, st.logl, st.logdet, st.logp)]
         out = {}
         if trace:

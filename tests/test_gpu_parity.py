@@ -153,11 +153,15 @@ HARD = {
 }
 
 
-def _run_replay(engine, g, mode, init_u=None, init_z=None, init_logl=None, loglstar=None, step_size=0.0, dynamic=False):
+IMPLS = [pytest.param(1, id='ffma'), pytest.param(2, id='tcgen05')]
+
+
+def _run_replay(engine, g, mode, init_u=None, init_z=None, init_logl=None, loglstar=None, step_size=0.0, dynamic=False,
+                impl=0):
     steps, n = int(g['steps']), int(g['chains'])
     st, nbad, ncall0 = engine.mcmc_init(n, init_u=init_u, init_z=init_z, init_logl=init_logl)
     out = engine.mcmc_run(st, steps, mode=mode, loglstar=loglstar, step_size=step_size, dynamic_step_size=dynamic,
-                          trace=True, replay=(dev(g['normals']), dev(g['uniforms'])))
+                          trace=True, replay=(dev(g['normals']), dev(g['uniforms'])), impl=impl)
     samples = out['trace_x'].permute(2, 0, 1).cpu().numpy()
     latent = out['trace_z'].permute(2, 0, 1).cpu().numpy()
     loglikes = out['trace_logl'].permute(1, 0).cpu().numpy()
@@ -178,8 +182,9 @@ def _compare_trace(samples, latent, loglikes, scale, ncall, g, max_flipped_chain
         assert abs(scale - float(g['scale'])) <= 1e-12 * abs(float(g['scale']))
 
 
+@pytest.mark.parametrize('impl', IMPLS)
 @pytest.mark.parametrize('name', sorted(HARD))
-def test_mcmc_hard_replay_matches_reference_golden(engine, name):
+def test_mcmc_hard_replay_matches_reference_golden(engine, name, impl):
     g = load(name)
     mk, ts = HARD[name]
     d = int(g['d'])
@@ -189,12 +194,13 @@ def test_mcmc_hard_replay_matches_reference_golden(engine, name):
                       prior_hi=1.0)
     init_u = dev(np.ascontiguousarray(g['init_samples'].astype(np.float32).T))
     out = _run_replay(engine, g, 0, init_u=init_u, init_logl=dev(g['init_loglikes']), loglstar=float(g['loglstar']),
-                      step_size=float(g['step_size']), dynamic=bool(g['dynamic']))
+                      step_size=float(g['step_size']), dynamic=bool(g['dynamic']), impl=impl)
     _compare_trace(*out[:5], g)
 
 
+@pytest.mark.parametrize('impl', IMPLS)
 @pytest.mark.parametrize('name', ['mcmc_mh_gauss8.npz', 'mcmc_mh_gauss50.npz'])
-def test_mcmc_mh_replay_matches_reference_golden(engine, name):
+def test_mcmc_mh_replay_matches_reference_golden(engine, name, impl):
     g = load(name)
     d = int(g['d'])
     like = olike.Gaussian(d, float(g['corr']))
@@ -202,11 +208,12 @@ def test_mcmc_mh_replay_matches_reference_golden(engine, name):
     engine.set_target(d, like.like_id, like.params(), t_scale=g['std'], t_shift=g['mean'], compute_f64=True,
                       prior_kind=2, prior_lo=float(g['prior_min']), prior_hi=float(g['prior_max']))
     init_z = dev(np.ascontiguousarray(g['z0'].T))
-    out = _run_replay(engine, g, 1, init_z=init_z, loglstar=None, step_size=0.0, dynamic=False)
+    out = _run_replay(engine, g, 1, init_z=init_z, loglstar=None, step_size=0.0, dynamic=False, impl=impl)
     _compare_trace(*out[:5], g)
 
 
-def test_mcmc_free_running_matches_oracle_on_dumped_noise(engine):
+@pytest.mark.parametrize('impl', IMPLS)
+def test_mcmc_free_running_matches_oracle_on_dumped_noise(engine, impl):
     """Philox mode at a mid size: the kernel dumps the noise it used; the oracle replays it."""
     g = load('mcmc_hard_rosen30.npz')
     d, n, steps = 30, 1024, 12
@@ -219,7 +226,7 @@ def test_mcmc_free_running_matches_oracle_on_dumped_noise(engine):
     st, _, _ = engine.mcmc_init(n, init_u=dev(np.ascontiguousarray(init_samples.astype(np.float32).T)),
                                 init_logl=dev(init_logl), seed=5)
     out = engine.mcmc_run(st, steps, mode=0, loglstar=float(g['loglstar']), step_size=1 / 30 ** 0.5,
-                          dynamic_step_size=True, seed=5, trace=True, dump_noise=True)
+                          dynamic_step_size=True, seed=5, trace=True, dump_noise=True, impl=impl)
     target = omcmc.Target(olike.Rosenbrock(30), transform=lambda x: 5 * x, prior=olike.UniformPrior(d, -1, 1),
                           transform_prior=False)
     ref = omcmc.mcmc_sample(w, target, steps, omcmc.ReplayNoise(out['normals'].cpu().numpy(),
@@ -242,7 +249,8 @@ def test_mcmc_free_running_matches_oracle_on_dumped_noise(engine):
     assert torch.equal(st.logl, out['trace_logl'][-1])
 
 
-def test_mcmc_sharding_invariance(engine):
+@pytest.mark.parametrize('impl', IMPLS)
+def test_mcmc_sharding_invariance(engine, impl):
     """Chains keyed by global id: running [0,n) in one call equals running two halves with chain_offset."""
     g = load('mcmc_hard_mix10.npz')
     d, n, steps = 10, 512, 6
@@ -253,7 +261,7 @@ def test_mcmc_sharding_invariance(engine):
     idx = rng.randint(0, g['active_u'].shape[0], size=n)
     u = np.ascontiguousarray(g['active_u'][idx].astype(np.float32).T)
     logl = g['active_logl'][idx]
-    kw = dict(mode=0, loglstar=float(g['loglstar']), step_size=0.3, dynamic_step_size=False, seed=11)
+    kw = dict(mode=0, loglstar=float(g['loglstar']), step_size=0.3, dynamic_step_size=False, seed=11, impl=impl)
     st, _, _ = engine.mcmc_init(n, init_u=dev(u), init_logl=dev(logl))
     engine.mcmc_run(st, steps, **kw)
     halves = []
@@ -266,7 +274,8 @@ def test_mcmc_sharding_invariance(engine):
     assert torch.equal(torch.cat([h.logl for h in halves]), st.logl)
 
 
-def test_mcmc_hard_constraint_invariants_full_size(engine):
+@pytest.mark.parametrize('impl', IMPLS)
+def test_mcmc_hard_constraint_invariants_full_size(engine, impl):
     """Config-4 shape (65536 chains, d=30): every chain's end point obeys the constraint and the box."""
     g = load('mcmc_hard_rosen30.npz')
     d, n, steps = 30, 65536, 10
@@ -279,7 +288,8 @@ def test_mcmc_hard_constraint_invariants_full_size(engine):
     loglstar = float(g['loglstar'])
     st, nbad, _ = engine.mcmc_init(n, init_u=u, init_logl=logl0, seed=1)
     z0 = st.z.clone()
-    out = engine.mcmc_run(st, steps, mode=0, loglstar=loglstar, step_size=1 / 30 ** 0.5, dynamic_step_size=True, seed=1)
+    out = engine.mcmc_run(st, steps, mode=0, loglstar=loglstar, step_size=1 / 30 ** 0.5, dynamic_step_size=True, seed=1,
+                          impl=impl)
     moved = (st.z != z0).any(dim=0)
     assert 0 < out['naccept'] <= n * steps and out['ncall'] >= out['naccept']
     assert (st.logl[moved] > loglstar).all()
@@ -290,4 +300,7 @@ def test_mcmc_hard_constraint_invariants_full_size(engine):
     assert torch.equal(again[moved], st.logl[moved])
     # flow consistency of the end state
     x2, ld2 = engine.flow_inverse(st.z.t())
-    assert torch.equal(x2.t().contiguous(), st.x) and torch.equal(ld2, st.logdet)
+    if impl == 1:     # same FFMA arithmetic as the batch flow kernel: bit for bit
+        assert torch.equal(x2.t().contiguous(), st.x) and torch.equal(ld2, st.logdet)
+    else:             # tensor-core 3xTF32 path: FP32-class agreement
+        assert (x2.t() - st.x).abs().max().item() < 1e-5 and (ld2 - st.logdet).abs().max().item() < 1e-5
