@@ -49,6 +49,7 @@ extern "C" int nnb_create(int device, nnb_handle** out) {
     return fail(nullptr, NNB_ERR_CUDA, "libnnb is built for sm_100a (Blackwell B200) only");
   }
   h->sm_count = prop.multiProcessorCount;
+  h->coop_supported = prop.cooperativeLaunch;
   h->max_smem = (int)prop.sharedMemPerBlockOptin;
   if ((e = cudaMalloc(&h->d_ctrl, sizeof(Ctrl))) != cudaSuccess ||
       (e = cudaMallocHost(&h->h_ctrl, sizeof(Ctrl))) != cudaSuccess) {
@@ -64,6 +65,7 @@ extern "C" void nnb_destroy(nnb_handle* h) {
   cudaSetDevice(h->device);
   if (h->d_weights) cudaFree(h->d_weights);
   if (h->d_weights_tc) cudaFree(h->d_weights_tc);
+  if (h->d_step_counts) cudaFree(h->d_step_counts);
   if (h->d_target) cudaFree(h->d_target);
   if (h->d_ctrl) cudaFree(h->d_ctrl);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);

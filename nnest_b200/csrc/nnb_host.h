@@ -19,6 +19,9 @@ struct nnb_handle {
   bool tc_ok = false;
   nnb::TcFlowDesc tcflow{};
   float* d_weights_tc = nullptr;
+  unsigned int* d_step_counts = nullptr;   // workspace of the cooperative kernel
+  int step_counts_cap = 0;
+  int coop_supported = 0;
   Ctrl* d_ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;  // pinned
   std::string err;

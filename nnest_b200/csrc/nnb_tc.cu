@@ -1,4 +1,5 @@
 // nnb_tc.cu -- host side of the tensor-core MCMC kernel: weight packing into the UMMA layout and launch.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -54,7 +55,7 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
     for (int s = 0; s < 2; ++s)
       for (int q = 0; q < nout; ++q) bias3[N3 * s + q] = net[s][nat_off + (size_t)d * H + (o0 + 2 * q)];
   }
-  if (tc_smem_bytes(t, target_doubles(d, NNB_MAX_LIKE_PARAMS), 1) > (size_t)h->max_smem) return NNB_OK;
+  if (tc_smem_bytes(t, target_doubles(d, NNB_MAX_LIKE_PARAMS), 1, 2) > (size_t)h->max_smem) return NNB_OK;
   if (h->d_weights_tc) { cudaFree(h->d_weights_tc); h->d_weights_tc = nullptr; }
   NNB_CUDA(h, cudaMalloc(&h->d_weights_tc, buf.size() * sizeof(float)));
   NNB_CUDA(h, cudaMemcpy(h->d_weights_tc, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -63,33 +64,56 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
   return NNB_OK;
 }
 
-template <int MODE>
+template <int MODE, int NPART>
 static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t st) {
   const int tdoubles = target_doubles(h->tdesc.d, h->tdesc.n_params);
   const long long tiles_total = (p.n + 127) / 128;
   int ntiles = (int)((tiles_total + h->sm_count - 1) / h->sm_count);   // fill every SM before stacking tiles
   if (ntiles > kTcMaxTiles) ntiles = kTcMaxTiles;
   if (ntiles < 1) ntiles = 1;
-  while (ntiles > 1 && tc_smem_bytes(h->tcflow, tdoubles, ntiles) > (size_t)h->max_smem) --ntiles;
-  size_t sm = tc_smem_bytes(h->tcflow, tdoubles, ntiles);
+  while (ntiles > 1 && tc_smem_bytes(h->tcflow, tdoubles, ntiles, NPART) > (size_t)h->max_smem) --ntiles;
+  size_t sm = tc_smem_bytes(h->tcflow, tdoubles, ntiles, NPART);
   const size_t one_cta_per_sm = 116 * 1024;   // TMEM is allocated per CTA: keep a single CTA resident per SM
   if (sm < one_cta_per_sm) sm = one_cta_per_sm;
-  NNB_CUDA(h, nnb_set_smem(mcmc_tc_kernel<MODE>, sm));
+  NNB_CUDA(h, nnb_set_smem(mcmc_tc_kernel<MODE, NPART>, sm));
   const int grid = (int)((tiles_total + ntiles - 1) / ntiles);
+  const int block = ntiles * 128 * NPART;
+  // Persistent path: all steps in ONE cooperative launch (every CTA resident, one per SM), the global accept count
+  // of each step travels through a grid barrier.  Needs grid <= SM count; otherwise one launch per step.
+  static const bool no_coop = getenv("NNB_NO_COOP") != nullptr;
+  if (!no_coop && p.dynamic && h->coop_supported && grid <= h->sm_count && steps > 1) {
+    if (h->step_counts_cap < steps) {
+      if (h->d_step_counts) cudaFree(h->d_step_counts);
+      h->d_step_counts = nullptr;
+      NNB_CUDA(h, cudaMalloc(&h->d_step_counts, sizeof(unsigned int) * steps));
+      h->step_counts_cap = steps;
+    }
+    NNB_CUDA(h, cudaMemsetAsync(h->d_step_counts, 0, sizeof(unsigned int) * steps, st));
+    p.s0 = 0; p.nsteps = steps; p.coop = 1; p.step_counts = h->d_step_counts;
+    void* args[] = {(void*)&h->tcflow, (void*)&h->d_weights_tc, (void*)&h->tdesc, (void*)&h->d_target, (void*)&p};
+    NNB_CUDA(h, cudaLaunchCooperativeKernel((const void*)mcmc_tc_kernel<MODE, NPART>, dim3(grid), dim3(block), args, sm, st));
+    return NNB_OK;
+  }
+  p.coop = 0; p.step_counts = nullptr;
   if (p.dynamic) {
     for (int s = 0; s < steps; ++s) {
       p.s0 = s; p.nsteps = 1;
-      mcmc_tc_kernel<MODE><<<grid, ntiles * 128, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p);
+      mcmc_tc_kernel<MODE, NPART><<<grid, block, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p);
     }
   } else {
     p.s0 = 0; p.nsteps = steps;
-    mcmc_tc_kernel<MODE><<<grid, ntiles * 128, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p);
+    mcmc_tc_kernel<MODE, NPART><<<grid, block, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p);
   }
   NNB_CUDA(h, cudaGetLastError());
   return NNB_OK;
 }
 
 int nnb_launch_mcmc_tc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st) {
-  return p.mode == NNB_MODE_MH ? launch_tc_mode<NNB_MODE_MH>(h, p, steps, st)
-                               : launch_tc_mode<NNB_MODE_HARD>(h, p, steps, st);
+  // two threads per chain unless NNB_TC_NPART=1 (development switch)
+  static const int npart = [] { const char* e = getenv("NNB_TC_NPART"); return (e && e[0] == '1') ? 1 : 2; }();
+  if (npart == 1)
+    return p.mode == NNB_MODE_MH ? launch_tc_mode<NNB_MODE_MH, 1>(h, p, steps, st)
+                                 : launch_tc_mode<NNB_MODE_HARD, 1>(h, p, steps, st);
+  return p.mode == NNB_MODE_MH ? launch_tc_mode<NNB_MODE_MH, 2>(h, p, steps, st)
+                               : launch_tc_mode<NNB_MODE_HARD, 2>(h, p, steps, st);
 }

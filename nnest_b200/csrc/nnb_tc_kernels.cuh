@@ -3,9 +3,12 @@
 // Same contract as mcmc_kernel<16, MODE> (nnb_kernels.cuh; reference nnest/sampler.py:291-444); the six
 // small GEMMs of every coupling block -- s/t MLPs Linear(d,16) -> [Linear(16,16)] x L -> Linear(16,d),
 // nnest/networks.py:262-282 -- run on the 5th-generation tensor cores:
-//   * a warpgroup (128 threads) owns a tile of 128 chains = the M dimension of one tcgen05.mma; thread t owns
-//     chain t and TMEM lane t, so activations never leave the chain's own thread: D row -> registers
-//     (tcgen05.ld) -> bias + tanh/relu -> hi/lo split -> A row of the next layer (tcgen05.st);
+//   * a tile of 128 chains = the M dimension of one tcgen05.mma is owned by NPART warpgroups (128 threads each);
+//     thread (part, t) works on chain t = TMEM lane t (warps w and w+4 address the same lane quarter), so
+//     activations never leave the chain's own threads: D row -> registers (tcgen05.ld) -> bias + tanh/relu ->
+//     hi/lo split -> A row of the next layer (tcgen05.st).  With NPART = 2 the two threads of a chain split the
+//     8-column chunks of every phase (noise, A operands, epilogues, state update) between them: at 65 536 chains a
+//     B200 has only ~14 warps per SM with one thread per chain, too few to hide the MMA round trips;
 //   * weights (B operands) are pre-split into tf32 hi/lo halves on the host and staged once per CTA in shared
 //     memory in the canonical K-major core-matrix layout (nnb_tc.cuh);
 //   * layer 1 of both nets shares its input, so it is ONE N=32 MMA group; the hidden and output layers are
@@ -37,7 +40,7 @@ __host__ __device__ inline bool tc_supported(const FlowDesc& f) {
 }
 
 #ifndef NNB_TC_FAST_TANH
-#define NNB_TC_FAST_TANH 0
+#define NNB_TC_FAST_TANH 1
 #endif
 // tanh of the s-net.  Default: libdevice tanhf (<= 2 ulp).  NNB_TC_FAST_TANH: 1 - 2/(exp2(2x log2 e) + 1) with the
 // MUFU ex2/rcp approximations and an odd polynomial below 0.25 (<= ~1e-6 relative).
@@ -61,7 +64,7 @@ __device__ __forceinline__ float tc_tanh(float x) {
 }
 
 #ifndef NNB_TC_FAST_EXP
-#define NNB_TC_FAST_EXP 0
+#define NNB_TC_FAST_EXP 1
 #endif
 // exp of the coupling scale.  NNB_TC_FAST_EXP: ex2.approx(x * log2 e) (2 ulp + |x| * 2^-24)
 __device__ __forceinline__ float tc_exp(float x) {
@@ -75,20 +78,25 @@ __device__ __forceinline__ float tc_exp(float x) {
 }
 
 struct TcTile {
-  uint32_t tmem;      // TMEM address of the tile's column 0 (lane 0)
-  uint32_t lane_tmem; // + this warp's lane quarter
+  uint32_t tmem;        // TMEM address of the tile's column 0 (lane 0)
+  uint32_t lane_tmem;   // + this warp's lane quarter
   uint64_t* mbar;
   uint32_t phase;
   uint32_t bar_id;
-  bool issuer_warp;   // warp 0 of the warpgroup; its lane 0 issues the MMAs
+  uint32_t bar_threads; // 128 * NPART
+  int part;             // which of the chain's NPART threads this is
+  bool issuer_warp;     // warp 0 of the tile; its lane 0 issues the MMAs
 };
 
-// hand the freshly written A operands to the tensor core, run `issue`, wait for completion
+__device__ __forceinline__ void tile_sync(const TcTile& t) { tc::named_bar_sync(t.bar_id, t.bar_threads); }
+
+// hand the freshly written A operands to the tensor core, run `issue`, wait for completion.  Only the issuing
+// warp polls the mbarrier; the other warps of the tile sleep on the hardware named barrier (no issue slots).
 template <typename F>
 __device__ __forceinline__ void tc_round_trip(TcTile& t, F issue) {
   tc::wait_st();
   tc::fence_before_sync();
-  tc::named_bar_sync(t.bar_id, 128);
+  tile_sync(t);
   if (t.issuer_warp) {   // the whole warp takes the branch so that no lane spins next to the issuing lane
     tc::fence_after_sync();
     if ((threadIdx.x & 31) == 0) {
@@ -96,19 +104,21 @@ __device__ __forceinline__ void tc_round_trip(TcTile& t, F issue) {
       tc::mma_commit(t.mbar);
     }
     __syncwarp();
+    tc::mbar_wait(t.mbar, t.phase);
+    __syncwarp();
   }
-  tc::mbar_wait(t.mbar, t.phase);
   t.phase ^= 1u;
-  __syncwarp();
+  tile_sync(t);
   tc::fence_after_sync();
 }
 
 // bias + activation + hi/lo split of the 32 hidden pre-activations (s-net 16 tanh | t-net 16 relu):
-// D cols [64,96) -> A hi cols [0,32), lo cols [32,64).  A rolled loop over 8-column chunks keeps the code small
-// (the instruction cache matters: the step kernel is large).
+// D cols [64,96) -> A hi cols [0,32), lo cols [32,64), in 8-column chunks dealt round-robin to the chain's threads
+// (NPART = 2: each gets one tanh chunk and one relu chunk).  A rolled loop keeps the code small.
+template <int NPART>
 __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float* __restrict__ bias) {
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = t.part; c < 4; c += NPART) {
     uint32_t r[8], hi[8], lo[8];
     tc::tmem_ld8(t.lane_tmem + 64 + 8 * c, r);
     tc::wait_ld();
@@ -136,8 +146,10 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float*
   }
 }
 
-// Flow inverse of one tile, in place on y (shared memory, stride ys).  Returns log|det dx/dz| of the chain.
-// wsm_u32: shared-memory byte address of the packed TC weights; wsm: the same as a pointer (biases).
+// Flow inverse of one tile, in place on y (shared memory, stride ys).  Returns this thread's share of
+// log|det dx/dz| of the chain (the sum over the chain's NPART threads is the log-det).  Ends with a tile barrier:
+// afterwards every thread of the tile sees the complete x.
+template <int NPART>
 __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const float* __restrict__ wsm, uint32_t wsm_u32,
                                                  TcTile& t, float* y, int ys) {
   const int d = f.d, L = f.L;
@@ -147,7 +159,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
     const int K1 = round8(nin), N3 = round16(nout);
     const int base = f.off[k];
     // ---- layer 1: A = masked inputs (dims with mask == 1), zero padded to K1 --------------------------
-    for (int c0 = 0; c0 < K1; c0 += 8) {
+    for (int c0 = 8 * t.part; c0 < K1; c0 += 8 * NPART) {
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -163,7 +175,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
       tc_round_trip(t, [&] { tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, b_hi, b_lo, K1 / 8, 32, false); });
     }
     int off = base + 64 * K1;   // -> bias1
-    tc_hidden_epilogue(t, wsm + off);
+    tc_hidden_epilogue<NPART>(t, wsm + off);
     off += 32;
     // ---- hidden layers: block diagonal, s-net cols [0,16), t-net cols [16,32) --------------------------------
     for (int l = 0; l < L; ++l) {
@@ -172,7 +184,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
         tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, bs_hi, bs_lo, 2, 16, false);
         tc::mma_3xtf32(t.tmem + 80, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, 16, false);
       });
-      tc_hidden_epilogue(t, wsm + off + 1024);
+      tc_hidden_epilogue<NPART>(t, wsm + off + 1024);
       off += 1056;
     }
     // ---- output layer: log_s -> D cols [64, 64+N3), t -> D cols [96, 96+N3) ------------------------------------
@@ -187,7 +199,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
     const float* b3s = wsm + off + 64 * N3;
     const float* b3t = b3s + N3;
     // x = (z - t) * exp(-log_s), ld -= log_s on the dims with mask == 0   (networks.py:300-309)
-    for (int c0 = 0; c0 < nout; c0 += 8) {
+    for (int c0 = 8 * t.part; c0 < nout; c0 += 8 * NPART) {
       uint32_t rs[8], rt[8];
       tc::tmem_ld8(t.lane_tmem + 64 + c0, rs);
       tc::tmem_ld8(t.lane_tmem + 96 + c0, rt);
@@ -204,6 +216,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
         }
       }
     }
+    if (NPART > 1) tile_sync(t);   // the next block (or the caller) reads dims updated by the partner thread
   }
   return ld;
 }
@@ -218,22 +231,25 @@ static __device__ __noinline__ double tc_prior(const TargetSmem& tg, const float
   return prior_any(tg, row, false);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kTcMaxTiles * 128, 1)
+// shared-memory carve-up (bytes): [tc weights][target doubles][y: ntiles*d*128 f][zp: ntiles*d*128 f]
+//   [ldp: ntiles*NPART*128 f][flag: ntiles*128 i][mbar: 4 x 8][tmem base 8][red 32 x 4]
+template <int MODE, int NPART>
+__global__ void __launch_bounds__(kTcMaxTiles * 128 * NPART, 1)
 mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, const double* __restrict__ tgt_g,
                McmcParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int TPT = 128 * NPART;   // threads per tile
   const int d = f.d;
-  const int ntiles = blockDim.x >> 7;
-  // carve: [tc weights][target doubles][y: ntiles*d*128][zp: ntiles*d*128][mbar: 4 x 8B][tmem base][red 32]
+  const int ntiles = blockDim.x / TPT;
   float* wsm = reinterpret_cast<float*>(smem_raw);
   double* td_s = reinterpret_cast<double*>(smem_raw + (size_t)f.total_floats * 4);
   const int nd = target_doubles(td.d, td.n_params);
   float* y_all = reinterpret_cast<float*>(td_s + nd);
   float* zp_all = y_all + (size_t)ntiles * d * 128;
-  uint64_t* mbars = reinterpret_cast<uint64_t*>(zp_all + (size_t)ntiles * d * 128);
+  float* ldp_all = zp_all + (size_t)ntiles * d * 128;
+  int* flag_all = reinterpret_cast<int*>(ldp_all + (size_t)ntiles * NPART * 128);
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(flag_all + (size_t)ntiles * 128);
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(mbars + kTcMaxTiles);
-  unsigned int* red = tmem_base_s + 2;
 
   {
     const float4* s4 = reinterpret_cast<const float4*>(wglob);
@@ -245,8 +261,9 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   target_bind(tg, td, td_s);
 
   const int warp = threadIdx.x >> 5;
-  const int wg = warp >> 2;
-  const int wg_tid = threadIdx.x & 127;
+  const int tile = threadIdx.x / TPT;
+  const int tit = threadIdx.x % TPT;     // thread in tile
+  const int m = tit & 127;               // chain in tile = TMEM lane
   const uint32_t tmem_cols = ntiles <= 1 ? 128u : (ntiles == 2 ? 256u : 512u);
   if (warp == 0) tc::tmem_alloc(tmem_base_s, tmem_cols);
   if (threadIdx.x == 0) {
@@ -260,60 +277,83 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   tc::fence_after_sync();
 
   TcTile t;
-  t.tmem = *tmem_base_s + (uint32_t)wg * kTcColsPerTile;
-  t.lane_tmem = t.tmem + (((uint32_t)(warp & 3) * 32u) << 16);
-  t.mbar = &mbars[wg];
+  t.tmem = *tmem_base_s + (uint32_t)tile * kTcColsPerTile;
+  t.lane_tmem = t.tmem + (((uint32_t)((tit >> 5) & 3) * 32u) << 16);
+  t.mbar = &mbars[tile];
   t.phase = 0;
-  t.bar_id = 1 + wg;
-  t.issuer_warp = (warp & 3) == 0;
+  t.bar_id = 1 + tile;
+  t.bar_threads = TPT;
+  t.part = tit >> 7;
+  t.issuer_warp = (tit >> 5) == 0;
+  const int part = t.part;
   const uint32_t wsm_u32 = tc::smem_u32(wsm);
 
   const long long n = p.n;
-  const long long tile_base = ((long long)blockIdx.x * ntiles + wg) * 128;
-  const bool tile_active = tile_base < n;          // uniform over the warpgroup
-  const long long c = tile_base + wg_tid;
+  const long long tile_base = ((long long)blockIdx.x * ntiles + tile) * 128;
+  const bool tile_active = tile_base < n;          // uniform over the tile
+  const long long c = tile_base + m;
   const bool active = c < n;
-  float* y = y_all + (size_t)wg * d * 128 + wg_tid;
-  float* zp = zp_all + (size_t)wg * d * 128 + wg_tid;
+  float* y = y_all + (size_t)tile * d * 128 + m;
+  float* zp = zp_all + (size_t)tile * d * 128 + m;
+  float* ldp = ldp_all + (size_t)tile * NPART * 128 + m;
+  int* flag = flag_all + (size_t)tile * 128 + m;
   const unsigned int chain = (unsigned int)(p.chain_offset + (unsigned long long)c);
   unsigned int acc_total = 0, ncall_total = 0;
   float ld_cur = 0.f;
   double logl_cur = 0.0, logp_cur = 0.0;
-  if (active) {
+  if (active && part == 0) {
     ld_cur = p.logdet[c];
     logl_cur = p.logl[c];
     logp_cur = p.logp[c];
   }
+  const int nj = (d + 3) / 4;
+  // cooperative (persistent) mode: every CTA keeps its own copy of (scale, accept, reject); they stay identical
+  // because each is updated from the same grid-wide accept count after the per-step grid barrier
+  double co_scale = 0.0;
+  int co_accept = 0, co_reject = 0;
+  float* co_scale_s = reinterpret_cast<float*>(tmem_base_s + 1);
+  if (p.coop) {
+    co_scale = *reinterpret_cast<volatile double*>(&p.ctrl->scale);
+    co_accept = p.ctrl->accept;
+    co_reject = p.ctrl->reject;
+    if (threadIdx.x == 0) *co_scale_s = (float)co_scale;
+    __syncthreads();
+  }
 
   for (int s = p.s0 + 1; s <= p.s0 + p.nsteps; ++s) {
-    const float scale_f = (float)(*reinterpret_cast<volatile double*>(&p.ctrl->scale));
+    const float scale_f = p.coop ? *reinterpret_cast<volatile float*>(co_scale_s)
+                                 : (float)(*reinterpret_cast<volatile double*>(&p.ctrl->scale));
     const unsigned int step_abs = p.step_offset + (unsigned int)s;
     bool accept = false;
     unsigned int ncall = 0;
     if (tile_active) {
-      // ---- proposal ------------------------------------------------------------------------------------
+      // ---- proposal z' = z + scale * N(0, I): Philox block j (dims 4j..4j+3) belongs to thread j % NPART -------
       if (active) {
         // all loads of the current latent first (their latency overlaps), then the noise
-        for (int i = 0; i < d; ++i) y[i * 128] = p.z[(long long)i * n + c];
+        for (int j = part; j < nj; j += NPART)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i = 4 * j + q;
+            if (i < d) y[i * 128] = p.z[(long long)i * n + c];
+          }
         if (p.replay_normals) {
           const float* nr = p.replay_normals + ((long long)(s - 1) * n + c) * d;
-          for (int i = 0; i < d; ++i) {
-            float v = __fadd_rn(y[i * 128], __fmul_rn(nr[i], scale_f));
-            y[i * 128] = v;
-            zp[i * 128] = v;
-          }
-        } else {
-          const int nj = (d + 3) / 4;
-          for (int j = 0; j < nj; j += 2) {   // two Philox blocks per iteration: independent chains for ILP
-            float nrm[8];
-            uint4 r0 = philox4x32_10(j, step_abs, chain, kTagNormal, p.seed_lo, p.seed_hi);
-            uint4 r1 = philox4x32_10(j + 1, step_abs, chain, kTagNormal, p.seed_lo, p.seed_hi);
-            box_muller(r0.x, r0.y, nrm[0], nrm[1]);
-            box_muller(r0.z, r0.w, nrm[2], nrm[3]);
-            box_muller(r1.x, r1.y, nrm[4], nrm[5]);
-            box_muller(r1.z, r1.w, nrm[6], nrm[7]);
+          for (int j = part; j < nj; j += NPART)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < 4; ++q) {
+              const int i = 4 * j + q;
+              if (i < d) {
+                float v = __fadd_rn(y[i * 128], __fmul_rn(nr[i], scale_f));
+                y[i * 128] = v;
+                zp[i * 128] = v;
+              }
+            }
+        } else {
+          for (int j = part; j < nj; j += NPART) {
+            float nrm[4];
+            philox_normals4(j, step_abs, chain, kTagNormal, p.seed_lo, p.seed_hi, nrm);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
               const int i = 4 * j + q;
               if (i < d) {
                 float v = __fadd_rn(y[i * 128], __fmul_rn(nrm[q], scale_f));
@@ -325,12 +365,23 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
           }
         }
       } else {
-        for (int i = 0; i < d; ++i) y[i * 128] = 0.f;
+        for (int j = part; j < nj; j += NPART)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (4 * j + q < d) y[(4 * j + q) * 128] = 0.f;
       }
       __syncwarp();
-      // ---- flow inverse on the tensor cores (all 128 threads of the tile, converged) -------------------------
-      const float ld_prop = tc_flow_inverse(f, wsm, wsm_u32, t, y, 128);
-      if (active) {
+      if (NPART > 1) tile_sync(t);   // layer 1 reads dims written by the partner thread
+      // ---- flow inverse on the tensor cores (all threads of the tile, converged) ----------------------------------
+      const float ld_part = tc_flow_inverse<NPART>(f, wsm, wsm_u32, t, y, 128);
+      if (NPART > 1) {
+        ldp[part * 128] = ld_part;
+        tile_sync(t);
+      }
+      // ---- accept / reject: thread 0 of the chain --------------------------------------------------------------------
+      if (active && part == 0) {
+        float ld_prop = ld_part;
+        if (NPART > 1) ld_prop = ld_part + ldp[128];
         float u01;
         if (p.replay_uniforms) {
           u01 = p.replay_uniforms[(long long)(s - 1) * n + c];
@@ -362,37 +413,70 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
           accept = (double)u01 < ratio;
         }
         if (accept) {
-          for (int i = 0; i < d; ++i) {
-            p.z[(long long)i * n + c] = zp[i * 128];
-            p.x[(long long)i * n + c] = y[i * 128];
-          }
           ld_cur = ld_prop;
           logl_cur = lp;
           logp_cur = logp_prop;
         }
+        if (NPART > 1) *flag = accept ? 1 : 0;
+        if (p.trace_z) p.trace_logl[(long long)s * n + c] = logl_cur;
+      }
+      __syncwarp();
+      bool acc_chain = accept;
+      if (NPART > 1) {
+        tile_sync(t);
+        acc_chain = active && (*flag != 0);
+      }
+      // ---- state / trace update, dims dealt to the chain's threads (sampler.py:433-444) -------------------------------
+      if (active) {
+        if (acc_chain) {
+          for (int i = part; i < d; i += NPART) {
+            p.z[(long long)i * n + c] = zp[i * 128];
+            p.x[(long long)i * n + c] = y[i * 128];
+          }
+        }
         if (p.trace_z) {
           float* tz = p.trace_z + (long long)s * d * n + c;
           float* tx = p.trace_x + (long long)s * d * n + c;
-          if (accept) {
-            for (int i = 0; i < d; ++i) {
+          if (acc_chain) {
+            for (int i = part; i < d; i += NPART) {
               tz[(long long)i * n] = zp[i * 128];
               tx[(long long)i * n] = y[i * 128];
             }
           } else {
-            for (int i = 0; i < d; ++i) {
+            for (int i = part; i < d; i += NPART) {
               tz[(long long)i * n] = p.z[(long long)i * n + c];
               tx[(long long)i * n] = p.x[(long long)i * n + c];
             }
           }
-          p.trace_logl[(long long)s * n + c] = logl_cur;
         }
       }
-      __syncwarp();
+      if (NPART > 1) tile_sync(t);   // y / zp / flag are rewritten by the next step
     }
     acc_total += accept ? 1u : 0u;
     ncall_total += ncall;
 
-    if (p.dynamic) {
+    if (p.coop) {
+      // grid barrier carrying the accept count of this step (sampler.py:418-430).  All CTAs are co-resident
+      // (cooperative launch).  step_counts[s] was zeroed by the host; `arrive` counts CTA arrivals monotonically.
+      unsigned int blk = block_count(accept);
+      if (threadIdx.x == 0) {
+        const int si = s - p.s0 - 1;
+        if (blk) atomicAdd(&p.step_counts[si], blk);
+        __threadfence();
+        atomicAdd(&p.ctrl->ticket, 1u);
+        const unsigned int target = (unsigned int)(si + 1) * gridDim.x;
+        while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < target) __nanosleep(20);
+        __threadfence();
+        const unsigned int na = *reinterpret_cast<volatile unsigned int*>(&p.step_counts[si]);
+        if (p.dynamic) {
+          if (2ull * na > (unsigned long long)n) co_accept += 1; else co_reject += 1;
+          if (co_accept > co_reject) co_scale *= exp(1.0 / (1 + co_accept));
+          if (co_accept < co_reject) co_scale /= exp(1.0 / (1 + co_reject));
+          *co_scale_s = (float)co_scale;
+        }
+      }
+      __syncthreads();
+    } else if (p.dynamic) {
       unsigned int blk = block_count(accept);
       if (threadIdx.x == 0) {
         if (blk) atomicAdd(&p.ctrl->step_acc, blk);
@@ -414,14 +498,20 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       }
     }
   }
-  if (active) {
+  if (active && part == 0) {
     p.logdet[c] = ld_cur;
     p.logl[c] = logl_cur;
     p.logp[c] = logp_cur;
   }
-  unsigned int ta = block_sum_u32(acc_total, red);
-  unsigned int tcall = block_sum_u32(ncall_total, red);
-  if (threadIdx.x == 0) {
+  if (p.coop && blockIdx.x == 0 && threadIdx.x == 0) {   // publish the final scale bookkeeping
+    p.ctrl->scale = co_scale;
+    p.ctrl->accept = co_accept;
+    p.ctrl->reject = co_reject;
+  }
+  // totals: one atomic per warp (the counts of non-zero lanes only)
+  unsigned int ta = __reduce_add_sync(0xffffffffu, acc_total);
+  unsigned int tcall = __reduce_add_sync(0xffffffffu, ncall_total);
+  if ((threadIdx.x & 31) == 0) {
     if (ta) atomicAdd(&p.ctrl->naccept, (unsigned long long)ta);
     if (tcall) atomicAdd(&p.ctrl->ncall, (unsigned long long)tcall);
   }
@@ -430,9 +520,9 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   if (warp == 0) tc::tmem_dealloc(*tmem_base_s, tmem_cols);
 }
 
-__host__ inline size_t tc_smem_bytes(const TcFlowDesc& f, int tdoubles, int ntiles) {
-  return (size_t)f.total_floats * 4 + (size_t)tdoubles * 8 + 2 * (size_t)ntiles * f.d * 128 * 4 + kTcMaxTiles * 8 + 8 +
-         32 * 4;
+__host__ inline size_t tc_smem_bytes(const TcFlowDesc& f, int tdoubles, int ntiles, int npart) {
+  return (size_t)f.total_floats * 4 + (size_t)tdoubles * 8 + 2 * (size_t)ntiles * f.d * 128 * 4 +
+         (size_t)ntiles * npart * 128 * 4 + (size_t)ntiles * 128 * 4 + kTcMaxTiles * 8 + 8 + 32 * 4;
 }
 
 }  // namespace nnb
