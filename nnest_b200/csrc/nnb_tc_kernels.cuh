@@ -151,7 +151,7 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float*
 // afterwards every thread of the tile sees the complete x.
 template <int NPART>
 __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const float* __restrict__ wsm, uint32_t wsm_u32,
-                                                 TcTile& t, float* y, int ys) {
+                                                 TcTile& t, float* y, int ys, float* ld_slot) {
   const int d = f.d, L = f.L;
   float ld = 0.f;
   for (int k = f.B - 1; k >= 0; --k) {
@@ -216,7 +216,10 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
         }
       }
     }
-    if (NPART > 1) tile_sync(t);   // the next block (or the caller) reads dims updated by the partner thread
+    if (NPART > 1) {
+      if (k == 0) *ld_slot = ld;   // the chain's threads exchange their log-det shares through shared memory
+      tile_sync(t);                // the next block (or the caller) reads dims updated by the partner thread
+    }
   }
   return ld;
 }
@@ -232,7 +235,7 @@ static __device__ __noinline__ double tc_prior(const TargetSmem& tg, const float
 }
 
 // shared-memory carve-up (bytes): [tc weights][target doubles][y: ntiles*d*128 f][zp: ntiles*d*128 f]
-//   [ldp: ntiles*NPART*128 f][flag: ntiles*128 i][mbar: 4 x 8][tmem base 8][red 32 x 4]
+//   [nz: ntiles*d*128 f][ldp: ntiles*NPART*128 f][flag: ntiles*128 i][mbar: 4 x 8][tmem base 8][red 32 x 4]
 template <int MODE, int NPART>
 __global__ void __launch_bounds__(kTcMaxTiles * 128 * NPART, 1)
 mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, const double* __restrict__ tgt_g,
@@ -246,7 +249,8 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   const int nd = target_doubles(td.d, td.n_params);
   float* y_all = reinterpret_cast<float*>(td_s + nd);
   float* zp_all = y_all + (size_t)ntiles * d * 128;
-  float* ldp_all = zp_all + (size_t)ntiles * d * 128;
+  float* nz_all = zp_all + (size_t)ntiles * d * 128;
+  float* ldp_all = nz_all + (size_t)ntiles * d * 128;
   int* flag_all = reinterpret_cast<int*>(ldp_all + (size_t)ntiles * NPART * 128);
   uint64_t* mbars = reinterpret_cast<uint64_t*>(flag_all + (size_t)ntiles * 128);
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(mbars + kTcMaxTiles);
@@ -307,6 +311,8 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
     logp_cur = p.logp[c];
   }
   const int nj = (d + 3) / 4;
+  const size_t ns = (size_t)n;
+  float* nz = nz_all + (size_t)tile * d * 128 + m;
   // cooperative (persistent) mode: every CTA keeps its own copy of (scale, accept, reject); they stay identical
   // because each is updated from the same grid-wide accept count after the per-step grid barrier
   double co_scale = 0.0;
@@ -320,75 +326,73 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
     __syncthreads();
   }
 
+  // raw N(0,1) draws of Philox blocks j = j0, j0 + jstep, ... < j1 of step `step_abs` into nz (and the dump buffer)
+  auto gen_normals = [&](int j0, int j1, int jstep, unsigned int step_abs, int sidx) {
+    for (int j = j0; j < j1; j += jstep) {
+      float nrm[4];
+      philox_normals4(j, step_abs, chain, kTagNormal, p.seed_lo, p.seed_hi, nrm);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = 4 * j + q;
+        if (i < d) {
+          nz[i * 128] = nrm[q];
+          if (p.dump_normals) p.dump_normals[((size_t)sidx * ns + (size_t)c) * d + i] = nrm[q];
+        }
+      }
+    }
+  };
+  // The noise of step s+1 does not depend on the adapted scale, so it is produced while step s finishes: jc blocks
+  // by the chain's second thread during the accept phase of the first, the rest by both after the CTA has arrived
+  // at the grid barrier (overlapping its latency).
+  const int jc = NPART > 1 ? (3 * nj + 4) / 8 : 0;
+  const bool philox = p.replay_normals == nullptr;
+  if (tile_active && active && philox) gen_normals(part, nj, NPART, p.step_offset + (unsigned int)(p.s0 + 1), p.s0);
+
   for (int s = p.s0 + 1; s <= p.s0 + p.nsteps; ++s) {
     const float scale_f = p.coop ? *reinterpret_cast<volatile float*>(co_scale_s)
                                  : (float)(*reinterpret_cast<volatile double*>(&p.ctrl->scale));
     const unsigned int step_abs = p.step_offset + (unsigned int)s;
+    const bool more = s < p.s0 + p.nsteps;
     bool accept = false;
     unsigned int ncall = 0;
+    bool acc_chain = false;
     if (tile_active) {
-      // ---- proposal z' = z + scale * N(0, I): Philox block j (dims 4j..4j+3) belongs to thread j % NPART -------
+      if (NPART > 1) tile_sync(t);   // nz complete (written by both threads of the chain)
+      // ---- proposal z' = z + scale * N(0, I) (sampler.py:310-316), dims dealt to the chain's threads ----------------
       if (active) {
-        // all loads of the current latent first (their latency overlaps), then the noise
-        for (int j = part; j < nj; j += NPART)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int i = 4 * j + q;
-            if (i < d) y[i * 128] = p.z[(long long)i * n + c];
+        const float* pz = p.z + (size_t)c + (size_t)part * ns;
+        if (philox) {
+          for (int i = part; i < d; i += NPART, pz += NPART * ns) {
+            float v = __fadd_rn(*pz, __fmul_rn(nz[i * 128], scale_f));
+            y[i * 128] = v;
+            zp[i * 128] = v;
           }
-        if (p.replay_normals) {
-          const float* nr = p.replay_normals + ((long long)(s - 1) * n + c) * d;
-          for (int j = part; j < nj; j += NPART)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int i = 4 * j + q;
-              if (i < d) {
-                float v = __fadd_rn(y[i * 128], __fmul_rn(nr[i], scale_f));
-                y[i * 128] = v;
-                zp[i * 128] = v;
-              }
-            }
         } else {
-          for (int j = part; j < nj; j += NPART) {
-            float nrm[4];
-            philox_normals4(j, step_abs, chain, kTagNormal, p.seed_lo, p.seed_hi, nrm);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int i = 4 * j + q;
-              if (i < d) {
-                float v = __fadd_rn(y[i * 128], __fmul_rn(nrm[q], scale_f));
-                y[i * 128] = v;
-                zp[i * 128] = v;
-                if (p.dump_normals) p.dump_normals[((long long)(s - 1) * n + c) * d + i] = nrm[q];
-              }
-            }
+          const float* nr = p.replay_normals + ((size_t)(s - 1) * ns + (size_t)c) * d;
+          for (int i = part; i < d; i += NPART, pz += NPART * ns) {
+            float v = __fadd_rn(*pz, __fmul_rn(nr[i], scale_f));
+            y[i * 128] = v;
+            zp[i * 128] = v;
           }
         }
       } else {
-        for (int j = part; j < nj; j += NPART)
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (4 * j + q < d) y[(4 * j + q) * 128] = 0.f;
+        for (int i = part; i < d; i += NPART) y[i * 128] = 0.f;
       }
       __syncwarp();
       if (NPART > 1) tile_sync(t);   // layer 1 reads dims written by the partner thread
       // ---- flow inverse on the tensor cores (all threads of the tile, converged) ----------------------------------
-      const float ld_part = tc_flow_inverse<NPART>(f, wsm, wsm_u32, t, y, 128);
-      if (NPART > 1) {
-        ldp[part * 128] = ld_part;
-        tile_sync(t);
-      }
-      // ---- accept / reject: thread 0 of the chain --------------------------------------------------------------------
+      const float ld_part = tc_flow_inverse<NPART>(f, wsm, wsm_u32, t, y, 128, ldp + part * 128);
+      // ---- accept / reject: thread 0 of the chain; thread 1 starts on the next step's noise -------------------------
       if (active && part == 0) {
         float ld_prop = ld_part;
         if (NPART > 1) ld_prop = ld_part + ldp[128];
         float u01;
         if (p.replay_uniforms) {
-          u01 = p.replay_uniforms[(long long)(s - 1) * n + c];
+          u01 = p.replay_uniforms[(size_t)(s - 1) * ns + (size_t)c];
         } else {
           uint4 r = philox4x32_10(0u, step_abs, chain, kTagUniform, p.seed_lo, p.seed_hi);
           u01 = uniform01(r.x);
-          if (p.dump_uniforms) p.dump_uniforms[(long long)(s - 1) * n + c] = u01;
+          if (p.dump_uniforms) p.dump_uniforms[(size_t)(s - 1) * ns + (size_t)c] = u01;
         }
         double lp = 0.0, logp_prop = 0.0;
         if (MODE == NNB_MODE_HARD) {
@@ -418,64 +422,59 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
           logp_cur = logp_prop;
         }
         if (NPART > 1) *flag = accept ? 1 : 0;
-        if (p.trace_z) p.trace_logl[(long long)s * n + c] = logl_cur;
+        if (p.trace_z) p.trace_logl[(size_t)s * ns + (size_t)c] = logl_cur;
+      } else if (NPART > 1 && active && more && philox) {
+        gen_normals(0, jc, 1, step_abs + 1u, s);
       }
       __syncwarp();
-      bool acc_chain = accept;
+      acc_chain = accept;
       if (NPART > 1) {
         tile_sync(t);
         acc_chain = active && (*flag != 0);
       }
       // ---- state / trace update, dims dealt to the chain's threads (sampler.py:433-444) -------------------------------
       if (active) {
+        float* pz = p.z + (size_t)c + (size_t)part * ns;
+        float* px = p.x + (size_t)c + (size_t)part * ns;
         if (acc_chain) {
-          for (int i = part; i < d; i += NPART) {
-            p.z[(long long)i * n + c] = zp[i * 128];
-            p.x[(long long)i * n + c] = y[i * 128];
+          for (int i = part; i < d; i += NPART, pz += NPART * ns, px += NPART * ns) {
+            *pz = zp[i * 128];
+            *px = y[i * 128];
           }
         }
         if (p.trace_z) {
-          float* tz = p.trace_z + (long long)s * d * n + c;
-          float* tx = p.trace_x + (long long)s * d * n + c;
+          float* tz = p.trace_z + (size_t)s * d * ns + (size_t)c + (size_t)part * ns;
+          float* tx = p.trace_x + (size_t)s * d * ns + (size_t)c + (size_t)part * ns;
           if (acc_chain) {
-            for (int i = part; i < d; i += NPART) {
-              tz[(long long)i * n] = zp[i * 128];
-              tx[(long long)i * n] = y[i * 128];
+            for (int i = part; i < d; i += NPART, tz += NPART * ns, tx += NPART * ns) {
+              *tz = zp[i * 128];
+              *tx = y[i * 128];
             }
           } else {
-            for (int i = part; i < d; i += NPART) {
-              tz[(long long)i * n] = p.z[(long long)i * n + c];
-              tx[(long long)i * n] = p.x[(long long)i * n + c];
+            pz = p.z + (size_t)c + (size_t)part * ns;
+            px = p.x + (size_t)c + (size_t)part * ns;
+            for (int i = part; i < d; i += NPART, tz += NPART * ns, tx += NPART * ns, pz += NPART * ns, px += NPART * ns) {
+              *tz = *pz;
+              *tx = *px;
             }
           }
         }
       }
-      if (NPART > 1) tile_sync(t);   // y / zp / flag are rewritten by the next step
     }
     acc_total += accept ? 1u : 0u;
     ncall_total += ncall;
 
+    // ---- global accept count of the step -> scale adaptation (sampler.py:418-430) ------------------------------------
+    const int si = s - p.s0 - 1;
     if (p.coop) {
-      // grid barrier carrying the accept count of this step (sampler.py:418-430).  All CTAs are co-resident
-      // (cooperative launch).  step_counts[s] was zeroed by the host; `arrive` counts CTA arrivals monotonically.
+      // arrive at the grid barrier (all CTAs are co-resident: cooperative launch).  step_counts[si] was zeroed by
+      // the host; `ticket` counts CTA arrivals monotonically.
       unsigned int blk = block_count(accept);
       if (threadIdx.x == 0) {
-        const int si = s - p.s0 - 1;
         if (blk) atomicAdd(&p.step_counts[si], blk);
         __threadfence();
         atomicAdd(&p.ctrl->ticket, 1u);
-        const unsigned int target = (unsigned int)(si + 1) * gridDim.x;
-        while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < target) __nanosleep(20);
-        __threadfence();
-        const unsigned int na = *reinterpret_cast<volatile unsigned int*>(&p.step_counts[si]);
-        if (p.dynamic) {
-          if (2ull * na > (unsigned long long)n) co_accept += 1; else co_reject += 1;
-          if (co_accept > co_reject) co_scale *= exp(1.0 / (1 + co_accept));
-          if (co_accept < co_reject) co_scale /= exp(1.0 / (1 + co_reject));
-          *co_scale_s = (float)co_scale;
-        }
       }
-      __syncthreads();
     } else if (p.dynamic) {
       unsigned int blk = block_count(accept);
       if (threadIdx.x == 0) {
@@ -496,6 +495,23 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
           p.ctrl->scale = sc;
         }
       }
+    }
+    // ---- rest of the next step's noise (overlaps the grid barrier) --------------------------------------------------------
+    if (tile_active && active && more && philox) gen_normals(jc + part, nj, NPART, step_abs + 1u, s);
+    if (p.coop) {
+      if (threadIdx.x == 0) {
+        const unsigned int target = (unsigned int)(si + 1) * gridDim.x;
+        while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < target) __nanosleep(20);
+        __threadfence();
+        const unsigned int na = *reinterpret_cast<volatile unsigned int*>(&p.step_counts[si]);
+        if (p.dynamic) {
+          if (2ull * na > (unsigned long long)n) co_accept += 1; else co_reject += 1;
+          if (co_accept > co_reject) co_scale *= exp(1.0 / (1 + co_accept));
+          if (co_accept < co_reject) co_scale /= exp(1.0 / (1 + co_reject));
+          *co_scale_s = (float)co_scale;
+        }
+      }
+      __syncthreads();
     }
   }
   if (active && part == 0) {
@@ -521,7 +537,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
 }
 
 __host__ inline size_t tc_smem_bytes(const TcFlowDesc& f, int tdoubles, int ntiles, int npart) {
-  return (size_t)f.total_floats * 4 + (size_t)tdoubles * 8 + 2 * (size_t)ntiles * f.d * 128 * 4 +
+  return (size_t)f.total_floats * 4 + (size_t)tdoubles * 8 + 3 * (size_t)ntiles * f.d * 128 * 4 +
          (size_t)ntiles * npart * 128 * 4 + (size_t)ntiles * 128 * 4 + kTcMaxTiles * 8 + 8 + 32 * 4;
 }
 
