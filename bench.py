@@ -258,11 +258,20 @@ def run_gpu(args, wl):
         init_kw = dict(init_z=torch.from_numpy(np.ascontiguousarray(prob['init_z'].T)).cuda())
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device='cuda')   # > 126 MB L2
 
-    def one_refill(it):
+    kernel_impl = {'auto': L.NNB_IMPL_AUTO, 'ffma': L.NNB_IMPL_FFMA, 'tcgen05': L.NNB_IMPL_TCGEN05}[args.kernel]
+    run_ev = []
+
+    def one_refill(it, timed=False):
         st, _, _ = eng.mcmc_init(n, seed=args.seed, chain_offset=chain_offset, **init_kw)
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
         out = eng.mcmc_run(st, S, mode=mode, loglstar=prob['loglstar'], step_size=step_size,
                            dynamic_step_size=wl['dynamic'], seed=args.seed, chain_offset=chain_offset,
-                           step_offset=it * S)
+                           step_offset=it * S, impl=kernel_impl)
+        if timed:
+            b.record()
+            run_ev.append((a, b))
         return st, out
 
     def barrier():
@@ -282,7 +291,7 @@ def run_gpu(args, wl):
     for it in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (not inside the event pair)
         ev[it][0].record()
-        st, out = one_refill(args.warmup + it)
+        st, out = one_refill(args.warmup + it, timed=True)
         ev[it][1].record()
         naccept += out['naccept']
         ncall += out['ncall']
@@ -319,7 +328,8 @@ def run_gpu(args, wl):
         st, _, _ = eng.mcmc_init(n, seed=args.seed, chain_offset=chain_offset, **kw)
         h_first.copy_(st.x, non_blocking=True)
         eng.mcmc_run(st, S, mode=mode, loglstar=prob['loglstar'], step_size=step_size,
-                     dynamic_step_size=wl['dynamic'], seed=args.seed, chain_offset=chain_offset, step_offset=it * S)
+                     dynamic_step_size=wl['dynamic'], seed=args.seed, chain_offset=chain_offset, step_offset=it * S,
+                     impl=kernel_impl)
         h_last.copy_(st.x, non_blocking=True)
         h_logl.copy_(st.logl, non_blocking=True)
         torch.cuda.synchronize()
@@ -343,19 +353,31 @@ def run_gpu(args, wl):
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
-        # dominant kernel = mcmc_kernel; all launches of one step are that kernel (+1 init kernel)
-        per_gpu_props = n * S * args.steps
+        # dominant kernel = the fused MCMC step kernel (mcmc_tc_kernel / mcmc_kernel): >99% of the step's device time
+        # (profiles/).  Its launches are timed live with CUDA events around nnb_mcmc_run on the launching stream.
+        run_ms = float(np.mean([a.elapsed_time(b) for a, b in run_ev]))
+        kernel_launches = out['launches']
         flops = flow_flops_per_proposal(d)
-        achieved_tflops = per_gpu_props * flops / (total_ms * 1e-3) / 1e12
-        fp32_peak = 148 * 128 * 2 * (clk['sm_max_mhz'] or 1965.0) * 1e6 / 1e12 if clk else None
+        used_tc = out['impl'] == L.NNB_IMPL_TCGEN05
+        achieved_tflops = n * S * flops / (run_ms * 1e-3) / 1e12           # algorithmic flops of one refill / its duration
+        fp32_peak = 148 * 128 * 2 * ((clk or {}).get('sm_max_mhz') or 1965.0) * 1e6 / 1e12
+        if used_tc and peaks.get('bf16_tflops'):
+            peak, peak_src = peaks['bf16_tflops'] / 2.0, 'tf32 dense = 1/2 of the measured bf16 burst peak (MEASURED_PEAKS.json)'
+        elif used_tc:
+            peak, peak_src = 1590.0 / 2.0, 'tf32 dense = 1/2 of the fallback bf16 peak (B200_PROFILING.md)'
+        else:
+            peak, peak_src = fp32_peak, 'FP32 FMA pipe: 148 SMs x 128 lanes x 2 x max SM clock (not in MEASURED_PEAKS.json)'
         roofline = {
-            'bound': 'fp32-fma', 'achieved': achieved_tflops, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-            'frac': achieved_tflops / fp32_peak if fp32_peak else None, 'traffic': None,
-            'note': 'algorithmic flops = dense nn.Linear count of one flow inverse per proposal (4*B*H*(2d+L*H) = %d); '
-                    'peak = 148 SMs x 128 FFMA/clk x 2 x max SM clock (FP32 pipe; MEASURED_PEAKS.json has no FP32 '
-                    'figure); vs measured bf16 tensor peak %.1f TF/s the fraction is %.4f'
-                    % (flops, peaks.get('bf16_tflops', float('nan')),
-                       achieved_tflops / peaks['bf16_tflops'] if peaks.get('bf16_tflops') else float('nan')),
+            'bound': 'tensor' if used_tc else 'fp32-fma', 'achieved': achieved_tflops, 'peak': peak, 'unit': 'TFLOP/s',
+            'frac': achieved_tflops / peak, 'traffic': 17.3e6 * (n * S) / (65536.0 * 150) if used_tc else None,
+            'kernel': 'mcmc_tc_kernel<MODE,2> (tcgen05 3xTF32)' if used_tc else 'mcmc_kernel<16,MODE> (FP32 FMA)',
+            'launches_per_step': kernel_launches, 'launch_ms': run_ms / max(kernel_launches, 1),
+            'algorithmic_flop_per_proposal': flops, 'peak_source': peak_src,
+            'frac_of_fp32_fma_peak': achieved_tflops / fp32_peak,
+            'note': 'algorithmic flops = dense nn.Linear count of one flow inverse per proposal, 4*B*H*(2d+L*H); the '
+                    'tensor pipe executes them as 3xTF32 (x3) on mask-reduced operands (x0.6).  The kernel is bound by '
+                    'the per-element epilogues (tanh/exp/RNG/split on the FP32+ALU+MUFU pipes: ncu issue slots 57% busy, '
+                    'tensor pipe 5%), not by the MMA rate; traffic = ncu dram bytes of one refill launch scaled to this size',
         }
         cpu = cpu_baseline_quick(wl) if world == 1 and not args.no_cpu_baseline else None
         print(json.dumps({
@@ -365,6 +387,7 @@ def run_gpu(args, wl):
             'config': {'workload': args.workload + ': ' + wl['desc'], 'chains_per_gpu': n, 'x_dim': d,
                        'mcmc_steps': S, 'hidden_dim': HIDDEN, 'num_blocks': BLOCKS, 'num_layers': LAYERS,
                        'flow_weights': 'random init (nn.Linear default)', 'l2': 'flushed between timed steps',
+                       'kernel': 'tcgen05' if out['impl'] == L.NNB_IMPL_TCGEN05 else 'ffma',
                        'accept_rate': naccept / float(n * S * args.steps),
                        'loglike_calls_per_proposal': ncall / float(n * S * args.steps)},
             'e2e': {'value': e2e_value, 'unit': 'proposals/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
@@ -383,6 +406,7 @@ def main():
     ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--kernel', default='auto', choices=['auto', 'ffma', 'tcgen05'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

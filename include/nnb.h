@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 2
+#define NNB_ABI_VERSION 3
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -196,6 +196,8 @@ typedef struct {
   int64_t* ncall_out;    /* likelihood calls (sampler.py:363,397) */
   int64_t* naccept_out;  /* accepted proposals (total_accepted, sampler.py:418-420) */
   int impl;              /* NNB_IMPL_* */
+  int64_t* launches_out; /* [host] kernels launched by this call (1 when the persistent cooperative kernel ran) */
+  int* impl_out;         /* [host] NNB_IMPL_FFMA or NNB_IMPL_TCGEN05: the variant that ran */
 } nnb_mcmc_args;
 
 int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream); /* synchronous at return */

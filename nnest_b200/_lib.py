@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libnnb.so')
 
-NNB_ABI_VERSION = 2
+NNB_ABI_VERSION = 3
 NNB_MAX_DIM = 128
 NNB_MAX_BLOCKS = 16
 
@@ -46,7 +46,7 @@ class nnb_mcmc_args(C.Structure):
                 ('logp', C.c_void_p), ('trace_x', C.c_void_p), ('trace_z', C.c_void_p), ('trace_logl', C.c_void_p),
                 ('replay_normals', C.c_void_p), ('replay_uniforms', C.c_void_p), ('dump_normals', C.c_void_p),
                 ('dump_uniforms', C.c_void_p), ('scale_out', _dp), ('ncall_out', _ip), ('naccept_out', _ip),
-                ('impl', C.c_int)]
+                ('impl', C.c_int), ('launches_out', _ip), ('impl_out', C.POINTER(C.c_int))]
 
 
 # name -> (restype, argtypes); every symbol include/nnb.h declares

@@ -352,6 +352,8 @@ extern "C" int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream)
   if (a->scale_out) *a->scale_out = h->h_ctrl->scale;
   if (a->ncall_out) *a->ncall_out = (int64_t)h->h_ctrl->ncall;
   if (a->naccept_out) *a->naccept_out = (int64_t)h->h_ctrl->naccept;
+  if (a->launches_out) *a->launches_out = a->steps > 0 ? h->last_launches : 0;
+  if (a->impl_out) *a->impl_out = use_tc ? NNB_IMPL_TCGEN05 : NNB_IMPL_FFMA;
   return NNB_OK;
 }
 

@@ -22,6 +22,7 @@ struct nnb_handle {
   unsigned int* d_step_counts = nullptr;   // workspace of the cooperative kernel
   int step_counts_cap = 0;
   int coop_supported = 0;
+  long long last_launches = 0;             // kernels launched by the last nnb_mcmc_run
   Ctrl* d_ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;  // pinned
   std::string err;

@@ -92,6 +92,7 @@ static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t s
     p.s0 = 0; p.nsteps = steps; p.coop = 1; p.step_counts = h->d_step_counts;
     void* args[] = {(void*)&h->tcflow, (void*)&h->d_weights_tc, (void*)&h->tdesc, (void*)&h->d_target, (void*)&p};
     NNB_CUDA(h, cudaLaunchCooperativeKernel((const void*)mcmc_tc_kernel<MODE, NPART>, dim3(grid), dim3(block), args, sm, st));
+    h->last_launches = 1;
     return NNB_OK;
   }
   p.coop = 0; p.step_counts = nullptr;
@@ -105,6 +106,7 @@ static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t s
     mcmc_tc_kernel<MODE, NPART><<<grid, block, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p);
   }
   NNB_CUDA(h, cudaGetLastError());
+  h->last_launches = p.dynamic ? steps : 1;
   return NNB_OK;
 }
 

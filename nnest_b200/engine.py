@@ -219,9 +219,10 @@ class Engine(object):
             out['normals'] = torch.empty((steps, n, d), dtype=torch.float32, device=self.device)
             out['uniforms'] = torch.empty((steps, n), dtype=torch.float32, device=self.device)
             a.dump_normals, a.dump_uniforms = out['normals'].data_ptr(), out['uniforms'].data_ptr()
-        scale, ncall, nacc = C.c_double(0), C.c_int64(0), C.c_int64(0)
+        scale, ncall, nacc, nl, impl_ran = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int(0)
         a.scale_out, a.ncall_out, a.naccept_out = C.pointer(scale), C.pointer(ncall), C.pointer(nacc)
+        a.launches_out, a.impl_out = C.pointer(nl), C.pointer(impl_ran)
         self._check(self.lib.nnb_mcmc_run(self.h, C.byref(a), _stream()))
-        self.gpu_launches += (steps if dynamic_step_size else (1 if steps else 0))
-        out.update(scale=scale.value, ncall=ncall.value, naccept=nacc.value)
+        self.gpu_launches += nl.value
+        out.update(scale=scale.value, ncall=ncall.value, naccept=nacc.value, launches=nl.value, impl=impl_ran.value)
         return out
