@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 3
+#define NNB_ABI_VERSION 4
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -212,6 +212,26 @@ int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream); /* synchr
  */
 int64_t nnb_consume_scan(const float* first, const float* last, const double* logl_last, int64_t n_chains,
                          int d, double loglstar, int64_t* nb);
+
+/*
+ * Many nested-sampling iterations at once (replaces a run of iterations of the loop nnest/nested.py:269-471 in
+ * strategy 'mcmc' between two refills / retrains / checkpoints).  Host-side and exact.  Starting from the live
+ * likelihoods active_logl [host] (nlive, NOT modified) and the consume pointer *nb into the current batch, it
+ * repeats up to max_iters times:
+ *     worst = first index of min(active_logl)               (np.argmin, nested.py:272)
+ *     scan the batch from *nb as nnb_consume_scan does      (nested.py:429-439)
+ *     on success the live point `worst` takes the end loglike of the chain found
+ * and records for every successful iteration k: worst_out[k], chain_out[k], loglstar_out[k] (the likelihood of the
+ * worst point = the constraint of that iteration), maxlogl_out[k] (np.max(active_logl) after the replacement,
+ * nested.py:462) and prev_out[k] (the earlier iteration of this call that wrote the slot `worst`, or -1: tells which
+ * physical point is saved as dead point, nested.py:288-290).  It stops early when the batch is exhausted without a
+ * usable chain: then *exhausted = 1 and worst_out[K] / loglstar_out[K] describe that unfinished iteration (its evidence
+ * update is due, nested.py:280-293).  Output arrays need max_iters + 1 entries.  Returns K, or a negative error code.
+ */
+int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, const float* first, const float* last,
+                       const double* logl_last, int64_t n_chains, int d, int64_t* nb, int64_t max_iters,
+                       int64_t* worst_out, int64_t* chain_out, int64_t* prev_out, double* loglstar_out,
+                       double* maxlogl_out, int* exhausted);
 
 #ifdef __cplusplus
 }

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -369,4 +370,74 @@ extern "C" int64_t nnb_consume_scan(const float* first, const float* last, const
     if (all_differ && logl_last[ib] > loglstar) return ib;
   }
   return -1;
+}
+
+// Min-heap over (logl, index): the top is np.argmin's answer (first index among equal minima).
+namespace {
+struct LiveHeap {
+  std::vector<double> key;
+  std::vector<int64_t> heap;   // heap of slot indices
+  explicit LiveHeap(const double* logl, int64_t n) : key(logl, logl + n), heap((size_t)n) {
+    for (int64_t i = 0; i < n; ++i) heap[(size_t)i] = i;
+    for (int64_t i = n / 2 - 1; i >= 0; --i) sift_down(i);
+  }
+  bool less(int64_t a, int64_t b) const { return key[(size_t)a] < key[(size_t)b] || (key[(size_t)a] == key[(size_t)b] && a < b); }
+  void sift_down(int64_t i) {
+    const int64_t n = (int64_t)heap.size();
+    for (;;) {
+      int64_t l = 2 * i + 1, r = l + 1, m = i;
+      if (l < n && less(heap[(size_t)l], heap[(size_t)m])) m = l;
+      if (r < n && less(heap[(size_t)r], heap[(size_t)m])) m = r;
+      if (m == i) return;
+      std::swap(heap[(size_t)i], heap[(size_t)m]);
+      i = m;
+    }
+  }
+  int64_t top() const { return heap[0]; }
+  void replace_top(double v) {   // the slot at the top takes a new (larger) key
+    key[(size_t)heap[0]] = v;
+    sift_down(0);
+  }
+};
+}  // namespace
+
+extern "C" int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, const float* first, const float* last,
+                                  const double* logl_last, int64_t n_chains, int d, int64_t* nb, int64_t max_iters,
+                                  int64_t* worst_out, int64_t* chain_out, int64_t* prev_out, double* loglstar_out,
+                                  double* maxlogl_out, int* exhausted) {
+  if (!active_logl || nlive <= 0 || !first || !last || !logl_last || !nb || !worst_out || !chain_out || !prev_out ||
+      !loglstar_out || !maxlogl_out || !exhausted || max_iters < 0)
+    return NNB_ERR_ARG;
+  for (int64_t i = 0; i < nlive; ++i)
+    if (active_logl[i] != active_logl[i]) return NNB_ERR_ARG;   // NaN has no place in the ordering
+  LiveHeap hp(active_logl, nlive);
+  std::vector<int64_t> writer((size_t)nlive, -1);
+  double maxl = active_logl[0];
+  for (int64_t i = 1; i < nlive; ++i) maxl = active_logl[i] > maxl ? active_logl[i] : maxl;
+  *exhausted = 0;
+  int64_t k = 0;
+  for (; k < max_iters; ++k) {
+    const int64_t worst = hp.top();
+    const double loglstar = hp.key[(size_t)worst];
+    worst_out[k] = worst;
+    loglstar_out[k] = loglstar;
+    prev_out[k] = writer[(size_t)worst];
+    const int64_t ib = nnb_consume_scan(first, last, logl_last, n_chains, d, loglstar, nb);
+    if (ib < 0) {
+      *exhausted = 1;
+      return k;
+    }
+    const double nl = logl_last[ib];
+    chain_out[k] = ib;
+    writer[(size_t)worst] = k;
+    hp.replace_top(nl);
+    if (loglstar == maxl) {   // every live point was equal: recompute (np.max after the replacement)
+      maxl = hp.key[0];
+      for (int64_t i = 1; i < nlive; ++i) maxl = hp.key[(size_t)i] > maxl ? hp.key[(size_t)i] : maxl;
+    } else if (nl > maxl) {
+      maxl = nl;
+    }
+    maxlogl_out[k] = maxl;
+  }
+  return k;
 }

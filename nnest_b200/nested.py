@@ -1,11 +1,13 @@
 """NestedSampler with the reference's interface (nnest/nested.py:24-510).
 
 The MCMC refill (nested.py:398-427) runs in the fused CUDA kernels (Sampler._mcmc_refill); live-point
-replacement (nested.py:429-439) uses the exact host scan exported by the C ABI (nnb_consume_scan); evidence
-bookkeeping (nested.py:272-293,458-464,487-500) is the reference's float64 arithmetic, kept verbatim on the
-host so that logZ, H and the posterior arrays are bit-identical given identical likelihood values.  The
-per-iteration O(it) rebuild of self.samples/weights/loglikes (nested.py:469-471) is deferred to the points
-where they are read (checkpoints, end of run): same values, linear instead of quadratic cost.
+replacement (nested.py:429-439) uses the exact host routines exported by the C ABI (nnb_consume_scan for a single
+iteration, nnb_ns_consume for a run of iterations with a heap instead of an O(nlive) argmin per iteration);
+evidence bookkeeping (nested.py:272-293,458-464,487-500) is the reference's float64 arithmetic in the reference's
+order (bookkeeping.NSBook: sequential NumPy accumulations between refills / retrains / checkpoints, the scalar code
+around them), so that logZ, H and the posterior arrays are bit-identical given identical likelihood values
+(tests/test_bookkeeping.py, tests/test_gpu_api.py).  The per-iteration O(it) rebuild of self.samples/weights/loglikes
+(nested.py:469-471) is deferred to the points where they are read (checkpoints, end of run).
 
 Multi-GPU: one process per GPU under torchrun; every rank runs its own shard of chains, the end states are
 all-gathered over NCCL in rank order (the reference's gather + bcast + concatenate, nested.py:416-427) and
@@ -25,6 +27,7 @@ import torch
 
 from . import _lib as L
 from . import dist
+from .bookkeeping import NSBook
 from .priors import UniformPrior
 from .sampler import Sampler
 
@@ -148,14 +151,15 @@ class NestedSampler(Sampler):
             for f in glob.glob(os.path.join(self.logs['checkpoint'], 'checkpoint_*.txt')):
                 it = max(it, int(f.split('/checkpoint_')[1].split('.txt')[0]))
 
+        bk = NSBook(nlive)
         if it >= 0:
             if primary:
                 self.logger.info('Using checkpoint [%d]' % it)
             with open(os.path.join(self.logs['checkpoint'], 'checkpoint_%s.txt' % it), 'r') as f:
                 data = json.load(f)
-            logz, h, logvol = data['logz'], data['h'], data['logvol']
+            bk.logz, bk.h, bk.logvol, bk.it = data['logz'], data['h'], data['logvol'], it
             self.total_calls = int(data['ncall'] / self.mpi_size)
-            fraction_remain = data['fraction_remain']
+            bk.fraction_remain = data['fraction_remain']
             strategy = data['strategy']
             expired_strategies = data['expired_strategies']
             ckpt = self.logs['checkpoint']
@@ -163,10 +167,10 @@ class NestedSampler(Sampler):
             active_v = self.transform(active_u)
             active_logl = np.load(os.path.join(ckpt, 'active_logl_%s.npy' % it))
             active_derived = np.load(os.path.join(ckpt, 'active_derived_%s.npy' % it))
-            saved_v = np.load(os.path.join(ckpt, 'saved_v.npy')).tolist()
-            saved_logl = np.load(os.path.join(ckpt, 'saved_logl.npy')).tolist()
-            saved_logwt = np.load(os.path.join(ckpt, 'saved_logwt.npy')).tolist()
-            assert it == len(saved_logl)
+            bk.saved_v = [np.load(os.path.join(ckpt, 'saved_v.npy')).reshape(it, -1)]
+            bk.saved_logl = [np.load(os.path.join(ckpt, 'saved_logl.npy'))]
+            bk.saved_logwt = [np.load(os.path.join(ckpt, 'saved_logwt.npy'))]
+            assert it == bk.num_dead()
             total_calls = data['ncall']
         else:
             active_u = self.sample_prior(nlive) if primary else np.empty((nlive, self.x_dim), dtype=np.float64)
@@ -177,16 +181,11 @@ class NestedSampler(Sampler):
             total_calls = self.total_calls
             if primary:
                 self.logger.info('Step [0] max logl [%5.4e] vol [1.0] ncalls [%d]' % (np.max(active_logl), total_calls))
-            saved_v, saved_logl, saved_logwt = [], [], []
-            h = 0.0
-            logz = -1e300
-            logvol = np.log(1.0 - np.exp(-1.0 / nlive))
-            fraction_remain = 1.0
-            it = 0
-            if primary:
-                self._write_checkpoint(it, active_u, active_v, active_logl, active_derived, saved_v, saved_logl,
-                                       saved_logwt, logz, h, logvol, total_calls, fraction_remain, strategy,
+                self._write_checkpoint(bk, active_u, active_v, active_logl, active_derived, total_calls, strategy,
                                        expired_strategies)
+        active_u = np.ascontiguousarray(active_u, dtype=np.float64)
+        active_v = np.ascontiguousarray(active_v, dtype=np.float64)
+        active_logl = np.ascontiguousarray(active_logl, dtype=np.float64)
 
         lib = L.load()
         first_time = True
@@ -198,22 +197,41 @@ class NestedSampler(Sampler):
         scale = step_size
         batch = None
         samples = loglikes = None
+        b_first = b_last = b_logl = None
         max_logl = np.max(active_logl)
 
-        while fraction_remain > dlogz and it <= max_iters:
+        def next_special(i):
+            """first iteration index >= i that needs the single-iteration path (retrain, log line, checkpoint)"""
+            up = lambda v, q: ((v + q - 1) // q) * q
+            return min(up(i, update_interval), up(i, log_interval), up(i + 1, log_interval) - 1)
 
+        while bk.fraction_remain > dlogz and bk.it <= max_iters:
+
+            # ---- many plain iterations at once (bit-identical to running them one by one) ----------------------
+            if current_method == 'mcmc' and accept_point and not get_samples and not first_time \
+                    and b_first is not None:
+                kmax = min(next_special(bk.it) - bk.it, 1 << 20)
+                if kmax > 0:
+                    nb, n_done, exhausted, finished = bk.bulk(active_u, active_v, active_logl, self.transform, b_first,
+                                                              b_last, b_logl, nb, kmax, dlogz, max_iters)
+                    if n_done:
+                        max_logl = np.max(active_logl)
+                    if exhausted:
+                        accept_point = False
+                    get_samples = nb == b_first.shape[0]
+                    if primary and self.trainer.writer is not None and n_done:
+                        self.trainer.writer.add_scalar('logz', bk.logz, bk.it)
+                    if finished:
+                        break
+                    continue
+
+            it = bk.it
             worst = int(np.argmin(active_logl))               # nested.py:272 (first index on ties)
-            logwt = logvol + active_logl[worst]
             loglstar = active_logl[worst]
             expected_vol = np.exp(-it / nlive)
 
             if accept_point:                                   # nested.py:280-293
-                logz_new = np.logaddexp(logz, logwt)
-                h = (np.exp(logwt - logz_new) * active_logl[worst] + np.exp(logz - logz_new) * (h + logz) - logz_new)
-                logz = logz_new
-                saved_v.append(np.array(active_v[worst], copy=True))
-                saved_logwt.append(logwt)
-                saved_logl.append(active_logl[worst])
+                bk.evidence_update(active_v, active_logl, worst)
                 accept_point = False
 
             old_method = current_method
@@ -256,7 +274,7 @@ class NestedSampler(Sampler):
                 if accept_point and it > 0 and (it + 1) % log_interval == 0 and primary:
                     self.logger.info(
                         'Step [%d] loglstar [%5.4e] max logl [%5.4e] logz [%5.4e] vol [%6.5e] ncalls [%d] mean '
-                        'calls [%5.4f]' % (it + 1, loglstar, np.max(active_logl), logz, expected_vol, total_calls,
+                        'calls [%5.4f]' % (it + 1, loglstar, np.max(active_logl), bk.logz, expected_vol, total_calls,
                                            mean_calls))
 
             elif current_method == 'mcmc':
@@ -271,16 +289,14 @@ class NestedSampler(Sampler):
                     b_first = np.ascontiguousarray(batch['first'].cpu().numpy())
                     b_last = np.ascontiguousarray(batch['last'].cpu().numpy())
                     b_logl = np.ascontiguousarray(batch['logl_last'].cpu().numpy())
-                    fp = ctypes.POINTER(ctypes.c_float)
-                    p_first, p_last = b_first.ctypes.data_as(fp), b_last.ctypes.data_as(fp)
-                    p_logl = b_logl.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-                    n_batch = b_first.shape[0]
 
                 c_nb = ctypes.c_int64(nb)                       # nested.py:429-439
-                ib = lib.nnb_consume_scan(p_first, p_last, p_logl, n_batch, self.x_dim, float(loglstar),
-                                          ctypes.byref(c_nb))
+                fp = ctypes.POINTER(ctypes.c_float)
+                ib = lib.nnb_consume_scan(b_first.ctypes.data_as(fp), b_last.ctypes.data_as(fp),
+                                          b_logl.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), b_first.shape[0],
+                                          self.x_dim, float(loglstar), ctypes.byref(c_nb))
                 nb = c_nb.value
-                get_samples = nb == n_batch
+                get_samples = nb == b_first.shape[0]
                 if ib >= 0:
                     active_u[worst] = b_last[ib, :]
                     active_v[worst] = self.transform(active_u[worst])
@@ -296,11 +312,11 @@ class NestedSampler(Sampler):
                         acceptance, ess, jump_distance = np.nan, np.array([np.nan]), np.nan
                     self.logger.info(
                         'Step [%d] loglstar [%5.4e] maxlogl [%5.4e] logz [%5.4e] vol [%6.5e] ncalls [%d] '
-                        'scale [%5.4f]' % (it, loglstar, np.max(active_logl), logz, expected_vol, total_calls, scale))
+                        'scale [%5.4f]' % (it, loglstar, np.max(active_logl), bk.logz, expected_vol, total_calls, scale))
                     with open(os.path.join(self.logs['results'], 'results.csv'), 'a') as f:
                         writer = csv.writer(f)
                         writer.writerow([it, acceptance, np.min(ess), np.max(ess),
-                                         jump_distance, scale, loglstar, logz, fraction_remain, total_calls])
+                                         jump_distance, scale, loglstar, bk.logz, bk.fraction_remain, total_calls])
 
             if accept_point:                                    # nested.py:458-485
                 # np.max(active_logl) without the O(nlive) pass: the maximum only changes when the new point
@@ -310,40 +326,37 @@ class NestedSampler(Sampler):
                     max_logl = np.max(active_logl)
                 elif new_logl > max_logl:
                     max_logl = new_logl
-                logvol -= 1.0 / nlive
-                logz_remain = max_logl - it / nlive
-                fraction_remain = np.logaddexp(logz, logz_remain) - logz
-                it += 1
+                bk.shrink(max_logl)
 
                 if primary and self.trainer.writer is not None:
-                    self.trainer.writer.add_scalar('logz', logz, it)
+                    self.trainer.writer.add_scalar('logz', bk.logz, bk.it)
 
-                if it > 0 and it % log_interval == 0 and primary:
-                    self._write_checkpoint(it, active_u, active_v, active_logl, active_derived, saved_v, saved_logl,
-                                           saved_logwt, logz, h, logvol, total_calls, fraction_remain, strategy,
+                if bk.it > 0 and bk.it % log_interval == 0 and primary:
+                    self._write_checkpoint(bk, active_u, active_v, active_logl, active_derived, total_calls, strategy,
                                            expired_strategies)
-                    self.samples = np.array(saved_v)
-                    self.weights = np.exp(np.array(saved_logwt) - logz)
-                    self.loglikes = np.array(saved_logl)
+                    self.samples, self.loglikes, logwt = bk.dead_points()
+                    self.weights = np.exp(logwt - bk.logz)
                     self._save_samples(self.samples, self.loglikes, weights=self.weights)
 
-        logvol = -len(saved_v) / nlive - np.log(nlive)         # nested.py:487-500
+        saved_v, saved_logl, saved_logwt = bk.dead_points()
+        logz, h, it = bk.logz, bk.h, bk.it
+        logvol = -len(saved_logl) / nlive - np.log(nlive)      # nested.py:487-500
+        fin_logwt = np.empty(nlive)
         for i in range(nlive):
             logwt = logvol + active_logl[i]
             logz_new = np.logaddexp(logz, logwt)
             h = (np.exp(logwt - logz_new) * active_logl[i] + np.exp(logz - logz_new) * (h + logz) - logz_new)
             logz = logz_new
-            saved_v.append(np.array(active_v[i]))
-            saved_logwt.append(logwt)
-            saved_logl.append(active_logl[i])
+            fin_logwt[i] = logwt
 
         self.logz = logz
         self.h = h
         self.logzerr = np.sqrt(h / nlive)
         self.niter = it + 1
-        self.samples = np.array(saved_v)
-        self.weights = np.exp(np.array(saved_logwt) - logz)
-        self.loglikes = np.array(saved_logl)
+        self.samples = np.concatenate((saved_v.reshape(-1, self.x_dim), active_v)) if len(saved_logl) else \
+            np.array(active_v, copy=True)
+        self.weights = np.exp(np.concatenate((saved_logwt, fin_logwt)) - logz)
+        self.loglikes = np.concatenate((saved_logl, active_logl))
         self.active_u, self.active_logl = active_u, active_logl
 
         if primary:
@@ -353,20 +366,22 @@ class NestedSampler(Sampler):
                 writer.writerow([it + 1, total_calls, logz, np.sqrt(h / nlive), h])
             self._save_samples(self.samples, self.loglikes, weights=self.weights)
             self.logger.info("niter: {:d}\n ncall: {:d}\n nsamples: {:d}\n logz: {:6.3f} +/- {:6.3f}\n h: {:6.3f}"
-                             .format(it + 1, int(total_calls), len(saved_v), logz, np.sqrt(h / nlive), h))
+                             .format(it + 1, int(total_calls), len(self.loglikes), logz, np.sqrt(h / nlive), h))
 
-    def _write_checkpoint(self, it, active_u, active_v, active_logl, active_derived, saved_v, saved_logl,
-                          saved_logwt, logz, h, logvol, total_calls, fraction_remain, strategy, expired_strategies):
+    def _write_checkpoint(self, bk, active_u, active_v, active_logl, active_derived, total_calls, strategy,
+                          expired_strategies):
         """Checkpoint files of the reference (nested.py:249-260,473-484)."""
         ckpt = self.logs['checkpoint']
+        it = bk.it
+        saved_v, saved_logl, saved_logwt = bk.dead_points()
         np.save(os.path.join(ckpt, 'active_u_%s.npy' % it), active_u)
         np.save(os.path.join(ckpt, 'active_v_%s.npy' % it), active_v)
         np.save(os.path.join(ckpt, 'active_logl_%s.npy' % it), active_logl)
         np.save(os.path.join(ckpt, 'active_derived_%s.npy' % it), active_derived)
-        np.save(os.path.join(ckpt, 'saved_v.npy'), saved_v)
+        np.save(os.path.join(ckpt, 'saved_v.npy'), saved_v if len(saved_logl) else [])
         np.save(os.path.join(ckpt, 'saved_logl.npy'), saved_logl)
         np.save(os.path.join(ckpt, 'saved_logwt.npy'), saved_logwt)
         with open(os.path.join(ckpt, 'checkpoint_%s.txt' % it), 'w') as f:
-            json.dump({'logz': float(logz), 'h': float(h), 'logvol': float(logvol), 'ncall': int(total_calls),
-                       'fraction_remain': float(fraction_remain), 'strategy': strategy,
+            json.dump({'logz': float(bk.logz), 'h': float(bk.h), 'logvol': float(bk.logvol), 'ncall': int(total_calls),
+                       'fraction_remain': float(bk.fraction_remain), 'strategy': strategy,
                        'expired_strategies': expired_strategies}, f)

@@ -1,0 +1,124 @@
+"""CPU tests: the batched nested-sampling bookkeeping (nnest_b200/bookkeeping.py + nnb_ns_consume in the C ABI)
+against the per-iteration oracle of nested.py:269-500 -- bit for bit."""
+import numpy as np
+import pytest
+
+from oracle import nested as onested
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from nnest_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def _make_batches(rng, nbatch, n, d, lo, hi, p_move=0.7, ties=False):
+    out = []
+    for _ in range(nbatch):
+        first = rng.uniform(-1, 1, size=(n, d)).astype(np.float32)
+        last = first.copy()
+        moved = rng.uniform(size=n) < p_move
+        last[moved] += rng.uniform(0.01, 0.1, size=(moved.sum(), d)).astype(np.float32)
+        half = rng.uniform(size=n) < 0.1
+        last[half, 0] = first[half, 0]                     # moved in some coordinates only: not usable
+        logl = rng.uniform(lo, hi, size=n)
+        if ties:
+            logl = np.round(logl, 1)
+        out.append((first, last, logl))
+    return out
+
+
+def _oracle_run(u0, logl0, tr, batches, dlogz, max_iters=10 ** 9):
+    it = iter(batches)
+    cur = {}
+
+    def randint(n, size):
+        cur['b'] = next(it)
+        return np.zeros(size, dtype=np.int64)
+
+    def batch_fn(init_samples, init_loglikes, loglstar):
+        first, last, logl = cur['b']
+        return np.stack([first, last], axis=1), np.stack([np.zeros_like(logl), logl], axis=1)
+
+    st, au, av, al, trace = onested.run_mcmc_strategy(u0, logl0, tr, batch_fn, dlogz=dlogz, max_iters=max_iters,
+                                                      mcmc_num_chains=batches[0][0].shape[0], randint=randint)
+    return st, au, av, al
+
+
+def _bulk_run(u0, logl0, tr, batches, dlogz, chunk, max_iters=10 ** 9):
+    """The driver pattern of nnest_b200/nested.py: slow path around refills, bulk in between."""
+    from nnest_b200.bookkeeping import NSBook
+    nlive = u0.shape[0]
+    au = np.array(u0, dtype=np.float64, copy=True)
+    al = np.array(logl0, dtype=np.float64, copy=True)
+    av = tr(au)
+    bk = NSBook(nlive)
+    it_b = iter(batches)
+    accept_point, get_samples, nb = True, True, 0
+    first = last = logl = None
+    while bk.fraction_remain > dlogz and bk.it <= max_iters:
+        if get_samples or not accept_point:
+            worst = int(np.argmin(al))
+            loglstar = al[worst]
+            if accept_point:
+                bk.evidence_update(av, al, worst)
+                accept_point = False
+            if get_samples:
+                nb = 0
+                first, last, logl = next(it_b)
+            # one scan by hand (nested.py:429-439)
+            found = -1
+            for ib in range(nb, first.shape[0]):
+                nb += 1
+                get_samples = nb == first.shape[0]
+                if np.all(first[ib] != last[ib]) and logl[ib] > loglstar:
+                    found = ib
+                    break
+            if found >= 0:
+                au[worst] = last[found]
+                av[worst] = tr(au[worst][None, :])[0]
+                al[worst] = logl[found]
+                accept_point = True
+                bk.shrink(np.max(al))
+            continue
+        nb, n_done, exhausted, finished = bk.bulk(au, av, al, tr, first, last, logl, nb, chunk, dlogz, max_iters)
+        if exhausted:
+            accept_point = False
+        get_samples = nb == first.shape[0]
+        if finished:
+            break
+    return bk, au, av, al
+
+
+@pytest.mark.parametrize('seed,nlive,n,ties,chunk', [(0, 50, 16, False, 7), (1, 200, 64, False, 1000), (2, 64, 8, True, 5),
+                                                    (3, 128, 256, True, 50), (4, 30, 4, False, 3)])
+def test_bulk_bookkeeping_bit_exact(lib, seed, nlive, n, ties, chunk):
+    rng = np.random.RandomState(seed)
+    d = 3
+    tr = lambda x: 5 * x
+    u0 = rng.uniform(-1, 1, size=(nlive, d))
+    logl0 = rng.uniform(-50, -10, size=nlive)
+    if ties:
+        logl0 = np.round(logl0, 0)
+    batches = _make_batches(rng, 4000, n, d, -30, 5, ties=ties)
+    st, au, av, al = _oracle_run(u0, logl0, tr, batches, dlogz=0.5)
+    bk, bu, bv, bl = _bulk_run(u0, logl0, tr, batches, dlogz=0.5, chunk=chunk)
+    assert bk.it == st.it and bk.logz == st.logz and bk.h == st.h
+    assert bk.logvol == st.logvol and bk.fraction_remain == st.fraction_remain
+    sv, sl, sw = bk.dead_points()
+    assert np.array_equal(sv, np.array(st.saved_v)) and np.array_equal(sl, np.array(st.saved_logl))
+    assert np.array_equal(sw, np.array(st.saved_logwt))
+    assert np.array_equal(bu, au) and np.array_equal(bv, av) and np.array_equal(bl, al)
+
+
+def test_bulk_respects_iteration_limit(lib):
+    rng = np.random.RandomState(9)
+    tr = lambda x: 5 * x
+    u0 = rng.uniform(-1, 1, size=(40, 2))
+    logl0 = rng.uniform(-50, -10, size=40)
+    batches = _make_batches(rng, 500, 32, 2, -30, 5)
+    st, au, av, al = _oracle_run(u0, logl0, tr, batches, dlogz=1e-9, max_iters=57)
+    bk, bu, bv, bl = _bulk_run(u0, logl0, tr, batches, dlogz=1e-9, chunk=1000, max_iters=57)
+    assert bk.it == st.it == 58 and bk.logz == st.logz and bk.h == st.h
+    assert np.array_equal(bl, al) and np.array_equal(bu, au)
