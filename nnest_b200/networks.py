@@ -6,6 +6,8 @@ keeps PyTorch autograd for now, and so that `models/netG.pt` stays interchangeab
 parameter names are those of nnest/networks.py (flow.flows.<k>.{scale_net,translate_net}.<2j>.{weight,bias},
 ScaleLayer 'scale'), coupling masks are (arange(d) + k) % 2 and are not parameters.
 """
+import math
+
 import torch
 import torch.nn as nn
 
@@ -101,6 +103,7 @@ class SingleSpeedNVP(nn.Module):
         self.device = device
         if device is not None:
             self.flow.to(device)
+        self._std_normal = prior is None
         if prior is None:
             loc = torch.zeros(num_inputs, device=device)
             prior = torch.distributions.MultivariateNormal(loc, torch.eye(num_inputs, device=device))
@@ -114,6 +117,10 @@ class SingleSpeedNVP(nn.Module):
 
     def log_probs(self, inputs):
         u, log_det = self.forward(inputs)
+        if self._std_normal:
+            # N(0, I) log-density written out (what MultivariateNormal.log_prob evaluates); no host sync, so the
+            # training step can be captured in a CUDA graph
+            return -0.5 * (self.num_inputs * math.log(2 * math.pi) + (u * u).sum(-1)) + log_det
         lp = self.prior.log_prob(u)
         if lp.dim() > 1:
             lp = lp.sum(1)

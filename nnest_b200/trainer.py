@@ -26,6 +26,48 @@ from .networks import SingleSpeedNVP
 from .utils.logger import create_logger
 
 
+class _GraphedStep(object):
+    """One Adam step on -mean(log p(x + jitter * eps)) captured in a CUDA graph: the flow is tiny (<= 12k parameters),
+    so the eager iteration is pure launch latency (~100 kernels); replaying the graph is a single launch."""
+
+    def __init__(self, net, optimizer, batch_size, dim, device):
+        self.x = torch.zeros((batch_size, dim), device=device)
+        self.jitter = torch.zeros((), device=device)
+        self.loss = torch.zeros((), device=device)
+        self.net, self.opt = net, optimizer
+
+        def step():
+            data = self.x + self.jitter * torch.randn_like(self.x)
+            self.opt.zero_grad(set_to_none=False)
+            loss = -self.net.log_probs(data).mean()
+            loss.backward()
+            self.opt.step()
+            self.loss.copy_(loss.detach())
+
+        # warm-up on a side stream must not change the weights / optimizer state that training starts from
+        saved = copy.deepcopy(net.state_dict())
+        saved_opt = copy.deepcopy(optimizer.state_dict())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        net.load_state_dict(saved)
+        optimizer.load_state_dict(saved_opt)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            step()
+        net.load_state_dict(saved)
+        optimizer.load_state_dict(saved_opt)
+
+    def __call__(self, batch, jitter):
+        self.x.copy_(batch)
+        self.jitter.fill_(float(jitter))
+        self.graph.replay()
+        return self.loss
+
+
 class Trainer(object):
     best_validation_epoch = None
     best_validation_loss = None
@@ -79,7 +121,10 @@ class Trainer(object):
         else:
             self.path = None
 
-        self.optimizer = torch.optim.Adam(self.netG.parameters(), lr=learning_rate, weight_decay=weight_decay)
+        # capturable: the optimizer step lives inside the CUDA graph of one training iteration (_GraphedStep)
+        self.optimizer = torch.optim.Adam(self.netG.parameters(), lr=learning_rate, weight_decay=weight_decay,
+                                          capturable=True)
+        self._graphed = {}
         self.logger = create_logger(__name__, level=log_level)
         self.log = log
         self.writer = None
@@ -137,7 +182,8 @@ class Trainer(object):
 
         best_validation_loss = float('inf')
         best_validation_epoch = 0
-        best_state = copy.deepcopy(self.netG.state_dict())
+        params = list(self.netG.parameters())
+        best_state = torch.nn.utils.parameters_to_vector(params).detach().clone()   # one flat copy, not 36 tensors
         counter = 0
 
         for epoch in range(1, max_iters + 1):
@@ -148,7 +194,7 @@ class Trainer(object):
             if validation_loss < best_validation_loss:
                 best_validation_epoch = epoch
                 best_validation_loss = validation_loss
-                best_state = copy.deepcopy(self.netG.state_dict())
+                best_state = torch.nn.utils.parameters_to_vector(params).detach().clone()
                 counter = 0
 
             if epoch == 1 or epoch % log_interval == 0:
@@ -171,25 +217,39 @@ class Trainer(object):
                          % (best_validation_epoch, best_validation_loss, time.time() - start_time))
         self.best_validation_epoch = best_validation_epoch
         self.best_validation_loss = best_validation_loss
-        self.netG.load_state_dict(best_state)
+        with torch.no_grad():
+            torch.nn.utils.vector_to_parameters(best_state, params)
         self._sync_device()
 
     def _train(self, epoch, x_train, jitter=0.0, l2_norm=0.0):
+        """One epoch (trainer.py:384-403): shuffled mini-batches, jittered inputs, Adam on -mean(log p).  Full batches
+        replay a captured CUDA graph (forward + backward + Adam in one launch); a trailing partial batch runs eagerly."""
         self.netG.train()
         n = x_train.shape[0]
         order = torch.randperm(n, device=x_train.device)
-        total = 0.0
-        for s in range(0, n, self.batch_size):
-            data = x_train[order[s:s + self.batch_size]]
+        bs = self.batch_size
+        total = torch.zeros((), device=x_train.device)
+        nfull = n // bs
+        if nfull and not l2_norm:
+            step = self._graphed.get(bs)
+            if step is None:
+                step = self._graphed[bs] = _GraphedStep(self.netG, self.optimizer, bs, self.x_dim, x_train.device)
+            for b in range(nfull):
+                total += step(x_train[order[b * bs:(b + 1) * bs]], jitter)
+            rest = range(nfull * bs, n, bs)
+        else:
+            rest = range(0, n, bs)
+        for s in rest:
+            data = x_train[order[s:s + bs]]
             data = data + jitter * torch.randn_like(data)
-            self.optimizer.zero_grad(set_to_none=True)
+            self.optimizer.zero_grad(set_to_none=False)
             loss = -self.netG.log_probs(data).mean()
-            total += loss.item()
+            total += loss.detach()
             if l2_norm:
                 loss = loss + l2_norm * sum((p ** 2).sum() for p in self.netG.parameters())
             loss.backward()
             self.optimizer.step()
-        return total / n      # the reference divides by the dataset size (trainer.py:403)
+        return total.item() / n      # the reference divides by the dataset size (trainer.py:403)
 
     def _validate(self, epoch, x_valid):
         self.netG.eval()
