@@ -158,7 +158,8 @@ typedef struct {
   int64_t* ncall;        /* likelihood evaluations performed */
 } nnb_mcmc_init_args;
 
-int nnb_mcmc_init(nnb_handle* h, const nnb_mcmc_init_args* a, void* stream); /* synchronous */
+/* synchronous when n_bad_start or ncall is requested, otherwise stream-ordered and asynchronous */
+int nnb_mcmc_init(nnb_handle* h, const nnb_mcmc_init_args* a, void* stream);
 
 typedef struct {
   int64_t n_chains;

@@ -293,6 +293,7 @@ extern "C" int nnb_mcmc_init(nnb_handle* h, const nnb_mcmc_init_args* a, void* s
     default: rc = fail(h, NNB_ERR_UNSUPPORTED, "hidden_dim");
   }
   if (rc) return rc;
+  if (!a->n_bad_start && !a->ncall) return NNB_OK;   // counters not wanted: stay asynchronous
   NNB_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
   NNB_CUDA(h, cudaStreamSynchronize(st));
   if (a->n_bad_start) *a->n_bad_start = (int64_t)h->h_ctrl->nbad;

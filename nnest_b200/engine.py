@@ -174,8 +174,11 @@ class Engine(object):
         return (logl, logp) if want_prior else logl
 
     # ---- MCMC -------------------------------------------------------------------------------
-    def mcmc_init(self, n, init_u=None, init_z=None, init_logl=None, seed=0, chain_offset=0, start_try=0):
-        """init_u / init_z: chain-minor (d,n) float32 cuda tensors.  Returns (ChainState, n_bad_start, ncall)."""
+    def mcmc_init(self, n, init_u=None, init_z=None, init_logl=None, seed=0, chain_offset=0, start_try=0,
+                  want_counts=None):
+        """init_u / init_z: chain-minor (d,n) float32 cuda tensors.  Returns (ChainState, n_bad_start, ncall).
+        When the start log-likelihoods are supplied nothing has to be counted and the call stays asynchronous
+        (the two counters are then returned as 0)."""
         st = ChainState(n, self.d, self.device)
         a = L.nnb_mcmc_init_args()
         a.n_chains = n
@@ -187,7 +190,10 @@ class Engine(object):
                 setattr(a, name, t.data_ptr())
         a.seed, a.chain_offset, a.start_try = seed, chain_offset, start_try
         nbad, ncall = C.c_int64(0), C.c_int64(0)
-        a.n_bad_start, a.ncall = C.pointer(nbad), C.pointer(ncall)
+        if want_counts is None:
+            want_counts = init_logl is None
+        if want_counts:
+            a.n_bad_start, a.ncall = C.pointer(nbad), C.pointer(ncall)
         self._check(self.lib.nnb_mcmc_init(self.h, C.byref(a), _stream()))
         self.gpu_launches += 1
         return st, nbad.value, ncall.value
