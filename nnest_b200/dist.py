@@ -53,8 +53,12 @@ def broadcast_parameters(module, src=0):
     params = list(module.parameters())
     flat = torch.nn.utils.parameters_to_vector(params).detach().clone()
     dist.broadcast(flat, src=src)
-    with torch.no_grad():
-        torch.nn.utils.vector_to_parameters(flat, params)
+    off = 0
+    with torch.no_grad():      # in place: captured CUDA graphs hold the parameter addresses
+        for p in params:
+            n = p.numel()
+            p.copy_(flat[off:off + n].view_as(p))
+            off += n
 
 
 def allreduce_sum_int(v, device):

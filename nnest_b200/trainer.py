@@ -26,6 +26,17 @@ from .networks import SingleSpeedNVP
 from .utils.logger import create_logger
 
 
+def _copy_into_params(params, vec):
+    """In-place parameter update from a flat vector.  (torch's vector_to_parameters re-points .data at views of the
+    vector, which would silently detach the parameters from the addresses a captured CUDA graph updates.)"""
+    off = 0
+    with torch.no_grad():
+        for p in params:
+            n = p.numel()
+            p.copy_(vec[off:off + n].view_as(p))
+            off += n
+
+
 class _GraphedStep(object):
     """One Adam step on -mean(log p(x + jitter * eps)) captured in a CUDA graph: the flow is tiny (<= 12k parameters),
     so the eager iteration is pure launch latency (~100 kernels); replaying the graph is a single launch."""
@@ -44,22 +55,34 @@ class _GraphedStep(object):
             self.opt.step()
             self.loss.copy_(loss.detach())
 
-        # warm-up on a side stream must not change the weights / optimizer state that training starts from
-        saved = copy.deepcopy(net.state_dict())
-        saved_opt = copy.deepcopy(optimizer.state_dict())
+        # Warm-up (on a side stream) and capture must not change the weights / optimizer state training starts from.
+        # Everything is restored IN PLACE: the graph keeps the addresses of the parameter and Adam state tensors.
+        saved_w = torch.nn.utils.parameters_to_vector(list(net.parameters())).detach().clone()
+        saved_state = {p: {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}
+                       for p, st in optimizer.state.items()}
+
+        def restore():
+            with torch.no_grad():
+                _copy_into_params(list(net.parameters()), saved_w)
+                for p, st in optimizer.state.items():
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            if p in saved_state and k in saved_state[p]:
+                                v.copy_(saved_state[p][k])
+                            else:
+                                v.zero_()
+
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
                 step()
         torch.cuda.current_stream().wait_stream(side)
-        net.load_state_dict(saved)
-        optimizer.load_state_dict(saved_opt)
+        restore()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             step()
-        net.load_state_dict(saved)
-        optimizer.load_state_dict(saved_opt)
+        restore()
 
     def __call__(self, batch, jitter):
         self.x.copy_(batch)
@@ -217,8 +240,7 @@ class Trainer(object):
                          % (best_validation_epoch, best_validation_loss, time.time() - start_time))
         self.best_validation_epoch = best_validation_epoch
         self.best_validation_loss = best_validation_loss
-        with torch.no_grad():
-            torch.nn.utils.vector_to_parameters(best_state, params)
+        _copy_into_params(params, best_state)
         self._sync_device()
 
     def _train(self, epoch, x_train, jitter=0.0, l2_norm=0.0):
