@@ -52,6 +52,7 @@ struct McmcParams {
   float* dump_normals;
   float* dump_uniforms;
   Ctrl* ctrl;
+  int cpc;                     // chains per CTA (tensor-core kernel)
   int coop;                    // persistent cooperative launch: grid barrier per step (tensor-core kernel)
   unsigned int* step_counts;   // [nsteps] accepted proposals per step, zeroed by the host (coop mode)
 };

@@ -67,17 +67,22 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
 template <int MODE, int NPART>
 static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t st) {
   const int tdoubles = target_doubles(h->tdesc.d, h->tdesc.n_params);
-  const long long tiles_total = (p.n + 127) / 128;
-  int ntiles = (int)((tiles_total + h->sm_count - 1) / h->sm_count);   // fill every SM before stacking tiles
-  if (ntiles > kTcMaxTiles) ntiles = kTcMaxTiles;
-  if (ntiles < 1) ntiles = 1;
-  while (ntiles > 1 && tc_smem_bytes(h->tcflow, tdoubles, ntiles, NPART) > (size_t)h->max_smem) --ntiles;
+  // chains per CTA: spread the batch evenly over all SMs in units of a warp (32 chains), at most 4 tiles of 128
+  long long cpc = ((p.n + h->sm_count - 1) / h->sm_count + 31) / 32 * 32;
+  if (cpc > 128 * kTcMaxTiles) cpc = 128 * kTcMaxTiles;
+  if (cpc < 32) cpc = 32;
+  int ntiles = (int)((cpc + 127) / 128);
+  while (ntiles > 1 && tc_smem_bytes(h->tcflow, tdoubles, ntiles, NPART) > (size_t)h->max_smem) {
+    --ntiles;
+    cpc = 128 * ntiles;
+  }
   size_t sm = tc_smem_bytes(h->tcflow, tdoubles, ntiles, NPART);
   const size_t one_cta_per_sm = 116 * 1024;   // TMEM is allocated per CTA: keep a single CTA resident per SM
   if (sm < one_cta_per_sm) sm = one_cta_per_sm;
   NNB_CUDA(h, nnb_set_smem(mcmc_tc_kernel<MODE, NPART>, sm));
-  const int grid = (int)((tiles_total + ntiles - 1) / ntiles);
-  const int block = ntiles * 128 * NPART;
+  const int grid = (int)((p.n + cpc - 1) / cpc);
+  const int block = ntiles * 128 * NPART;   // fixed warp slots; a partial last tile leaves some idle
+  p.cpc = (int)cpc;
   // Persistent path: all steps in ONE cooperative launch (every CTA resident, one per SM), the global accept count
   // of each step travels through a grid barrier.  Needs grid <= SM count; otherwise one launch per step.
   static const bool no_coop = getenv("NNB_NO_COOP") != nullptr;

@@ -89,17 +89,18 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 // 3xTF32 product over `ksteps` K=8 steps: D (+)= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
 //   a_hi / a_lo: TMEM addresses of the hi / lo activations (column of k = 0)
 //   b_hi / b_lo: shared-memory byte addresses of the packed weights (k step 0); nN = N / 8
-__device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                           int ksteps, uint32_t n, bool accumulate_first) {
-  const uint32_t nN = n >> 3;
+// n: N of the instruction; nN_packed: n-blocks per K chunk in the packed buffer (== n / 8 unless a wider packed
+// matrix is issued in column slices)
+__device__ __forceinline__ void mma_3xtf32_n(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                             int ksteps, uint32_t n, uint32_t nN_packed, bool accumulate_first) {
   const uint32_t idesc = idesc_tf32_m128(n);
   // descriptor = hi word (SBO = 128 B, version 1) : lo word (start address >> 4 | LBO >> 4 << 16); a K step moves
   // the start address by 2 * nN * 128 B
   const uint64_t desc_hi = ((uint64_t)((128u >> 4) | (1u << 14))) << 32;
-  const uint32_t lbo_field = ((nN * 128u) >> 4) << 16;
+  const uint32_t lbo_field = ((nN_packed * 128u) >> 4) << 16;
   uint32_t lo_h = ((b_hi & 0x3FFFFu) >> 4) | lbo_field;
   uint32_t lo_l = ((b_lo & 0x3FFFFu) >> 4) | lbo_field;
-  const uint32_t kstep = (2u * nN * 128u) >> 4;
+  const uint32_t kstep = (2u * nN_packed * 128u) >> 4;
   uint32_t acc = accumulate_first ? 1u : 0u;
   for (int ks = 0; ks < ksteps; ++ks) {
     const uint64_t dh = desc_hi | lo_h, dl = desc_hi | lo_l;
@@ -109,6 +110,10 @@ __device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint3
     acc = 1u;
     lo_h += kstep; lo_l += kstep; a_hi += 8u; a_lo += 8u;
   }
+}
+__device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                           int ksteps, uint32_t n, bool accumulate_first) {
+  mma_3xtf32_n(d_tmem, a_hi, a_lo, b_hi, b_lo, ksteps, n, n >> 3, accumulate_first);
 }
 
 // ---- TMEM <-> registers, 32x32b (thread = lane), 8 columns at a time -------------------------------------------
@@ -140,11 +145,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       : "memory");
 }
 
-// hi = x rounded to tf32 (round half away on the magnitude: add half an ulp of tf32, clear the low 13 bits --
-// the bit pattern cvt.rna.tf32.f32 produces for finite x), lo = x - hi (exact in fp32; the tensor core
-// reads its top 19 bits, a relative error below 2^-22 of x).  3 ALU instructions per element.
+// hi = x truncated to tf32 (low 13 mantissa bits cleared), lo = x - hi (exact in fp32; |lo| < 2^-10 |x|, and the
+// tensor core reads its top 19 bits: a relative error below 2^-20 of x).  2 ALU instructions per element.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  hi = __float_as_uint(x) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 

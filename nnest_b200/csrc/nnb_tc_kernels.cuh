@@ -42,22 +42,16 @@ __host__ __device__ inline bool tc_supported(const FlowDesc& f) {
 #ifndef NNB_TC_FAST_TANH
 #define NNB_TC_FAST_TANH 1
 #endif
-// tanh of the s-net.  Default: libdevice tanhf (<= 2 ulp).  NNB_TC_FAST_TANH: 1 - 2/(exp2(2x log2 e) + 1) with the
-// MUFU ex2/rcp approximations and an odd polynomial below 0.25 (<= ~1e-6 relative).
+// tanh of the s-net.  NNB_TC_FAST_TANH=0: libdevice tanhf (<= 2 ulp).  Default: MUFU ex2/rcp form below.
 __device__ __forceinline__ float tc_tanh(float x) {
 #if NNB_TC_FAST_TANH
-  const float ax = fabsf(x);
+  // 1 - 2 / (e^{2x} + 1) for every x: e -> inf gives 1, e -> 0 gives -1; near 0 the ABSOLUTE error stays ~2e-7
+  // (what matters for the sums the activations feed), so no small-argument branch is needed.  5 instructions.
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.885390081777927f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
   float rc;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(e + 1.0f));
-  const float big = copysignf(fmaf(-2.0f, rc, 1.0f), x);
-  const float x2 = x * x;
-  float pl = fmaf(x2, 0.021869488536155203f, -0.05396825396825397f);
-  pl = fmaf(pl, x2, 0.13333333333333333f);
-  pl = fmaf(pl, x2, -0.3333333333333333f);
-  const float small = fmaf(pl * x2, x, x);
-  return ax < 0.25f ? small : big;
+  return fmaf(-2.0f, rc, 1.0f);
 #else
   return tanhf(x);
 #endif
@@ -80,31 +74,34 @@ __device__ __forceinline__ float tc_exp(float x) {
 struct TcTile {
   uint32_t tmem;        // TMEM address of the tile's column 0 (lane 0)
   uint32_t lane_tmem;   // + this warp's lane quarter
-  uint64_t* mbar;
+  uint64_t* mbar;       // two mbarriers: [0] scale-net group, [1] translate-net group
   uint32_t phase;
   uint32_t bar_id;
   uint32_t bar_threads; // 128 * NPART
   int part;             // which of the chain's NPART threads this is
-  bool issuer_warp;     // warp 0 of the tile; its lane 0 issues the MMAs
+  bool single;          // only one issuing warp exists (32-chain tile): it issues both MMA groups
+  int issuer;           // 0 / 1: this warp issues MMA group 0 / 1 (warps 0 and 1 of the tile); -1: none
 };
 
 __device__ __forceinline__ void tile_sync(const TcTile& t) { tc::named_bar_sync(t.bar_id, t.bar_threads); }
 
-// hand the freshly written A operands to the tensor core, run `issue`, wait for completion.  Only the issuing
-// warp polls the mbarrier; the other warps of the tile sleep on the hardware named barrier (no issue slots).
-template <typename F>
-__device__ __forceinline__ void tc_round_trip(TcTile& t, F issue) {
+// Hand the freshly written A operands to the tensor core and wait for completion.  Issuing a tcgen05.mma costs
+// ~70 cycles of one lane (measured, csrc/dev/tc_latency.cu), so the MMAs of a round trip are split into two
+// independent groups (different D columns) issued concurrently by lane 0 of the tile's warps 0 and 1, each
+// committing to its own mbarrier.  Only those two warps poll; the other warps sleep on the hardware barrier.
+template <typename F0, typename F1>
+__device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1) {
   tc::wait_st();
   tc::fence_before_sync();
   tile_sync(t);
-  if (t.issuer_warp) {   // the whole warp takes the branch so that no lane spins next to the issuing lane
+  if (t.issuer >= 0) {   // warp-uniform: the whole warp takes the branch so that no lane spins next to the issuing lane
     tc::fence_after_sync();
     if ((threadIdx.x & 31) == 0) {
-      issue();
-      tc::mma_commit(t.mbar);
+      if (t.issuer == 0) issue0(); else issue1();
+      tc::mma_commit(t.mbar + t.issuer);
     }
     __syncwarp();
-    tc::mbar_wait(t.mbar, t.phase);
+    tc::mbar_wait(t.mbar + t.issuer, t.phase);
     __syncwarp();
   }
   t.phase ^= 1u;
@@ -172,7 +169,14 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
     }
     {
       const uint32_t b_hi = wsm_u32 + 4u * base, b_lo = b_hi + 4u * 32u * K1;
-      tc_round_trip(t, [&] { tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, b_hi, b_lo, K1 / 8, 32, false); });
+      // B1 is packed for N = 32 (nN = 4 n-blocks per K chunk); the two issuers take n-blocks {0,1} / {2,3}:
+      // same LBO (4 * 128 B), start address + 2 * 128 B, N = 16
+      tc_round_trip(t,
+                    [&] {
+                      if (t.single) tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, b_hi, b_lo, K1 / 8, 32, false);
+                      else tc::mma_3xtf32_n(t.tmem + 64, t.tmem, t.tmem + 32, b_hi, b_lo, K1 / 8, 16, 4, false);
+                    },
+                    [&] { tc::mma_3xtf32_n(t.tmem + 80, t.tmem, t.tmem + 32, b_hi + 256u, b_lo + 256u, K1 / 8, 16, 4, false); });
     }
     int off = base + 64 * K1;   // -> bias1
     tc_hidden_epilogue<NPART>(t, wsm + off);
@@ -180,10 +184,12 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
     // ---- hidden layers: block diagonal, s-net cols [0,16), t-net cols [16,32) --------------------------------
     for (int l = 0; l < L; ++l) {
       const uint32_t bs_hi = wsm_u32 + 4u * off, bs_lo = bs_hi + 1024u, bt_hi = bs_hi + 2048u, bt_lo = bs_hi + 3072u;
-      tc_round_trip(t, [&] {
-        tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, bs_hi, bs_lo, 2, 16, false);
-        tc::mma_3xtf32(t.tmem + 80, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, 16, false);
-      });
+      tc_round_trip(t,
+                    [&] {
+                      tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, bs_hi, bs_lo, 2, 16, false);
+                      if (t.single) tc::mma_3xtf32(t.tmem + 80, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, 16, false);
+                    },
+                    [&] { tc::mma_3xtf32(t.tmem + 80, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, 16, false); });
       tc_hidden_epilogue<NPART>(t, wsm + off + 1024);
       off += 1056;
     }
@@ -191,10 +197,12 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
     {
       const uint32_t sz = 4u * 16u * N3;
       const uint32_t bs_hi = wsm_u32 + 4u * off, bs_lo = bs_hi + sz, bt_hi = bs_hi + 2 * sz, bt_lo = bs_hi + 3 * sz;
-      tc_round_trip(t, [&] {
-        tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, bs_hi, bs_lo, 2, N3, false);
-        tc::mma_3xtf32(t.tmem + 96, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, N3, false);
-      });
+      tc_round_trip(t,
+                    [&] {
+                      tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, bs_hi, bs_lo, 2, N3, false);
+                      if (t.single) tc::mma_3xtf32(t.tmem + 96, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, N3, false);
+                    },
+                    [&] { tc::mma_3xtf32(t.tmem + 96, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, N3, false); });
     }
     const float* b3s = wsm + off + 64 * N3;
     const float* b3t = b3s + N3;
@@ -241,9 +249,12 @@ __global__ void __launch_bounds__(kTcMaxTiles * 128 * NPART, 1)
 mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, const double* __restrict__ tgt_g,
                McmcParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int TPT = 128 * NPART;   // threads per tile
+  // A CTA owns p.cpc chains (a multiple of 32): full tiles of 128 plus, possibly, a partial last tile, so that
+  // the batch can be spread evenly over all SMs (65 536 chains = 148 x 448 - a few).  Threads are laid out
+  // tile-major, then part-major; a partial tile simply has fewer warps per part (lane quarters).
   const int d = f.d;
-  const int ntiles = blockDim.x / TPT;
+  const int cpc = p.cpc;
+  const int ntiles = (cpc + 127) >> 7;
   float* wsm = reinterpret_cast<float*>(smem_raw);
   double* td_s = reinterpret_cast<double*>(smem_raw + (size_t)f.total_floats * 4);
   const int nd = target_doubles(td.d, td.n_params);
@@ -253,7 +264,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   float* ldp_all = nz_all + (size_t)ntiles * d * 128;
   int* flag_all = reinterpret_cast<int*>(ldp_all + (size_t)ntiles * NPART * 128);
   uint64_t* mbars = reinterpret_cast<uint64_t*>(flag_all + (size_t)ntiles * 128);
-  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(mbars + kTcMaxTiles);
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(mbars + 2 * kTcMaxTiles);
 
   {
     const float4* s4 = reinterpret_cast<const float4*>(wglob);
@@ -265,13 +276,17 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   target_bind(tg, td, td_s);
 
   const int warp = threadIdx.x >> 5;
-  const int tile = threadIdx.x / TPT;
-  const int tit = threadIdx.x % TPT;     // thread in tile
-  const int m = tit & 127;               // chain in tile = TMEM lane
+  // warp slots: tile j owns warps [4*NPART*j, 4*NPART*(j+1)); part p, lane quarter q -> warp 4*NPART*j + 4p + q.  The
+  // hardware lets a warp touch only the TMEM lane quarter (warp id % 4), so a partial tile keeps this layout and
+  // leaves the warps of its unused quarters idle.
+  const int tile = threadIdx.x / (128 * NPART);
+  const int rows = tile == ntiles - 1 ? cpc - 128 * (ntiles - 1) : 128;   // chains of this tile
+  const int tit = threadIdx.x % (128 * NPART);                             // thread slot in tile
+  const int m = tit & 127;                                                 // chain in tile = TMEM lane
   const uint32_t tmem_cols = ntiles <= 1 ? 128u : (ntiles == 2 ? 256u : 512u);
   if (warp == 0) tc::tmem_alloc(tmem_base_s, tmem_cols);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kTcMaxTiles; ++i) tc::mbar_init(&mbars[i], 1);
+    for (int i = 0; i < 2 * kTcMaxTiles; ++i) tc::mbar_init(&mbars[i], 1);
     tc::mbar_fence_init();
   }
   // weights were written through the generic proxy; the tensor core reads them through the async proxy
@@ -282,21 +297,22 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
 
   TcTile t;
   t.tmem = *tmem_base_s + (uint32_t)tile * kTcColsPerTile;
-  t.lane_tmem = t.tmem + (((uint32_t)((tit >> 5) & 3) * 32u) << 16);
-  t.mbar = &mbars[tile];
+  t.lane_tmem = t.tmem + (((uint32_t)(m >> 5) * 32u) << 16);   // == (warp id % 4) * 32
+  t.mbar = &mbars[2 * tile];
   t.phase = 0;
   t.bar_id = 1 + tile;
-  t.bar_threads = TPT;
+  t.bar_threads = rows * NPART;
   t.part = tit >> 7;
-  t.issuer_warp = (tit >> 5) == 0;
+  t.issuer = tit < 32 ? 0 : (tit < 64 && rows > 32 ? 1 : -1);
+  t.single = rows <= 32;   // a 32-chain tile has only one warp per part
   const int part = t.part;
   const uint32_t wsm_u32 = tc::smem_u32(wsm);
 
   const long long n = p.n;
-  const long long tile_base = ((long long)blockIdx.x * ntiles + tile) * 128;
-  const bool tile_active = tile_base < n;          // uniform over the tile
+  const long long tile_base = (long long)blockIdx.x * cpc + tile * 128;
+  const bool tile_active = tile_base < n && m < rows;   // uniform over a warp; idle quarter warps of a partial tile skip
   const long long c = tile_base + m;
-  const bool active = c < n;
+  const bool active = c < n && m < rows;   // idle quarter warps of a partial tile own no chain
   float* y = y_all + (size_t)tile * d * 128 + m;
   float* zp = zp_all + (size_t)tile * d * 128 + m;
   float* ldp = ldp_all + (size_t)tile * NPART * 128 + m;
@@ -538,7 +554,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
 
 __host__ inline size_t tc_smem_bytes(const TcFlowDesc& f, int tdoubles, int ntiles, int npart) {
   return (size_t)f.total_floats * 4 + (size_t)tdoubles * 8 + 3 * (size_t)ntiles * f.d * 128 * 4 +
-         (size_t)ntiles * npart * 128 * 4 + (size_t)ntiles * 128 * 4 + kTcMaxTiles * 8 + 8 + 32 * 4;
+         (size_t)ntiles * npart * 128 * 4 + (size_t)ntiles * 128 * 4 + 2 * kTcMaxTiles * 8 + 8 + 32 * 4;
 }
 
 }  // namespace nnb
