@@ -15,7 +15,10 @@ import numpy as np
 
 sys.path.insert(0, os.path.realpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', '..')))
 
-ANALYTIC = {('rosenbrock', 2): -5.8041, ('himmelblau', 2): -5.5038, ('eggbox', 2): 235.895}
+# uniform prior on the boxes of the reference's run.py:25-44; Rosenbrock by transfer-matrix quadrature
+# (examples/nested/analytic_rosenbrock.py), the others by 2-D quadrature
+ANALYTIC = {('rosenbrock', 2): -5.8041, ('rosenbrock', 3): -10.4770, ('rosenbrock', 10): -43.1084,
+            ('rosenbrock', 30): -137.4875, ('himmelblau', 2): -5.5038, ('eggbox', 2): 235.895}
 
 
 def main(args):
@@ -51,7 +54,8 @@ def main(args):
     start_time = time.time()
     sampler.run(train_iters=args.train_iters, mcmc_steps=args.mcmc_steps, volume_switch=args.switch,
                 jitter=args.jitter, mcmc_num_chains=args.mcmc_num_chains,
-                mcmc_dynamic_step_size=not args.mcmc_fixed_step_size,
+                mcmc_dynamic_step_size=not args.mcmc_fixed_step_size, log_interval=args.log_interval,
+                update_interval=args.update_interval, chain_stats=not args.no_chain_stats,
                 strategy=args.strategy.split(',') if args.strategy else None)
     elapsed = time.time() - start_time
     print('Run time %s' % datetime.timedelta(seconds=elapsed))
@@ -91,4 +95,7 @@ if __name__ == '__main__':
     parser.add_argument('--batch_size', type=int, default=100)
     parser.add_argument('--seed', type=int, default=None)
     parser.add_argument('--strategy', type=str, default='')
+    parser.add_argument('--log_interval', type=int, default=None, help="NestedSampler.run(log_interval=...)")
+    parser.add_argument('--update_interval', type=int, default=None, help="NestedSampler.run(update_interval=...)")
+    parser.add_argument('-no_chain_stats', action='store_true', help="skip the ESS/jump statistics at log lines")
     main(parser.parse_args())

@@ -234,6 +234,16 @@ int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, const float* fi
                        int64_t* worst_out, int64_t* chain_out, int64_t* prev_out, double* loglstar_out,
                        double* maxlogl_out, int* exhausted);
 
+/*
+ * Chain / posterior text files in the reference's layout (nnest/sampler.py:494-511, `_save_samples`): `rows` lines of
+ * `cols` numbers, each formatted '%.5E' and separated by single spaces (weight, -loglike, parameters, derived).
+ * table [host] float64 row-major (rows, cols); header (may be NULL/empty) is written first, followed by '\n';
+ * append != 0 appends to an existing file.  Host-side (multi-threaded formatting).  Returns the number of bytes
+ * written, or a negative error code.
+ */
+int64_t nnb_write_chain_text(const char* path, const char* header, const double* table, int64_t rows, int cols,
+                             int append);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nnb_host.h"
@@ -441,4 +442,52 @@ extern "C" int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, cons
     maxlogl_out[k] = maxl;
   }
   return k;
+}
+
+// Chain files of the reference (nnest/sampler.py:494-511): one row per sample, every number '%.5E', single spaces.
+// Rows are formatted by several host threads into private buffers and written in order.
+extern "C" int64_t nnb_write_chain_text(const char* path, const char* header, const double* table, int64_t rows,
+                                        int cols, int append) {
+  if (!path || (!table && rows > 0) || rows < 0 || cols <= 0) return NNB_ERR_ARG;
+  FILE* f = fopen(path, append ? "a" : "w");
+  if (!f) return NNB_ERR_ARG;
+  int64_t written = 0;
+  if (header && header[0]) written += fprintf(f, "%s\n", header);
+  const int64_t chunk = 1 << 16;   // rows per batch of threads' work items
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nthreads = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
+  const size_t per_row = (size_t)cols * 14 + 2;   // "-1.23456E+308 " is 14 characters at most
+  std::vector<std::string> bufs((size_t)nthreads);
+  bool ok = true;
+  for (int64_t r0 = 0; r0 < rows && ok; r0 += chunk * nthreads) {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+      const int64_t a = r0 + t * chunk, b = std::min(rows, a + chunk);
+      bufs[(size_t)t].clear();
+      if (a >= b) continue;
+      th.emplace_back([&, t, a, b] {
+        std::string& out = bufs[(size_t)t];
+        out.resize((size_t)(b - a) * per_row);
+        char* w = &out[0];
+        for (int64_t r = a; r < b; ++r) {
+          const double* row = table + r * cols;
+          for (int c = 0; c < cols; ++c) {
+            w += snprintf(w, 16, "%.5E", row[c]);
+            *w++ = c + 1 < cols ? ' ' : '\n';
+          }
+        }
+        out.resize((size_t)(w - &out[0]));
+      });
+    }
+    for (auto& x : th) x.join();
+    for (int t = 0; t < nthreads; ++t) {
+      const std::string& o = bufs[(size_t)t];
+      if (!o.empty()) {
+        if (fwrite(o.data(), 1, o.size(), f) != o.size()) ok = false;
+        written += (int64_t)o.size();
+      }
+    }
+  }
+  if (fclose(f) != 0) ok = false;
+  return ok ? written : (int64_t)NNB_ERR_ARG;
 }

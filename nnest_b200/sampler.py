@@ -323,6 +323,14 @@ class Sampler(object):
     def _chain_stats(self, samples, mean=None, std=None, step=None):
         """Acceptance, ESS and jump distance with the reference's definitions (sampler.py:474-492); `samples` may be
         a numpy array or a device tensor of shape (chains, steps, dim)."""
+        if isinstance(samples, np.ndarray) and samples.size >= (1 << 22) and torch.cuda.is_available():
+            # large traces: the O(chains x steps x lags) statistics run on the device (nnest/utils/evaluation.py is a
+            # Python double loop over chains and steps in the reference)
+            if mean is None:
+                mean = samples.reshape(-1, samples.shape[2]).mean(0, dtype=np.float64)
+            if std is None:
+                std = samples.reshape(-1, samples.shape[2]).std(0, dtype=np.float64)
+            samples = torch.from_numpy(np.ascontiguousarray(samples)).to(self.device)
         acceptance = acceptance_rate(samples)
         flat = samples.reshape(-1, samples.shape[2])
         if mean is None:
@@ -350,12 +358,14 @@ class Sampler(object):
             cols = [np.maximum(wts, min_weight)[:, None], -np.asarray(lgl)[:, None], smp]
             if der is not None:
                 cols.append(der)
-            table = np.concatenate([np.asarray(c, dtype=np.float64) for c in cols], axis=1)
-            with open(path, 'w') as f:
-                if self.param_names is not None:
-                    f.write('#weight minusloglike ' + ' '.join(self.param_names) + '\n')
-                for row in table:
-                    f.write(' '.join('%.5E' % v for v in row) + '\n')
+            table = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float64) for c in cols], axis=1))
+            header = None
+            if self.param_names is not None:
+                header = ('#weight minusloglike ' + ' '.join(self.param_names)).encode()
+            rc = L.load().nnb_write_chain_text(path.encode(), header, table.ctypes.data_as(L._dp), table.shape[0],
+                                               table.shape[1], 0)
+            if rc < 0:
+                raise IOError('could not write %s' % path)
 
         if len(samples.shape) == 2:
             write(os.path.join(self.logs['chains'], outfile + '.txt'), samples, loglikes, weights, derived_samples)

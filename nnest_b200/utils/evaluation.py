@@ -44,11 +44,24 @@ def auto_correlation_time(x, s, mu, var):
 
 
 def effective_sample_size(x, mu, var):
-    """t / (1 + 2 sum_s rho_s (1 - s/t)), lags accumulated while any rho_s > 0.05 (:17-39)."""
+    """t / (1 + 2 sum_s rho_s (1 - s/t)), lags accumulated while any rho_s > 0.05 (:17-39).  The centred series is
+    formed once (float64, on the device for tensors); each lag is then one fused multiply-reduce."""
     b, t, d = x.shape
     ess = np.ones([d])
+    if _xp(x) is torch:
+        mu_t = torch.as_tensor(mu, dtype=torch.float64, device=x.device)
+        var_t = torch.as_tensor(var, dtype=torch.float64, device=x.device)
+        y = x.double() - mu_t
+
+        def rho(s):
+            return (torch.einsum('btd,btd->d', y[:, :-s], y[:, s:]) / (float(t - s) * b) / var_t).cpu().numpy()
+    else:
+        y = np.asarray(x, dtype=np.float64) - mu
+
+        def rho(s):
+            return np.einsum('btd,btd->d', y[:, :-s], y[:, s:]) / (float(t - s) * b) / var
     for s in range(1, t):
-        p = np.asarray(auto_correlation_time(x, s, mu, var))
+        p = np.asarray(rho(s))
         if np.sum(p > 0.05) == 0:
             break
         ess = ess + np.where(p > 0.05, 2.0 * p * (1.0 - float(s) / t), 0.0)
