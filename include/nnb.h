@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 4
+#define NNB_ABI_VERSION 5
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -233,6 +233,59 @@ int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, const float* fi
                        const double* logl_last, int64_t n_chains, int d, int64_t* nb, int64_t max_iters,
                        int64_t* worst_out, int64_t* chain_out, int64_t* prev_out, double* loglstar_out,
                        double* maxlogl_out, int* exhausted);
+
+/*
+ * Flow fitting: ONE EPOCH of the reference's Trainer._train + Trainer._validate (nnest/trainer.py:384-418) in one
+ * kernel launch.  For every mini-batch (visiting order `perm`, the short tail batch is kept like DataLoader does)
+ *     data = x_train[perm[..]] + jitter * N(0, I);  loss = -mean(log p(data));  backward;  Adam step
+ * with torch.optim.Adam semantics (L2 weight decay added to the gradient, bias corrections from the step count),
+ * then the validation negative log-likelihood with the final weights.  log p is the flow's forward map + log-det under
+ * a N(0, I) base density (nnest/networks.py:71-76, 289-298).
+ *   params / adam_m / adam_v [device] float32, n_params = netG.state_dict() order as for nnb_set_flow (scale == '' only),
+ *       updated in place; step0 = optimizer steps taken so far (the call takes ceil(n_train / batch_size) more).
+ *   x_train (n_train, x_dim), x_valid (n_valid, x_dim) [device] float32 row-major; perm [device] int64 or NULL.
+ *   noise [device] optional (n_train, x_dim) N(0,1) draws in visiting order (replays torch.randn_like); NULL = the
+ *       library's Philox stream keyed by (seed, epoch, position).
+ *   grad_out [device] optional: data gradient (without weight decay) of the last mini-batch.
+ *   do_train == 0: validation only (params untouched).
+ *   train_loss_sum_out [host] = sum over mini-batches of the mini-batch mean loss (trainer.py:396; the reference then
+ *       divides by the dataset size); val_nll_sum_out [host] = sum of -log p over x_valid.
+ * Synchronises the stream before returning (the losses drive early stopping on the host).
+ */
+typedef struct nnb_train_args {
+  int x_dim, hidden_dim, num_layers, num_blocks;
+  const float* x_train;
+  int64_t n_train;
+  const int64_t* perm;
+  int batch_size;
+  const float* x_valid;
+  int64_t n_valid;
+  const float* noise;
+  double jitter;
+  uint64_t seed;
+  uint32_t epoch;
+  double lr, beta1, beta2, eps, weight_decay;
+  int64_t step0;
+  float* params;
+  float* adam_m;
+  float* adam_v;
+  size_t n_params;
+  float* grad_out;
+  int do_train;
+  double* train_loss_sum_out;
+  double* val_nll_sum_out;
+  int* grid_out;               /* [host] optional: CTAs the epoch kernel ran on */
+} nnb_train_args;
+
+int nnb_train_epoch(nnb_handle* h, const nnb_train_args* args, void* stream);
+/* 1 when nnb_train_epoch handles this architecture with max_smem_bytes of shared memory per CTA (B200: 232448) */
+int nnb_train_supported(int x_dim, int hidden_dim, int num_layers, int num_blocks, int max_smem_bytes);
+
+/*
+ * Mean over the n rows of x [device] float64 row-major (n, d) of the distance to the nearest OTHER row: the quantity
+ * behind the reference's training jitter, 0.2 * np.mean(cKDTree(x).query(x, 2)[0]) = 0.1 * this (trainer.py:147-150).
+ */
+int nnb_mean_nn_distance(nnb_handle* h, const double* x, int64_t n, int d, double* out, void* stream);
 
 /*
  * Chain / posterior text files in the reference's layout (nnest/sampler.py:494-511, `_save_samples`): `rows` lines of

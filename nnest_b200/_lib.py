@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libnnb.so')
 
-NNB_ABI_VERSION = 4
+NNB_ABI_VERSION = 5
 NNB_MAX_DIM = 128
 NNB_MAX_BLOCKS = 16
 
@@ -49,6 +49,17 @@ class nnb_mcmc_args(C.Structure):
                 ('impl', C.c_int), ('launches_out', _ip), ('impl_out', C.POINTER(C.c_int))]
 
 
+class nnb_train_args(C.Structure):
+    _fields_ = [('x_dim', C.c_int), ('hidden_dim', C.c_int), ('num_layers', C.c_int), ('num_blocks', C.c_int),
+                ('x_train', C.c_void_p), ('n_train', C.c_int64), ('perm', C.c_void_p), ('batch_size', C.c_int),
+                ('x_valid', C.c_void_p), ('n_valid', C.c_int64), ('noise', C.c_void_p), ('jitter', C.c_double),
+                ('seed', C.c_uint64), ('epoch', C.c_uint32), ('lr', C.c_double), ('beta1', C.c_double),
+                ('beta2', C.c_double), ('eps', C.c_double), ('weight_decay', C.c_double), ('step0', C.c_int64),
+                ('params', C.c_void_p), ('adam_m', C.c_void_p), ('adam_v', C.c_void_p), ('n_params', C.c_size_t),
+                ('grad_out', C.c_void_p), ('do_train', C.c_int), ('train_loss_sum_out', _dp),
+                ('val_nll_sum_out', _dp), ('grid_out', C.POINTER(C.c_int))]
+
+
 # name -> (restype, argtypes); every symbol include/nnb.h declares
 SYMBOLS = {
     'nnb_abi_version': (C.c_int, []),
@@ -68,6 +79,9 @@ SYMBOLS = {
     'nnb_consume_scan': (C.c_int64, [_fp, _fp, _dp, C.c_int64, C.c_int, C.c_double, _ip]),
     'nnb_ns_consume': (C.c_int64, [_dp, C.c_int64, _fp, _fp, _dp, C.c_int64, C.c_int, _ip, C.c_int64, _ip, _ip, _ip, _dp,
                                    _dp, C.POINTER(C.c_int)]),
+    'nnb_train_epoch': (C.c_int, [C.c_void_p, C.POINTER(nnb_train_args), C.c_void_p]),
+    'nnb_train_supported': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'nnb_mean_nn_distance': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, _dp, C.c_void_p]),
     'nnb_write_chain_text': (C.c_int64, [C.c_char_p, C.c_char_p, _dp, C.c_int64, C.c_int, C.c_int]),
 }
 

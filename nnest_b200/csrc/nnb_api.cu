@@ -71,6 +71,9 @@ extern "C" void nnb_destroy(nnb_handle* h) {
   if (h->d_target) cudaFree(h->d_target);
   if (h->d_ctrl) cudaFree(h->d_ctrl);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  if (h->d_train_ctrl) cudaFree(h->d_train_ctrl);
+  if (h->h_train_ctrl) cudaFreeHost(h->h_train_ctrl);
+  if (h->d_train_ws) cudaFree(h->d_train_ws);
   delete h;
 }
 

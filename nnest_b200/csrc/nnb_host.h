@@ -25,6 +25,11 @@ struct nnb_handle {
   long long last_launches = 0;             // kernels launched by the last nnb_mcmc_run
   Ctrl* d_ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;  // pinned
+  // flow fitting (nnb_train.cu)
+  void* d_train_ctrl = nullptr;
+  void* h_train_ctrl = nullptr;   // pinned
+  float* d_train_ws = nullptr;    // gradient exchange buffers + per-CTA Adam moments (several CTAs per mini-batch)
+  size_t train_ws_floats = 0;
   std::string err;
 };
 

@@ -1,0 +1,130 @@
+// nnb_train.cu -- host side of the fused flow-fitting kernel (nnb_train.cuh): nnb_train_epoch, nnb_mean_nn_distance.
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "nnb_host.h"
+#include "nnb_train.cuh"
+
+using namespace nnb;
+
+namespace {
+
+template <int H, int L>
+int launch_train(nnb_handle* h, TrainParams& p, int grid, size_t smem, cudaStream_t st) {
+  NNB_CUDA(h, nnb_set_smem(train_epoch_kernel<H, L>, smem));
+  if (grid > 1) {
+    void* args[] = {(void*)&p};
+    NNB_CUDA(h, cudaLaunchCooperativeKernel((const void*)train_epoch_kernel<H, L>, dim3(grid), dim3(kTrainThreads), args,
+                                            smem, st));
+  } else {
+    train_epoch_kernel<H, L><<<1, kTrainThreads, smem, st>>>(p);
+    NNB_CUDA(h, cudaGetLastError());
+  }
+  return NNB_OK;
+}
+
+}  // namespace
+
+extern "C" int nnb_train_supported(int x_dim, int hidden_dim, int num_layers, int num_blocks, int max_smem_bytes) {
+  if (x_dim < 2 || x_dim > NNB_MAX_DIM || num_blocks < 1 || num_blocks > NNB_MAX_BLOCKS) return 0;
+  if (!((hidden_dim == 16 || hidden_dim == 32) && (num_layers == 1 || num_layers == 2))) return 0;
+  return train_smem_bytes(x_dim, hidden_dim, num_layers, num_blocks) <= (size_t)max_smem_bytes ? 1 : 0;
+}
+
+extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* stream) {
+  if (!h || !a) return NNB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = a->x_dim, H = a->hidden_dim, L = a->num_layers, B = a->num_blocks;
+  if (!nnb_train_supported(d, H, L, B, h->max_smem))
+    return nnb_fail(h, NNB_ERR_UNSUPPORTED,
+                    "nnb_train_epoch supports hidden_dim in {16, 32}, num_layers in {1, 2}, scale == '' and flows that "
+                    "fit one CTA's shared memory");
+  const int netP = train_net_floats(d, H, L);
+  const int P = 2 * B * netP;
+  if (a->n_params != (size_t)P) return nnb_fail(h, NNB_ERR_ARG, "n_params does not match (x_dim, hidden_dim, num_layers, num_blocks)");
+  if (!a->params) return nnb_fail(h, NNB_ERR_ARG, "params is NULL");
+  if (a->do_train) {
+    if (!a->adam_m || !a->adam_v) return nnb_fail(h, NNB_ERR_ARG, "adam_m / adam_v are NULL");
+    if (a->n_train < 0 || (a->n_train > 0 && !a->x_train)) return nnb_fail(h, NNB_ERR_ARG, "x_train");
+    if (a->batch_size < 1) return nnb_fail(h, NNB_ERR_ARG, "batch_size must be >= 1");
+    if (a->n_train >= (1ll << 32)) return nnb_fail(h, NNB_ERR_ARG, "n_train must be < 2^32");
+  }
+  if (a->n_valid < 0 || (a->n_valid > 0 && !a->x_valid)) return nnb_fail(h, NNB_ERR_ARG, "x_valid");
+  NNB_CUDA(h, cudaSetDevice(h->device));
+
+  long long work = a->do_train ? (long long)a->batch_size : (long long)a->n_valid;
+  if (a->do_train && a->n_train < work) work = a->n_train;
+  long long g = (work + kTrainThreads - 1) / kTrainThreads;
+  if (g < 1) g = 1;
+  if (g > h->sm_count) g = h->sm_count;
+  if (g > 1 && !h->coop_supported) g = 1;
+  const int grid = (int)g;
+  const int Psm = train_psm(d, H, L, B);
+
+  if (!h->d_train_ctrl) NNB_CUDA(h, cudaMalloc(&h->d_train_ctrl, sizeof(TrainCtrl)));
+  if (!h->h_train_ctrl) NNB_CUDA(h, cudaMallocHost(&h->h_train_ctrl, sizeof(TrainCtrl)));
+  NNB_CUDA(h, cudaMemsetAsync(h->d_train_ctrl, 0, sizeof(TrainCtrl), st));
+  if (grid > 1) {
+    const size_t need = (size_t)3 * Psm + (size_t)grid * 2 * P;
+    if (h->train_ws_floats < need) {
+      if (h->d_train_ws) cudaFree(h->d_train_ws);
+      h->d_train_ws = nullptr;
+      NNB_CUDA(h, cudaMalloc(&h->d_train_ws, need * sizeof(float)));
+      h->train_ws_floats = need;
+    }
+    NNB_CUDA(h, cudaMemsetAsync(h->d_train_ws, 0, (size_t)3 * Psm * sizeof(float), st));
+  }
+
+  TrainParams p{};
+  p.d = d; p.B = B; p.P = P; p.netP = netP;
+  p.x_train = a->x_train; p.n_train = a->n_train; p.perm = (const long long*)a->perm;
+  p.batch_size = a->batch_size;
+  p.x_valid = a->x_valid; p.n_valid = a->n_valid;
+  p.noise = a->noise; p.jitter = (float)a->jitter;
+  p.seed_lo = (unsigned int)(a->seed & 0xffffffffu); p.seed_hi = (unsigned int)(a->seed >> 32); p.epoch = a->epoch;
+  p.lr = (float)a->lr; p.beta1 = (float)a->beta1; p.beta2 = (float)a->beta2; p.eps = (float)a->eps;
+  p.weight_decay = (float)a->weight_decay;
+  p.step0 = a->step0;
+  p.params = a->params; p.adam_m = a->adam_m; p.adam_v = a->adam_v;
+  p.gbuf = grid > 1 ? h->d_train_ws : nullptr;
+  p.mv_priv = grid > 1 ? h->d_train_ws + (size_t)3 * Psm : nullptr;
+  p.ctrl = (TrainCtrl*)h->d_train_ctrl;
+  p.grad_out = a->grad_out;
+  p.do_train = a->do_train ? 1 : 0;
+
+  const size_t smem = train_smem_bytes(d, H, L, B);
+  int rc;
+  if (H == 16 && L == 1) rc = launch_train<16, 1>(h, p, grid, smem, st);
+  else if (H == 16 && L == 2) rc = launch_train<16, 2>(h, p, grid, smem, st);
+  else if (H == 32 && L == 1) rc = launch_train<32, 1>(h, p, grid, smem, st);
+  else rc = launch_train<32, 2>(h, p, grid, smem, st);
+  if (rc) return rc;
+  NNB_CUDA(h, cudaMemcpyAsync(h->h_train_ctrl, h->d_train_ctrl, sizeof(TrainCtrl), cudaMemcpyDeviceToHost, st));
+  NNB_CUDA(h, cudaStreamSynchronize(st));
+  const TrainCtrl* c = (const TrainCtrl*)h->h_train_ctrl;
+  if (a->train_loss_sum_out) *a->train_loss_sum_out = c->train_loss;
+  if (a->val_nll_sum_out) *a->val_nll_sum_out = c->val_loss;
+  if (a->grid_out) *a->grid_out = grid;
+  return NNB_OK;
+}
+
+extern "C" int nnb_mean_nn_distance(nnb_handle* h, const double* x, int64_t n, int d, double* out, void* stream) {
+  if (!h || !out || n < 0 || (n > 0 && !x) || d < 1 || d > NNB_MAX_DIM) return NNB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  NNB_CUDA(h, cudaSetDevice(h->device));
+  *out = 0.0;
+  if (n < 2) return NNB_OK;
+  if (!h->d_train_ctrl) NNB_CUDA(h, cudaMalloc(&h->d_train_ctrl, sizeof(TrainCtrl)));
+  if (!h->h_train_ctrl) NNB_CUDA(h, cudaMallocHost(&h->h_train_ctrl, sizeof(TrainCtrl)));
+  NNB_CUDA(h, cudaMemsetAsync(h->d_train_ctrl, 0, sizeof(TrainCtrl), st));
+  const size_t smem = (size_t)2 * d * 128 * sizeof(double);
+  NNB_CUDA(h, nnb_set_smem(nn_min_dist_kernel, smem));
+  const int grid = (int)((n + 127) / 128);
+  nn_min_dist_kernel<<<grid, 128, smem, st>>>(x, n, d, &((TrainCtrl*)h->d_train_ctrl)->train_loss);
+  NNB_CUDA(h, cudaGetLastError());
+  NNB_CUDA(h, cudaMemcpyAsync(h->h_train_ctrl, h->d_train_ctrl, sizeof(TrainCtrl), cudaMemcpyDeviceToHost, st));
+  NNB_CUDA(h, cudaStreamSynchronize(st));
+  *out = ((const TrainCtrl*)h->h_train_ctrl)->train_loss / (double)n;
+  return NNB_OK;
+}

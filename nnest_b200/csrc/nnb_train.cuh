@@ -1,0 +1,475 @@
+// nnb_train.cuh -- fused flow fitting: one launch = one epoch of Trainer._train + Trainer._validate
+// (reference nnest/trainer.py:384-418): for every mini-batch  data = x[perm] + jitter * N(0, I),
+// loss = -mean(log p(data)) (networks.py:71-76: N(0, I) log-density of the forward flow + log-det),
+// backward pass, Adam step (torch.optim.Adam semantics incl. L2 weight decay); then the validation loss.
+//
+// Design (sm_100a, FP32):
+//   * persistent kernel, 128 threads per CTA, one sample per thread in the per-sample phases; a mini-batch is
+//     spread over ceil(batch/128) CTAs (at most one per SM).  With the reference's default batch_size = 100 that
+//     is ONE CTA walking the whole epoch with weights, gradient and sample vectors resident in shared memory --
+//     no launches, no host round trips between iterations.
+//   * memory-free backward: a coupling block is invertible, so the backward pass walks the blocks in reverse,
+//     recomputes the s/t MLP activations of block k from the pass-through half of its OUTPUT (bit-identical to
+//     the forward pass) and recovers the block input as (y - t) * exp(-s).  Only the current vector and its
+//     gradient are kept per sample (2 d floats in shared memory).
+//   * weight gradients are batch contractions dW[o][i] = sum_b dpre[b][o] * in[b][i]: every thread stages its
+//     sample's `in` / `dpre` vectors as columns of two shared-memory matrices ([feature][sample], rows 16-byte
+//     aligned), then each (o, i) pair is owned by one thread, which runs down the sample axis with float4 loads.
+//     No atomics inside a CTA.
+//   * several CTAs per mini-batch: partial gradients are added into a global buffer (red.global.add.f32), a grid
+//     barrier (cooperative launch) follows, and every CTA applies the identical Adam update to its own
+//     shared-memory copy of the weights (optimizer moments: one private global copy per CTA, L2 resident).
+// Parameter layout: the caller's flat vector is netG.state_dict() order ("natural", as nnb_set_flow); in shared
+// memory each net starts at a multiple of 4 floats and the first layer is stored transposed (W1T[i][j]) so that
+// every inner loop reads float4 rows.  Adam is element-wise, so only the copy in / copy out permutes.
+#pragma once
+#include "nnb_kernels.cuh"
+
+namespace nnb {
+
+constexpr int kTrainThreads = 128;
+constexpr int kStageStride = 132;   // floats per staged row: 128 samples + 4 (rows 16-byte aligned, bank-conflict free)
+enum { kTagTrain = 3 };
+
+struct TrainCtrl {
+  double train_loss;     // sum over mini-batches of mean(-log p)          (trainer.py:396)
+  double val_loss;       // sum over validation samples of -log p          (trainer.py:414)
+  unsigned int ticket;   // grid-barrier arrivals (monotonic)
+  unsigned int pad;
+};
+
+struct TrainParams {
+  int d, B, P, netP;            // P = 2 B netP natural floats
+  const float* x_train;         // (n_train, d) row-major
+  long long n_train;
+  const long long* perm;        // visiting order of the epoch (n_train) or NULL = identity
+  int batch_size;
+  const float* x_valid;         // (n_valid, d) row-major
+  long long n_valid;
+  const float* noise;           // optional N(0,1) draws (n_train, d) in visiting order (replay); NULL = Philox
+  float jitter;
+  unsigned int seed_lo, seed_hi, epoch;
+  float lr, beta1, beta2, eps, weight_decay;
+  long long step0;              // Adam steps taken before this call
+  float* params;                // [P] in / out (natural layout)
+  float* adam_m;                // [P] in / out
+  float* adam_v;                // [P] in / out
+  float* mv_priv;               // [grid][2][P] workspace when grid > 1
+  float* gbuf;                  // [3][Psm] workspace when grid > 1 (zeroed by the host)
+  TrainCtrl* ctrl;
+  float* grad_out;              // optional [P]: data gradient of the LAST mini-batch (natural layout)
+  int do_train;
+};
+
+__host__ __device__ inline int train_net_floats(int d, int H, int L) { return H * d + H + L * (H * H + H) + d * H + d; }
+__host__ __device__ inline int train_psm(int d, int H, int L, int B) { return 2 * B * round4(train_net_floats(d, H, L)); }
+__host__ __device__ inline int train_stage_rows(int d, int H) {
+  const int half = (d + 1) / 2;
+  const int im = (H > half ? H : half) + 1, om = H > half ? H : half;
+  return 2 * (im + om);   // A and D matrices of both nets
+}
+__host__ inline size_t train_smem_bytes(int d, int H, int L, int B) {
+  return (size_t)2 * train_psm(d, H, L, B) * 4 + (size_t)2 * d * kTrainThreads * 4 +
+         (size_t)train_stage_rows(d, H) * kStageStride * 4 + 64;
+}
+
+// natural index -> shared-memory index
+template <int H>
+__device__ __forceinline__ int train_perm_index(int p, int d, int netP, int netPp) {
+  const int net = p / netP, r = p - net * netP;
+  if (r < H * d) {
+    const int j = r / d, i = r - j * d;
+    return net * netPp + i * H + j;
+  }
+  return net * netPp + r;
+}
+
+template <int ACT>
+__device__ __forceinline__ float train_act(float v) { return ACT == 0 ? tanhf(v) : fmaxf(v, 0.0f); }
+// derivative of the activation expressed through its OUTPUT
+template <int ACT>
+__device__ __forceinline__ float train_dact(float h) { return ACT == 0 ? (1.0f - h * h) : (h > 0.0f ? 1.0f : 0.0f); }
+
+// hidden activations h[0..L] of one net for the sample whose vector is the shared-memory column y
+template <int H, int L, int ACT>
+__device__ __forceinline__ void train_mlp_hidden(const float* __restrict__ w, int d, int nin, int i0,
+                                                 const float* __restrict__ y, float (&h)[L + 1][H]) {
+  const float* b1 = w + H * d;
+  float pre[H];
+#pragma unroll
+  for (int j = 0; j < H; ++j) pre[j] = b1[j];
+  for (int a = 0; a < nin; ++a) {
+    const int i = i0 + 2 * a;
+    const float v = y[i * kTrainThreads];
+    const float4* wr = reinterpret_cast<const float4*>(w + i * H);
+#pragma unroll
+    for (int j4 = 0; j4 < H / 4; ++j4) {
+      const float4 q = wr[j4];
+      pre[4 * j4 + 0] = fmaf(q.x, v, pre[4 * j4 + 0]);
+      pre[4 * j4 + 1] = fmaf(q.y, v, pre[4 * j4 + 1]);
+      pre[4 * j4 + 2] = fmaf(q.z, v, pre[4 * j4 + 2]);
+      pre[4 * j4 + 3] = fmaf(q.w, v, pre[4 * j4 + 3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < H; ++j) h[0][j] = train_act<ACT>(pre[j]);
+  const float* p = b1 + H;
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const float* b2 = p + H * H;
+#pragma unroll
+    for (int j = 0; j < H; ++j) h[l + 1][j] = train_act<ACT>(dot_row<H>(p + j * H, h[l]) + b2[j]);
+    p = b2 + H;
+  }
+}
+
+// acc[j] += row[j] * v  (row: 16-byte aligned shared memory)
+template <int H>
+__device__ __forceinline__ void axpy_row(const float* __restrict__ row, float v, float (&acc)[H]) {
+  const float4* wr = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int j4 = 0; j4 < H / 4; ++j4) {
+    const float4 q = wr[j4];
+    acc[4 * j4 + 0] = fmaf(q.x, v, acc[4 * j4 + 0]);
+    acc[4 * j4 + 1] = fmaf(q.y, v, acc[4 * j4 + 1]);
+    acc[4 * j4 + 2] = fmaf(q.z, v, acc[4 * j4 + 2]);
+    acc[4 * j4 + 3] = fmaf(q.w, v, acc[4 * j4 + 3]);
+  }
+}
+
+// G[base + o*so + i*si] += sum_b D[o][b] * A[i][b]  (i < nI);  G[bbase + o*sb] += sum_b D[o][b]   (bias = row nI of A == 1)
+__device__ __forceinline__ void train_stage_gemm(float* __restrict__ G, const float* __restrict__ A,
+                                                 const float* __restrict__ D, int nO, int nI, int base, int so, int si,
+                                                 int bbase, int sb) {
+  const int nI1 = nI + 1, total = nO * nI1;
+  for (int e = threadIdx.x; e < total; e += kTrainThreads) {
+    const int o = e / nI1, i = e - o * nI1;
+    const float4* a4 = reinterpret_cast<const float4*>(A + i * kStageStride);
+    const float4* d4 = reinterpret_cast<const float4*>(D + o * kStageStride);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+    for (int b = 0; b < kTrainThreads / 4; ++b) {
+      const float4 a = a4[b], q = d4[b];
+      s0 = fmaf(a.x, q.x, s0);
+      s1 = fmaf(a.y, q.y, s1);
+      s2 = fmaf(a.z, q.z, s2);
+      s3 = fmaf(a.w, q.w, s3);
+    }
+    const int idx = i < nI ? base + o * so + i * si : bbase + o * sb;
+    G[idx] += (s0 + s1) + (s2 + s3);
+  }
+}
+
+__device__ __forceinline__ void train_grid_barrier(TrainCtrl* c, unsigned int& phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&c->ticket, 1u);
+    ++phase;
+    const unsigned int target = phase * gridDim.x;
+    while (*reinterpret_cast<volatile unsigned int*>(&c->ticket) < target) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// forward flow of the thread's sample, in place on the column y; returns -log p(x)
+template <int H, int L>
+__device__ __forceinline__ float train_forward_nll(const float* __restrict__ W, int d, int B, int netPp, float* y) {
+  float ld = 0.f;
+  const int w3 = H * d + H + L * (H * H + H), b3 = w3 + d * H;
+  for (int k = 0; k < B; ++k) {
+    const int nin = blk_nin(d, k), i0 = blk_i0(k), nout = blk_nout(d, k), o0 = blk_o0(k);
+    const float* ws = W + (2 * k) * netPp;
+    const float* wt = ws + netPp;
+    float hs[L + 1][H], ht[L + 1][H];
+    train_mlp_hidden<H, L, 0>(ws, d, nin, i0, y, hs);
+    train_mlp_hidden<H, L, 1>(wt, d, nin, i0, y, ht);
+    for (int o = 0; o < nout; ++o) {
+      const int i = o0 + 2 * o;
+      const float s = dot_row<H>(ws + w3 + i * H, hs[L]) + ws[b3 + i];
+      const float t = dot_row<H>(wt + w3 + i * H, ht[L]) + wt[b3 + i];
+      y[i * kTrainThreads] = fmaf(y[i * kTrainThreads], expf(s), t);   // networks.py:296-297
+      ld += s;
+    }
+  }
+  float q = 0.f;
+  for (int i = 0; i < d; ++i) q = fmaf(y[i * kTrainThreads], y[i * kTrainThreads], q);
+  return 0.5f * q + 0.9189385332046727f * (float)d - ld;
+}
+
+template <int H, int L>
+__global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int d = p.d, B = p.B, netP = p.netP, netPp = round4(netP), Psm = 2 * B * netPp;
+  float* W = reinterpret_cast<float*>(smem_raw);
+  float* G = W + Psm;
+  float* y_all = G + Psm;
+  float* gy_all = y_all + d * kTrainThreads;
+  float* stage = gy_all + d * kTrainThreads;
+  const int half = (d + 1) / 2;
+  const int IM = (H > half ? H : half) + 1, OM = H > half ? H : half;
+  float* As = stage;
+  float* At = As + IM * kStageStride;
+  float* Ds = At + IM * kStageStride;
+  float* Dt = Ds + OM * kStageStride;
+  const int tid = threadIdx.x;
+  float* y = y_all + tid;
+  float* gy = gy_all + tid;
+  const int w2off = H * d + H, w3off = w2off + L * (H * H + H), b3off = w3off + d * H, b1off = H * d;
+
+  for (int q = tid; q < Psm; q += kTrainThreads) W[q] = 0.f;
+  __syncthreads();
+  for (int q = tid; q < p.P; q += kTrainThreads) W[train_perm_index<H>(q, d, netP, netPp)] = p.params[q];
+  const bool multi = gridDim.x > 1;
+  float* m_ptr = multi ? p.mv_priv + (size_t)blockIdx.x * 2 * p.P : p.adam_m;
+  float* v_ptr = multi ? m_ptr + p.P : p.adam_v;
+  if (multi && p.do_train) {
+    for (int q = tid; q < p.P; q += kTrainThreads) {
+      m_ptr[q] = p.adam_m[q];
+      v_ptr[q] = p.adam_v[q];
+    }
+  }
+  __syncthreads();
+
+  unsigned int phase = 0;
+  const long long bs = p.batch_size;
+  const long long nmb = p.do_train ? (p.n_train + bs - 1) / bs : 0;
+  for (long long mb = 0; mb < nmb; ++mb) {
+    const long long cnt = (p.n_train - mb * bs) < bs ? (p.n_train - mb * bs) : bs;   // DataLoader keeps the short tail
+    const float inv_bs = 1.0f / (float)cnt;
+    for (int q = tid; q < Psm; q += kTrainThreads) G[q] = 0.f;
+    float loss_t = 0.f;
+    for (long long s0 = (long long)blockIdx.x * kTrainThreads; s0 < cnt; s0 += (long long)gridDim.x * kTrainThreads) {
+      const long long s = s0 + tid;
+      const bool valid = s < cnt;
+      const float vscale = valid ? 1.0f : 0.0f;
+      // ---- load the sample: x[perm[pos]] + jitter * N(0, I)    (trainer.py:390) ---------------------------------
+      if (valid) {
+        const long long pos = mb * bs + s;
+        const long long row = p.perm ? p.perm[pos] : pos;
+        const float* xr = p.x_train + row * d;
+        if (p.jitter != 0.0f) {
+          if (p.noise) {
+            const float* nr = p.noise + pos * d;
+            for (int i = 0; i < d; ++i) y[i * kTrainThreads] = fmaf(p.jitter, nr[i], xr[i]);
+          } else {
+            for (int j = 0; j < (d + 3) / 4; ++j) {
+              float nrm[4];
+              philox_normals4(j, p.epoch, (unsigned int)pos, kTagTrain, p.seed_lo, p.seed_hi, nrm);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (4 * j + q < d) y[(4 * j + q) * kTrainThreads] = fmaf(p.jitter, nrm[q], xr[4 * j + q]);
+            }
+          }
+        } else {
+          for (int i = 0; i < d; ++i) y[i * kTrainThreads] = xr[i];
+        }
+      } else {
+        for (int i = 0; i < d; ++i) y[i * kTrainThreads] = 0.f;
+      }
+      // ---- forward: z = f(x), loss contribution, dL/dz = z / batch ------------------------------------------------------
+      const float nll = train_forward_nll<H, L>(W, d, B, netPp, y);
+      if (valid) loss_t += nll * inv_bs;
+      for (int i = 0; i < d; ++i) gy[i * kTrainThreads] = y[i * kTrainThreads] * inv_bs * vscale;
+      // ---- backward, blocks in reverse; y = output of block k on entry, its input on exit -----------------------------
+      for (int k = B - 1; k >= 0; --k) {
+        const int nin = blk_nin(d, k), i0 = blk_i0(k), nout = blk_nout(d, k), o0 = blk_o0(k);
+        const int sbase = (2 * k) * netPp, tbase = sbase + netPp;
+        const float* ws = W + sbase;
+        const float* wt = W + tbase;
+        float hs[L + 1][H], ht[L + 1][H];
+        train_mlp_hidden<H, L, 0>(ws, d, nin, i0, y, hs);
+        train_mlp_hidden<H, L, 1>(wt, d, nin, i0, y, ht);
+        float dhs[H], dht[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) dhs[j] = dht[j] = 0.f;
+        // output layer: z_i = x_i e^{s} + t, log-det += s   ->   ds = g (z_i - t) - 1/batch, dt = g, dx = g e^{s}
+        __syncthreads();   // previous GEMM finished with the staging buffers
+        for (int o = 0; o < nout; ++o) {
+          const int i = o0 + 2 * o;
+          const float s = dot_row<H>(ws + w3off + i * H, hs[L]) + ws[b3off + i];
+          const float t = dot_row<H>(wt + w3off + i * H, ht[L]) + wt[b3off + i];
+          const float zv = y[i * kTrainThreads], g = gy[i * kTrainThreads];
+          const float ds = (g * (zv - t) - inv_bs) * vscale, dt = g;
+          y[i * kTrainThreads] = (zv - t) * expf(-s);
+          gy[i * kTrainThreads] = g * expf(s);
+          axpy_row<H>(ws + w3off + i * H, ds, dhs);
+          axpy_row<H>(wt + w3off + i * H, dt, dht);
+          Ds[o * kStageStride + tid] = ds;
+          Dt[o * kStageStride + tid] = dt;
+        }
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          As[j * kStageStride + tid] = hs[L][j];
+          At[j * kStageStride + tid] = ht[L][j];
+        }
+        As[H * kStageStride + tid] = 1.0f;
+        At[H * kStageStride + tid] = 1.0f;
+        __syncthreads();
+        train_stage_gemm(G, As, Ds, nout, H, sbase + w3off + o0 * H, 2 * H, 1, sbase + b3off + o0, 2);
+        train_stage_gemm(G, At, Dt, nout, H, tbase + w3off + o0 * H, 2 * H, 1, tbase + b3off + o0, 2);
+        // hidden layers, last to first
+#pragma unroll
+        for (int l = L - 1; l >= 0; --l) {
+          float dps[H], dpt[H];
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            dps[j] = dhs[j] * train_dact<0>(hs[l + 1][j]);
+            dpt[j] = dht[j] * train_dact<1>(ht[l + 1][j]);
+            dhs[j] = dht[j] = 0.f;
+          }
+          const int wl = w2off + l * (H * H + H);
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            axpy_row<H>(ws + wl + j * H, dps[j], dhs);
+            axpy_row<H>(wt + wl + j * H, dpt[j], dht);
+            Ds[j * kStageStride + tid] = dps[j];
+            Dt[j * kStageStride + tid] = dpt[j];
+            As[j * kStageStride + tid] = hs[l][j];
+            At[j * kStageStride + tid] = ht[l][j];
+          }
+          As[H * kStageStride + tid] = 1.0f;
+          At[H * kStageStride + tid] = 1.0f;
+          __syncthreads();
+          train_stage_gemm(G, As, Ds, H, H, sbase + wl, H, 1, sbase + wl + H * H, 1);
+          train_stage_gemm(G, At, Dt, H, H, tbase + wl, H, 1, tbase + wl + H * H, 1);
+        }
+        // input layer
+        {
+          float dps[H], dpt[H];
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            dps[j] = dhs[j] * train_dact<0>(hs[0][j]);
+            dpt[j] = dht[j] * train_dact<1>(ht[0][j]);
+          }
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            Ds[j * kStageStride + tid] = dps[j];
+            Dt[j * kStageStride + tid] = dpt[j];
+          }
+          for (int a = 0; a < nin; ++a) {
+            const int i = i0 + 2 * a;
+            const float xv = y[i * kTrainThreads];
+            As[a * kStageStride + tid] = xv;
+            gy[i * kTrainThreads] += dot_row<H>(ws + i * H, dps) + dot_row<H>(wt + i * H, dpt);
+          }
+          As[nin * kStageStride + tid] = 1.0f;
+          __syncthreads();
+          // both nets share the input: A = As for both
+          train_stage_gemm(G, As, Ds, H, nin, sbase + i0 * H, 1, 2 * H, sbase + b1off, 1);
+          train_stage_gemm(G, As, Dt, H, nin, tbase + i0 * H, 1, 2 * H, tbase + b1off, 1);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- loss of the mini-batch (trainer.py:396) ----------------------------------------------------------------------------
+    {
+      float v = loss_t;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0 && v != 0.f) atomicAdd(&p.ctrl->train_loss, (double)v);
+    }
+    __syncthreads();
+    // ---- several CTAs per mini-batch: sum the partial gradients through global memory --------------------------------
+    if (multi) {
+      float* gb = p.gbuf + (size_t)(mb % 3) * Psm;
+      for (int q = tid; q < Psm; q += kTrainThreads)
+        if (G[q] != 0.f) atomicAdd(gb + q, G[q]);
+      train_grid_barrier(p.ctrl, phase);
+      for (int q = tid; q < Psm; q += kTrainThreads) G[q] = __ldcg(gb + q);
+      // the buffer of mini-batch mb + 2 was last read during mb - 1: every CTA is past that point
+      float* gz = p.gbuf + (size_t)((mb + 2) % 3) * Psm;
+      const int chunk = (Psm + gridDim.x - 1) / gridDim.x;
+      for (int q = blockIdx.x * chunk + tid; q < Psm && q < (int)(blockIdx.x + 1) * chunk; q += kTrainThreads) gz[q] = 0.f;
+      __syncthreads();
+    }
+    if (p.grad_out && mb == nmb - 1 && blockIdx.x == 0)
+      for (int q = tid; q < p.P; q += kTrainThreads) p.grad_out[q] = G[train_perm_index<H>(q, d, netP, netPp)];
+    // ---- Adam (torch.optim.Adam, weight decay added to the gradient), identical in every CTA -----------------------------
+    {
+      const double step = (double)(p.step0 + mb + 1);
+      const float bc1 = (float)(1.0 - pow((double)p.beta1, step));
+      const float bc2s = (float)sqrt(1.0 - pow((double)p.beta2, step));
+      const float step_size = p.lr / bc1;
+      for (int q = tid; q < p.P; q += kTrainThreads) {
+        const int w = train_perm_index<H>(q, d, netP, netPp);
+        const float wv = W[w];
+        const float g = fmaf(p.weight_decay, wv, G[w]);
+        float m = m_ptr[q], v = v_ptr[q];
+        m = m + (g - m) * (1.0f - p.beta1);                 // exp_avg.lerp_(grad, 1 - beta1)
+        v = fmaf(g * g, 1.0f - p.beta2, v * p.beta2);        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        m_ptr[q] = m;
+        v_ptr[q] = v;
+        const float denom = sqrtf(v) / bc2s + p.eps;
+        W[w] = wv - step_size * (m / denom);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- validation: -log p of the held-out samples with the epoch's final weights (trainer.py:405-418) -----------------
+  {
+    float loss_t = 0.f;
+    for (long long s0 = (long long)blockIdx.x * kTrainThreads; s0 < p.n_valid; s0 += (long long)gridDim.x * kTrainThreads) {
+      const long long s = s0 + tid;
+      const bool valid = s < p.n_valid;
+      const float* xr = p.x_valid + (valid ? s : 0) * d;
+      for (int i = 0; i < d; ++i) y[i * kTrainThreads] = valid ? xr[i] : 0.f;
+      const float nll = train_forward_nll<H, L>(W, d, B, netPp, y);
+      if (valid) loss_t += nll;
+    }
+    double v = (double)loss_t;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0 && p.n_valid > 0) atomicAdd(&p.ctrl->val_loss, v);
+  }
+  // ---- publish ----------------------------------------------------------------------------------------------------------------
+  if (blockIdx.x == 0 && p.do_train) {
+    for (int q = tid; q < p.P; q += kTrainThreads) {
+      p.params[q] = W[train_perm_index<H>(q, d, netP, netPp)];
+      if (multi) {
+        p.adam_m[q] = m_ptr[q];
+        p.adam_v[q] = v_ptr[q];
+      }
+    }
+  }
+}
+
+// ---- mean nearest-neighbour distance (training jitter, trainer.py:147-150) ------------------------------------------------
+// One query row per thread (coordinates as columns of a shared-memory matrix), candidates streamed through shared
+// memory in tiles of 128 rows; float64 like the reference's cKDTree on float64 samples.
+__global__ void __launch_bounds__(128, 2) nn_min_dist_kernel(const double* __restrict__ x, long long n, int d,
+                                                             double* __restrict__ sum_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* q = reinterpret_cast<double*>(smem_raw);   // [d][128]
+  double* c = q + (size_t)d * 128;                   // [128][d]
+  const int tid = threadIdx.x;
+  const long long row = (long long)blockIdx.x * 128 + tid;
+  const bool valid = row < n;
+  for (int i = 0; i < d; ++i) q[i * 128 + tid] = valid ? x[row * d + i] : 0.0;
+  double best = INFINITY;
+  for (long long c0 = 0; c0 < n; c0 += 128) {
+    const int m = (int)((n - c0) < 128 ? (n - c0) : 128);
+    __syncthreads();
+    for (int e = tid; e < m * d; e += 128) c[e] = x[c0 * d + e];
+    __syncthreads();
+    for (int j = 0; j < m; ++j) {
+      const double* cj = c + j * d;
+      double s = 0.0;
+      for (int i = 0; i < d; ++i) {
+        const double t = q[i * 128 + tid] - cj[i];
+        s = fma(t, t, s);
+      }
+      if (c0 + j != row && s < best) best = s;
+    }
+  }
+  double v = valid && n > 1 ? sqrt(best) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((tid & 31) == 0) atomicAdd(sum_out, v);
+}
+
+}  // namespace nnb

@@ -135,6 +135,57 @@ class Engine(object):
     def flow_forward(self, x):
         return self._flow(self.lib.nnb_flow_forward, x)
 
+    # ---- flow fitting -----------------------------------------------------------------------
+    B200_MAX_SMEM = 232448     # sharedMemPerBlockOptin on sm_100
+
+    def train_supported(self, d, hidden, num_layers, num_blocks):
+        return bool(self.lib.nnb_train_supported(d, hidden, num_layers, num_blocks, self.B200_MAX_SMEM))
+
+    def train_epoch(self, arch, params, adam_m, adam_v, step0, x_train, x_valid, batch_size, perm=None, jitter=0.0,
+                    lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, seed=0, epoch=0, noise=None,
+                    grad_out=None, do_train=True):
+        """One epoch of Trainer._train + _validate in one kernel launch (include/nnb.h: nnb_train_epoch).
+        arch = (d, hidden, num_layers, num_blocks); params / adam_m / adam_v: flat float32 cuda vectors in
+        state_dict order, updated in place.  Returns (train_loss_sum, val_nll_sum, grid)."""
+        d, hidden, nl, nb = arch
+        a = L.nnb_train_args()
+        a.x_dim, a.hidden_dim, a.num_layers, a.num_blocks = d, hidden, nl, nb
+        for t in (x_train, x_valid):
+            assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[1] == d)
+        for t in (params, adam_m, adam_v, grad_out):
+            assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+        a.x_train, a.n_train = _ptr(x_train), 0 if x_train is None else x_train.shape[0]
+        if perm is not None:
+            assert perm.is_cuda and perm.dtype == torch.int64 and perm.is_contiguous() and perm.numel() == a.n_train
+        a.perm = _ptr(perm)
+        a.batch_size = int(batch_size)
+        a.x_valid, a.n_valid = _ptr(x_valid), 0 if x_valid is None else x_valid.shape[0]
+        if noise is not None:
+            assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous() \
+                and tuple(noise.shape) == (a.n_train, d)
+        a.noise = _ptr(noise)
+        a.jitter = float(jitter)
+        a.seed, a.epoch = int(seed) & (2 ** 64 - 1), int(epoch) & 0xffffffff
+        a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = float(lr), float(betas[0]), float(betas[1]), float(eps), \
+            float(weight_decay)
+        a.step0 = int(step0)
+        a.params, a.adam_m, a.adam_v, a.n_params = _ptr(params), _ptr(adam_m), _ptr(adam_v), params.numel()
+        a.grad_out = _ptr(grad_out)
+        a.do_train = 1 if do_train else 0
+        tl, vl, grid = C.c_double(0.0), C.c_double(0.0), C.c_int(0)
+        a.train_loss_sum_out, a.val_nll_sum_out, a.grid_out = C.pointer(tl), C.pointer(vl), C.pointer(grid)
+        self._check(self.lib.nnb_train_epoch(self.h, C.byref(a), _stream()))
+        self.gpu_launches += 1
+        return tl.value, vl.value, grid.value
+
+    def mean_nn_distance(self, x):
+        """x (n, d) float64 cuda -> mean distance to the nearest other row (nnb_mean_nn_distance)."""
+        assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and x.dim() == 2
+        out = C.c_double(0.0)
+        self._check(self.lib.nnb_mean_nn_distance(self.h, _ptr(x), x.shape[0], x.shape[1], C.byref(out), _stream()))
+        self.gpu_launches += 1
+        return out.value
+
     # ---- target -----------------------------------------------------------------------------
     def set_target(self, d, like_id, like_params=(), t_scale=None, t_shift=None, compute_f64=False,
                    prior_kind=L.NNB_PRIOR_NONE, prior_lo=None, prior_hi=None):

@@ -4,9 +4,12 @@ The facade methods the MCMC loop calls -- forward / inverse / get_samples / get_
 get_prior_samples / get_synthetic_samples / log_probs (trainer.py:247-301) -- run on the hand-written
 CUDA flow kernels through the C ABI (nnb_flow_forward / nnb_flow_inverse); there is no ATen path for
 them.  Fitting (train / _train / _validate, trainer.py:134-245,384-418) keeps the reference's procedure
-(k-d tree jitter, 90/10 split, Adam, early stopping with patience, best-model restore, netG.pt /
-originals.npy / tensorboard artefacts) on PyTorch autograd; after every change of the weights they are
-re-exported to the device (`_sync_device`), and broadcast to all ranks when running multi-GPU.
+(nearest-neighbour jitter, 90/10 split, Adam, early stopping with patience, best-model restore, netG.pt /
+originals.npy / tensorboard artefacts).  One epoch -- every mini-batch's forward pass, backward pass and Adam
+step, plus the validation loss -- is ONE launch of the fused kernel behind nnb_train_epoch (csrc/nnb_train.cuh);
+architectures that kernel does not cover (scale != '', hidden_dim 64, more than two hidden layers) are fitted with
+PyTorch autograd captured in a CUDA graph.  After every change of the weights they are re-exported to the sampling
+kernels (`_sync_device`) and broadcast to all ranks when multi-GPU.
 
 Only flow='nvp' with num_slow=0 is implemented on the device (the hot path north_star
 names); other flows raise NotImplementedError.
@@ -148,6 +151,14 @@ class Trainer(object):
         self.optimizer = torch.optim.Adam(self.netG.parameters(), lr=learning_rate, weight_decay=weight_decay,
                                           capturable=True)
         self._graphed = {}
+        # fused fitting kernel (nnb_train_epoch): flat parameter vector + Adam moments in state_dict order
+        self._arch = (x_dim, hidden_dim, num_layers, num_blocks)
+        self._fused = scale == '' and self.engine.train_supported(*self._arch) \
+            and os.environ.get('NNB_TRAIN_AUTOGRAD', '0') != '1'
+        self._lr, self._wd = learning_rate, weight_decay
+        self._adam_m = self._adam_v = None
+        self._adam_step = 0
+        self._train_seed = None
         self.logger = create_logger(__name__, level=log_level)
         self.log = log
         self.writer = None
@@ -211,15 +222,30 @@ class Trainer(object):
         best_state = torch.nn.utils.parameters_to_vector(params).detach().clone()   # one flat copy, not 36 tensors
         counter = 0
 
+        fused = self._fused
+        if fused:
+            flat = torch.nn.utils.parameters_to_vector(params).detach().clone().contiguous()
+            if self._adam_m is None:
+                self._adam_m, self._adam_v = torch.zeros_like(flat), torch.zeros_like(flat)
+                self._train_seed = int(torch.randint(0, 2 ** 62, (1,)).item())    # follows torch.manual_seed
+            best_state = flat.clone()
+            x_train, x_valid = x_train.contiguous(), x_valid.contiguous()
+
         for epoch in range(1, max_iters + 1):
             self.total_iters += 1
-            train_loss = self._train(epoch, x_train, jitter=training_jitter, l2_norm=l2_norm)
-            validation_loss = self._validate(epoch, x_valid)
+            if fused:
+                train_loss, validation_loss = self._fused_epoch(flat, x_train, x_valid, training_jitter, l2_norm)
+            else:
+                train_loss = self._train(epoch, x_train, jitter=training_jitter, l2_norm=l2_norm)
+                validation_loss = self._validate(epoch, x_valid)
 
             if validation_loss < best_validation_loss:
                 best_validation_epoch = epoch
                 best_validation_loss = validation_loss
-                best_state = torch.nn.utils.parameters_to_vector(params).detach().clone()
+                if fused:
+                    best_state.copy_(flat)
+                else:
+                    best_state = torch.nn.utils.parameters_to_vector(params).detach().clone()
                 counter = 0
 
             if epoch == 1 or epoch % log_interval == 0:
@@ -229,12 +255,16 @@ class Trainer(object):
             if self.path:
                 self.writer.add_scalar('loss', validation_loss, self.total_iters)
                 if epoch % save_interval == 0:
+                    if fused:
+                        _copy_into_params(params, flat)
                     torch.save(self.netG.state_dict(), os.path.join(self.path, 'models', 'netG.pt'))
 
             counter += 1
             if counter > patience:
                 self.logger.info('Epoch [%i] ran out of patience' % (epoch))
                 if self.path:
+                    if fused:
+                        _copy_into_params(params, flat)
                     torch.save(self.netG.state_dict(), os.path.join(self.path, 'models', 'netG.pt'))
                 break
 
@@ -245,19 +275,25 @@ class Trainer(object):
         _copy_into_params(params, best_state)
         self._sync_device()
 
-    def _mean_two_nearest(self, samples, block=2048):
+    def _fused_epoch(self, flat, x_train, x_valid, jitter, l2_norm):
+        """Trainer._train + Trainer._validate (trainer.py:384-418) as one launch of nnb_train_epoch.  The l2 penalty's
+        gradient 2 * l2_norm * w is folded into the weight-decay term (identical update; the reported loss excludes
+        the penalty in the reference too, trainer.py:396-397)."""
+        n, n_valid = x_train.shape[0], x_valid.shape[0]
+        perm = torch.randperm(n, device=x_train.device) if n else None     # DataLoader(shuffle=True)
+        tl, vs, _ = self.engine.train_epoch(
+            self._arch, flat, self._adam_m, self._adam_v, self._adam_step, x_train if n else None,
+            x_valid if n_valid else None, self.batch_size, perm=perm, jitter=jitter, lr=self._lr,
+            weight_decay=self._wd + 2.0 * l2_norm, seed=self._train_seed, epoch=self.total_iters)
+        self._adam_step += (n + self.batch_size - 1) // self.batch_size
+        train_loss = tl / n if n else 0.0
+        validation_loss = (vs / n_valid) / n_valid if n_valid else 0.0      # trainer.py:414-418
+        return train_loss, validation_loss
+
+    def _mean_two_nearest(self, samples):
         """np.mean(cKDTree(samples).query(samples, 2)[0]): mean over samples of (0 + nearest other sample) / 2."""
         x = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)).to(self.device)
-        n = x.shape[0]
-        if n < 2:
-            return 0.0
-        total = torch.zeros((), dtype=torch.float64, device=self.device)
-        for s in range(0, n, block):
-            dm = torch.cdist(x[s:s + block], x, compute_mode='donot_use_mm_for_euclid_dist')
-            rows = torch.arange(dm.shape[0], device=self.device)
-            dm[rows, rows + s] = float('inf')
-            total += dm.min(dim=1).values.sum()
-        return float(total.item()) / (2.0 * n)
+        return 0.5 * self.engine.mean_nn_distance(x)
 
     def _train(self, epoch, x_train, jitter=0.0, l2_norm=0.0):
         """One epoch (trainer.py:384-403): shuffled mini-batches, jittered inputs, Adam on -mean(log p).  Full batches

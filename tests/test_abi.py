@@ -38,7 +38,7 @@ def test_struct_layout_matches_header(lib, tmp_path):
     import subprocess
     from nnest_b200 import _lib
     structs = {'nnb_target': _lib.nnb_target, 'nnb_mcmc_init_args': _lib.nnb_mcmc_init_args,
-               'nnb_mcmc_args': _lib.nnb_mcmc_args}
+               'nnb_mcmc_args': _lib.nnb_mcmc_args, 'nnb_train_args': _lib.nnb_train_args}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nnb.h"', 'int main(void) {']
     for name, cls in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))

@@ -1,0 +1,191 @@
+"""GPU: the fused flow-fitting kernel (nnb_train_epoch, csrc/nnb_train.cuh) through the C ABI against goldens recorded
+from the real reference's Trainer._train / _validate (tests/golden/make_golden_train.py) and the CPU oracle
+(oracle/train.py).  Tolerances: gradients and losses 1e-5 relative (max-norm); weights after k Adam steps are compared
+on the scale of the accumulated update (Adam's first steps move every weight by ~lr whatever the gradient's size)."""
+import logging
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+from oracle import train as otrain
+from helpers import load
+
+pytestmark = pytest.mark.gpu
+
+CASES = ['d2', 'd5_jit', 'd30', 'd10_big', 'd7_h32_l2_b5', 'd50']
+
+
+@pytest.fixture(scope='module')
+def engine():
+    from nnest_b200.engine import Engine
+    return Engine(0)
+
+
+def arch(g):
+    return int(g['d']), int(g['hidden']), int(g['layers']), int(g['blocks'])
+
+
+def flat_of(g, prefix):
+    sd = {k[len(prefix) + 1:]: g[k] for k in g.files if k.startswith(prefix + '/')}
+    return otrain.flatten_state_dict(sd, int(g['blocks']))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def dev(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to('cuda', dtype=dtype).contiguous()
+
+
+def opt_kw(g):
+    return dict(lr=float(g['lr']), betas=tuple(float(b) for b in g['betas']), eps=float(g['eps']),
+                weight_decay=float(g['weight_decay']))
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_gradient_and_losses_match_reference_autograd(engine, name):
+    g = load('train_%s.npz' % name)
+    a = arch(g)
+    assert engine.train_supported(*a)
+    batch = int(g['batch'])
+    w = dev(flat_of(g, 'sd'))
+    m, v, gout = torch.zeros_like(w), torch.zeros_like(w), torch.zeros_like(w)
+    tl, vs, grid = engine.train_epoch(a, w, m, v, 0, dev(g['x_train'][:batch]), dev(g['x_valid']), batch,
+                                      grad_out=gout, **opt_kw(g))
+    assert grid == (batch + 127) // 128
+    assert abs(tl - float(g['first_loss'])) <= 1e-5 * abs(float(g['first_loss']))
+    assert rel(gout.cpu().numpy(), flat_of(g, 'grad')) < 1e-5
+    # Adam moments after one step from zero: m = (1 - beta1) (g + wd w0), v = (1 - beta2) (g + wd w0)^2
+    g_tot = flat_of(g, 'grad').astype(np.float64) + float(g['weight_decay']) * flat_of(g, 'sd')
+    assert rel(m.cpu().numpy(), 0.1 * g_tot) < 1e-5
+    assert rel(v.cpu().numpy(), 0.001 * g_tot ** 2) < 2e-5
+    # validation only: parameters untouched, value = sum of -log p of the oracle
+    w2 = dev(flat_of(g, 'sd'))
+    _, vs0, _ = engine.train_epoch(a, w2, None, None, 0, None, dev(g['x_valid']), batch, do_train=False)
+    nll, _ = otrain.nll_and_grad(flat_of(g, 'sd'), g['x_valid'], *a, want_grad=False)
+    assert abs(vs0 - nll.sum()) <= 1e-5 * abs(nll.sum())
+    assert torch.equal(w2, dev(flat_of(g, 'sd')))
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_two_epochs_match_reference_trainer(engine, name):
+    g = load('train_%s.npz' % name)
+    a = arch(g)
+    batch, jit = int(g['batch']), float(g['jitter'])
+    n, nv = g['x_train'].shape[0], g['x_valid'].shape[0]
+    w0 = flat_of(g, 'sd')
+    w = dev(w0)
+    m, v = torch.zeros_like(w), torch.zeros_like(w)
+    xt, xv = dev(g['x_train']), dev(g['x_valid'])
+    steps = 0
+    for ep, (after, tlk, vlk, nk) in enumerate([('after', 'train_loss', 'val_loss', 'noise'),
+                                                ('after2', 'train_loss2', 'val_loss2', 'noise2')]):
+        tl, vs, _ = engine.train_epoch(a, w, m, v, steps, xt, xv, batch, jitter=jit,
+                                       noise=dev(g[nk]) if jit else None, **opt_kw(g))
+        steps += (n + batch - 1) // batch
+        assert abs(tl / n - float(g[tlk])) <= 2e-5 * abs(float(g[tlk]))
+        ref = flat_of(g, after)
+        assert np.abs(w.cpu().numpy() - ref).max() < 2e-3 * np.abs(ref - w0).max()
+        assert abs(vs / nv / nv - float(g[vlk])) <= 5e-5 * abs(float(g[vlk]))
+
+
+def test_identity_order_equals_explicit_permutation_and_reverse_differs(engine):
+    g = load('train_d5_jit.npz')
+    a = arch(g)
+    n = g['x_train'].shape[0]
+    outs = []
+    for perm in (None, torch.arange(n, device='cuda'), torch.arange(n - 1, -1, -1, device='cuda')):
+        w = dev(flat_of(g, 'sd'))
+        m, v = torch.zeros_like(w), torch.zeros_like(w)
+        engine.train_epoch(a, w, m, v, 0, dev(g['x_train']), dev(g['x_valid']), 100, perm=perm, **opt_kw(g))
+        outs.append(w.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    assert not np.array_equal(outs[0], outs[2])
+
+
+def test_philox_jitter_is_deterministic_and_has_unit_variance(engine):
+    """jitter * N(0, I) from the library's Philox stream: same (seed, epoch) -> same result, another epoch -> another
+    draw; E[-log p] under the noise agrees with the oracle fed numpy normals (4096 x 5 draws)."""
+    g = load('train_d5_jit.npz')
+    a = arch(g)
+    rng = np.random.RandomState(0)
+    x = np.repeat(g['x_train'][:64], 64, axis=0)
+    losses = []
+    for seed, epoch in ((7, 1), (7, 1), (7, 2)):
+        w = dev(flat_of(g, 'sd'))
+        m, v = torch.zeros_like(w), torch.zeros_like(w)
+        tl, _, _ = engine.train_epoch(a, w, m, v, 0, dev(x), None, x.shape[0], jitter=0.3, seed=seed, epoch=epoch,
+                                      **opt_kw(g))
+        losses.append(tl)
+    assert losses[0] == losses[1] and losses[0] != losses[2]
+    ref = [otrain.nll_and_grad(flat_of(g, 'sd'), x + 0.3 * rng.normal(size=x.shape), *a, want_grad=False)[0]
+           for _ in range(4)]
+    mu, sd = np.mean([r.mean() for r in ref]), np.std(np.concatenate(ref)) / np.sqrt(x.shape[0])
+    assert abs(losses[0] - mu) < 6 * sd and abs(losses[2] - mu) < 6 * sd
+
+
+def test_many_ctas_per_minibatch_match_oracle(engine):
+    """batch 4096 on 32 CTAs (cooperative launch, gradient exchange through global memory) against the float64 oracle."""
+    g = load('train_d10_big.npz')
+    a = arch(g)
+    rng = np.random.RandomState(3)
+    x = np.concatenate([g['x_train']] * 9)[:8192 + 1000] + 0.01 * rng.normal(size=(9000, 10)).astype(np.float32)
+    x = x[:8192 + 808].astype(np.float32)
+    w0 = flat_of(g, 'sd')
+    w = dev(w0)
+    m, v = torch.zeros_like(w), torch.zeros_like(w)
+    tl, vs, grid = engine.train_epoch(a, w, m, v, 0, dev(x), dev(g['x_valid']), 4096, **opt_kw(g))
+    assert grid == 32
+    opt = otrain.Adam(w0.size, lr=float(g['lr']), betas=tuple(g['betas']), eps=float(g['eps']),
+                      weight_decay=float(g['weight_decay']))
+    wr, tlr = otrain.train_epoch(w0.astype(np.float64), opt, x, 4096, *a)
+    assert abs(tl / x.shape[0] - tlr) <= 2e-5 * abs(tlr)
+    assert np.abs(w.cpu().numpy() - wr).max() < 2e-3 * np.abs(wr - w0).max()
+    assert rel(m.cpu().numpy(), opt.m) < 1e-4
+    assert abs(vs / 200 / 200 - otrain.validate(wr, g['x_valid'], *a)) <= 5e-5 * abs(otrain.validate(wr, g['x_valid'], *a))
+
+
+def test_unsupported_architecture_is_an_error(engine):
+    assert not engine.train_supported(5, 64, 1, 3)
+    from nnest_b200 import _lib as L
+    w = torch.zeros(otrain.net_floats(5, 64, 1) * 6, device='cuda')
+    with pytest.raises(L.NNBError):
+        engine.train_epoch((5, 64, 1, 3), w, w.clone(), w.clone(), 0, torch.zeros((10, 5), device='cuda'), None, 10)
+
+
+def test_mean_nn_distance_matches_kdtree(engine):
+    import scipy.spatial
+    rng = np.random.RandomState(0)
+    for n, d in ((1000, 2), (777, 30), (300, 50)):
+        x = rng.uniform(-1, 1, size=(n, d))
+        x[5] = x[6]                                  # duplicates give distance 0, as the k-d tree does
+        dists, _ = scipy.spatial.cKDTree(x).query(x, 2)
+        got = engine.mean_nn_distance(dev(x, torch.float64))
+        assert abs(got - dists[:, 1].mean()) <= 1e-12 * dists[:, 1].mean()
+        assert abs(0.5 * got - np.mean(dists)) <= 1e-12
+
+
+def test_trainer_uses_fused_kernel_and_fits(tmp_path):
+    """Trainer.train (trainer.py:134-245) on the fused path: the loss falls, the sampling kernels see the new weights,
+    netG.state_dict() holds them, and the autograd fallback reaches a comparable fit."""
+    from nnest_b200 import Trainer
+    np.random.seed(0)
+    torch.manual_seed(0)
+    cov = np.array([[1.0, 0.8], [0.8, 1.0]])
+    x = np.random.multivariate_normal([1.0, -1.0], cov, size=2000)
+    t = Trainer(2, flow='nvp', log_dir=str(tmp_path), log_level=logging.WARNING, learning_rate=0.001)
+    assert t._fused
+    before = -t.log_probs(x.astype(np.float32)).mean().item()
+    launches0 = t.engine.gpu_launches
+    t.train(x, max_iters=60, jitter=-1)
+    assert t.engine.gpu_launches - launches0 >= 60
+    after = -t.log_probs(x.astype(np.float32)).mean().item()
+    assert after < before - 0.5 and after < 2.6          # entropy of the target: 2.33
+    z, _ = t.forward(x.astype(np.float32))
+    zt, _ = t.netG.forward(torch.from_numpy(x.astype(np.float32)).cuda())
+    assert np.abs(z.cpu().numpy() - zt.detach().cpu().numpy()).max() < 1e-4
+    assert t.best_validation_epoch >= 1
