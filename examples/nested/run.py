@@ -55,7 +55,7 @@ def main(args):
     sampler.run(train_iters=args.train_iters, mcmc_steps=args.mcmc_steps, volume_switch=args.switch,
                 jitter=args.jitter, mcmc_num_chains=args.mcmc_num_chains,
                 mcmc_dynamic_step_size=not args.mcmc_fixed_step_size, log_interval=args.log_interval,
-                update_interval=args.update_interval, chain_stats=not args.no_chain_stats,
+                update_interval=args.update_interval, chain_stats=not args.no_chain_stats, max_iters=args.max_iters,
                 strategy=args.strategy.split(',') if args.strategy else None)
     elapsed = time.time() - start_time
     print('Run time %s' % datetime.timedelta(seconds=elapsed))
@@ -95,6 +95,7 @@ if __name__ == '__main__':
     parser.add_argument('--batch_size', type=int, default=100)
     parser.add_argument('--seed', type=int, default=None)
     parser.add_argument('--strategy', type=str, default='')
+    parser.add_argument('--max_iters', type=int, default=1000000, help="NestedSampler.run(max_iters=...)")
     parser.add_argument('--log_interval', type=int, default=None, help="NestedSampler.run(log_interval=...)")
     parser.add_argument('--update_interval', type=int, default=None, help="NestedSampler.run(update_interval=...)")
     parser.add_argument('-no_chain_stats', action='store_true', help="skip the ESS/jump statistics at log lines")

@@ -90,5 +90,5 @@ if __name__ == '__main__':
     make_train('d5_jit', 5, 300, 64, 100, jitter=0.05, seed=5)
     make_train('d30', 30, 384, 128, 128, seed=30)
     make_train('d10_big', 10, 1000, 200, 500, seed=10)              # several CTAs per mini-batch on the device
-    make_train('d7_h32_l2_b5', 7, 200, 50, 100, hidden=32, layers=2, blocks=5, seed=7)
+    make_train('d7_h32_l2_b2', 7, 200, 50, 100, hidden=32, layers=2, blocks=2, seed=7)
     make_train('d50', 50, 256, 64, 128, seed=50)

@@ -14,7 +14,7 @@ from helpers import load
 
 pytestmark = pytest.mark.gpu
 
-CASES = ['d2', 'd5_jit', 'd30', 'd10_big', 'd7_h32_l2_b5', 'd50']
+CASES = ['d2', 'd5_jit', 'd30', 'd10_big', 'd7_h32_l2_b2', 'd50']
 
 
 @pytest.fixture(scope='module')

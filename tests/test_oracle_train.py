@@ -6,7 +6,7 @@ import pytest
 from oracle import train as otrain
 from helpers import load
 
-CASES = ['d2', 'd5_jit', 'd30', 'd10_big', 'd7_h32_l2_b5', 'd50']
+CASES = ['d2', 'd5_jit', 'd30', 'd10_big', 'd7_h32_l2_b2', 'd50']
 
 
 def arch(g):
