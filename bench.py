@@ -408,8 +408,16 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--kernel', default='auto', choices=['auto', 'ffma', 'tcgen05'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--chains', type=int, default=0, help='development: override the chains per GPU of the workload')
+    ap.add_argument('--mcmc-steps', type=int, default=0, help='development: override the MCMC steps per refill')
+    ap.add_argument('--fixed-scale', action='store_true', help='development: dynamic_step_size=False')
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.chains or args.mcmc_steps or args.fixed_scale:
+        wl.update(chains=args.chains or wl['chains'], mcmc_steps=args.mcmc_steps or wl['mcmc_steps'],
+                  dynamic=wl['dynamic'] and not args.fixed_scale)
+        wl['desc'] += ' [development override: %d chains x %d steps, dynamic=%s]' % (wl['chains'], wl['mcmc_steps'],
+                                                                                      wl['dynamic'])
     if args.impl == 'reference':
         run_reference(args, wl)
     else:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 5
+#define NNB_ABI_VERSION 6
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -286,6 +286,24 @@ int nnb_train_supported(int x_dim, int hidden_dim, int num_layers, int num_block
  * behind the reference's training jitter, 0.2 * np.mean(cKDTree(x).query(x, 2)[0]) = 0.1 * this (trainer.py:147-150).
  */
 int nnb_mean_nn_distance(nnb_handle* h, const double* x, int64_t n, int d, double* out, void* stream);
+
+/*
+ * Chain diagnostics on the device trace (reference nnest/utils/evaluation.py:6-73 as used by Sampler._chain_stats,
+ * nnest/sampler.py:474-492).  trace_x [device] float32 [T][d][n] as written by nnb_mcmc_run (a prefix T' <= T of a longer
+ * trace is a valid input); statistics are taken on v = x * t_scale + t_shift in float64 (t_scale / t_shift [host] d
+ * doubles or NULL = identity).
+ *   nnb_chain_stats:    *moved_out = number of (chain, step >= 1) whose point differs from the previous one in any
+ *                       coordinate, *jump_sum_out = sum of the Euclidean step lengths, sum_out / sumsq_out [host, d,
+ *                       optional] = sum of v and of v^2 per dimension over all chains and steps.
+ *   nnb_chain_autocorr: out [host] (nlags, d): sum over chains and t of (v[t] - mean)(v[t - s] - mean) for the lags
+ *                       s = lag0 .. lag0 + nlags - 1, nlags <= 32; divide by n (T - s) and the variance to obtain
+ *                       evaluation.py:6-14.
+ */
+int nnb_chain_stats(nnb_handle* h, const float* trace_x, int64_t T, int d, int64_t n, const double* t_scale,
+                    const double* t_shift, double* moved_out, double* jump_sum_out, double* sum_out, double* sumsq_out,
+                    void* stream);
+int nnb_chain_autocorr(nnb_handle* h, const float* trace_x, int64_t T, int d, int64_t n, const double* t_scale,
+                       const double* t_shift, const double* mean, int lag0, int nlags, double* out, void* stream);
 
 /*
  * Chain / posterior text files in the reference's layout (nnest/sampler.py:494-511, `_save_samples`): `rows` lines of

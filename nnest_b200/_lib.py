@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libnnb.so')
 
-NNB_ABI_VERSION = 5
+NNB_ABI_VERSION = 6
 NNB_MAX_DIM = 128
 NNB_MAX_BLOCKS = 16
 
@@ -82,6 +82,10 @@ SYMBOLS = {
     'nnb_train_epoch': (C.c_int, [C.c_void_p, C.POINTER(nnb_train_args), C.c_void_p]),
     'nnb_train_supported': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     'nnb_mean_nn_distance': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, _dp, C.c_void_p]),
+    'nnb_chain_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp,
+                                  C.c_void_p]),
+    'nnb_chain_autocorr': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, _dp, _dp, _dp, C.c_int,
+                                     C.c_int, _dp, C.c_void_p]),
     'nnb_write_chain_text': (C.c_int64, [C.c_char_p, C.c_char_p, _dp, C.c_int64, C.c_int, C.c_int]),
 }
 

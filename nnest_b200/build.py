@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 OBJDIR = os.path.join(LIBDIR, 'obj')
 LIB = os.path.join(LIBDIR, 'libnnb.so')
-UNITS = ['nnb_api.cu', 'nnb_tc.cu', 'nnb_train.cu', 'nnb_h16.cu', 'nnb_h32.cu', 'nnb_h64.cu']
+UNITS = ['nnb_api.cu', 'nnb_tc.cu', 'nnb_tc_d2.cu', 'nnb_tc_d10.cu', 'nnb_tc_d30.cu', 'nnb_tc_d50.cu', 'nnb_train.cu', 'nnb_stats.cu', 'nnb_h16.cu', 'nnb_h32.cu', 'nnb_h64.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 NVCC_FLAGS = ARCH + ['-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '-Xptxas', '-v'] + \
     os.environ.get('NNB_EXTRA_NVCC_FLAGS', '').split()
@@ -46,19 +46,36 @@ def _obj(unit):
     return os.path.join(OBJDIR, unit.replace('.cu', '.o'))
 
 
-def _unit_stale(unit):
-    obj = _obj(unit)
-    if not os.path.exists(obj):
-        return True
-    t = os.path.getmtime(obj)
-    return any(os.path.getmtime(d) > t for d in _deps(os.path.join(CSRC, unit)))
+def _digest(unit):
+    """sha1 over the unit, every local header it includes and the compiler flags (mtimes do not survive a copy of the
+    tree to another machine; a rebuild of all units takes minutes)."""
+    import hashlib
+    h = hashlib.sha1(' '.join(NVCC_FLAGS).encode())
+    for path in sorted(_deps(os.path.join(CSRC, unit))):
+        h.update(path[len(CSRC):].encode())
+        h.update(open(path, 'rb').read())
+    return h.hexdigest()
+
+
+def _manifest():
+    import json
+    try:
+        return json.load(open(os.path.join(LIBDIR, 'build_manifest.json')))
+    except Exception:
+        return {}
+
+
+def _unit_stale(unit, manifest=None):
+    manifest = _manifest() if manifest is None else manifest
+    return not os.path.exists(_obj(unit)) or manifest.get(unit) != _digest(unit)
 
 
 def up_to_date():
     if not os.path.exists(LIB):
         return False
-    t = os.path.getmtime(LIB)
-    return not any(_unit_stale(u) for u in UNITS) and all(os.path.getmtime(_obj(u)) <= t for u in UNITS)
+    manifest = _manifest()
+    return not any(_unit_stale(u, manifest) for u in UNITS) and manifest.get('__lib__') == \
+        ' '.join(manifest.get(u, '?') for u in UNITS)
 
 
 def _compile(unit):
@@ -86,6 +103,11 @@ def build(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
+    import json
+    manifest = {u: _digest(u) for u in UNITS}
+    manifest['__lib__'] = ' '.join(manifest[u] for u in UNITS)
+    with open(os.path.join(LIBDIR, 'build_manifest.json'), 'w') as f:
+        json.dump(manifest, f, indent=1)
     return LIB
 
 

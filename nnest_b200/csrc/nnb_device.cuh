@@ -329,10 +329,10 @@ __device__ __forceinline__ T np_pairwise_sum(int n, F term) {
 
 // Returns the likelihood value as double plus whether the reference's result is float32-typed
 // (matters only for the -1e100 clamp of safe_loglike, sampler.py:128).
-template <typename T, typename XG>
+template <typename T, typename XG, int DFIX = 0>   // DFIX > 0: x_dim known at compile time
 __device__ __forceinline__ double loglike_T(const TargetSmem& tg, const XG& xg) {
   using A = Ar<T>;
-  const int d = tg.desc.d;
+  const int d = DFIX > 0 ? DFIX : tg.desc.d;
   Transformed<T, XG> v{tg, xg};
   double out;
   bool f32_typed = false;
@@ -424,9 +424,9 @@ __device__ __forceinline__ double loglike_T(const TargetSmem& tg, const XG& xg) 
 }
 
 // safe_prior (sampler.py:143-163) with UniformPrior (priors.py:39-43): 0 or -inf.
-template <typename T, typename XG>
+template <typename T, typename XG, int DFIX = 0>
 __device__ __forceinline__ double prior_T(const TargetSmem& tg, const XG& xg) {
-  const int d = tg.desc.d;
+  const int d = DFIX > 0 ? DFIX : tg.desc.d;
   if (tg.desc.prior_kind == NNB_PRIOR_NONE) return 0.0;
   bool bad = false;
   if (tg.desc.prior_kind == NNB_PRIOR_BOX_U) {
@@ -451,15 +451,15 @@ __device__ __forceinline__ double prior_T(const TargetSmem& tg, const XG& xg) {
   return bad ? -INFINITY : 0.0;
 }
 
-template <typename XG>
+template <typename XG, int DFIX = 0>
 __device__ __forceinline__ double loglike_any(const TargetSmem& tg, const XG& xg, bool in_f64) {
-  if (tg.desc.compute_f64 || in_f64) return loglike_T<double>(tg, xg);
-  return loglike_T<float>(tg, xg);
+  if (tg.desc.compute_f64 || in_f64) return loglike_T<double, XG, DFIX>(tg, xg);
+  return loglike_T<float, XG, DFIX>(tg, xg);
 }
-template <typename XG>
+template <typename XG, int DFIX = 0>
 __device__ __forceinline__ double prior_any(const TargetSmem& tg, const XG& xg, bool in_f64) {
-  if (tg.desc.compute_f64 || in_f64) return prior_T<double>(tg, xg);
-  return prior_T<float>(tg, xg);
+  if (tg.desc.compute_f64 || in_f64) return prior_T<double, XG, DFIX>(tg, xg);
+  return prior_T<float, XG, DFIX>(tg, xg);
 }
 
 // ---------------------------------------------------------------------------------------------

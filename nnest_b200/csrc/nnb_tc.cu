@@ -3,8 +3,7 @@
 #include <cstring>
 #include <vector>
 
-#include "nnb_host.h"
-#include "nnb_tc_kernels.cuh"
+#include "nnb_tc_launch.cuh"
 
 using namespace nnb;
 
@@ -64,63 +63,23 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
   return NNB_OK;
 }
 
-template <int MODE, int NPART>
-static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t st) {
-  const int tdoubles = target_doubles(h->tdesc.d, h->tdesc.n_params);
-  // chains per CTA: spread the batch evenly over all SMs in units of a warp (32 chains), at most 4 tiles of 128
-  long long cpc = ((p.n + h->sm_count - 1) / h->sm_count + 31) / 32 * 32;
-  if (cpc > 128 * kTcMaxTiles) cpc = 128 * kTcMaxTiles;
-  if (cpc < 32) cpc = 32;
-  int ntiles = (int)((cpc + 127) / 128);
-  while (ntiles > 1 && tc_smem_bytes(h->tcflow, tdoubles, ntiles, NPART) > (size_t)h->max_smem) {
-    --ntiles;
-    cpc = 128 * ntiles;
-  }
-  size_t sm = tc_smem_bytes(h->tcflow, tdoubles, ntiles, NPART);
-  const size_t one_cta_per_sm = 116 * 1024;   // TMEM is allocated per CTA: keep a single CTA resident per SM
-  if (sm < one_cta_per_sm) sm = one_cta_per_sm;
-  NNB_CUDA(h, nnb_set_smem(mcmc_tc_kernel<MODE, NPART>, sm));
-  const int grid = (int)((p.n + cpc - 1) / cpc);
-  const int block = ntiles * 128 * NPART;   // fixed warp slots; a partial last tile leaves some idle
-  p.cpc = (int)cpc;
-  // Persistent path: all steps in ONE cooperative launch (every CTA resident, one per SM), the global accept count
-  // of each step travels through a grid barrier.  Needs grid <= SM count; otherwise one launch per step.
-  static const bool no_coop = getenv("NNB_NO_COOP") != nullptr;
-  if (!no_coop && p.dynamic && h->coop_supported && grid <= h->sm_count && steps > 1) {
-    if (h->step_counts_cap < steps) {
-      if (h->d_step_counts) cudaFree(h->d_step_counts);
-      h->d_step_counts = nullptr;
-      NNB_CUDA(h, cudaMalloc(&h->d_step_counts, sizeof(unsigned int) * steps));
-      h->step_counts_cap = steps;
-    }
-    NNB_CUDA(h, cudaMemsetAsync(h->d_step_counts, 0, sizeof(unsigned int) * steps, st));
-    p.s0 = 0; p.nsteps = steps; p.coop = 1; p.step_counts = h->d_step_counts;
-    void* args[] = {(void*)&h->tcflow, (void*)&h->d_weights_tc, (void*)&h->tdesc, (void*)&h->d_target, (void*)&p};
-    NNB_CUDA(h, cudaLaunchCooperativeKernel((const void*)mcmc_tc_kernel<MODE, NPART>, dim3(grid), dim3(block), args, sm, st));
-    h->last_launches = 1;
-    return NNB_OK;
-  }
-  p.coop = 0; p.step_counts = nullptr;
-  if (p.dynamic) {
-    for (int s = 0; s < steps; ++s) {
-      p.s0 = s; p.nsteps = 1;
-      mcmc_tc_kernel<MODE, NPART><<<grid, block, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p);
-    }
-  } else {
-    p.s0 = 0; p.nsteps = steps;
-    mcmc_tc_kernel<MODE, NPART><<<grid, block, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p);
-  }
-  NNB_CUDA(h, cudaGetLastError());
-  h->last_launches = p.dynamic ? steps : 1;
-  return NNB_OK;
-}
-
 int nnb_launch_mcmc_tc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st) {
   // two threads per chain unless NNB_TC_NPART=1 (development switch)
   static const int npart = [] { const char* e = getenv("NNB_TC_NPART"); return (e && e[0] == '1') ? 1 : 2; }();
   if (npart == 1)
-    return p.mode == NNB_MODE_MH ? launch_tc_mode<NNB_MODE_MH, 1>(h, p, steps, st)
-                                 : launch_tc_mode<NNB_MODE_HARD, 1>(h, p, steps, st);
-  return p.mode == NNB_MODE_MH ? launch_tc_mode<NNB_MODE_MH, 2>(h, p, steps, st)
-                               : launch_tc_mode<NNB_MODE_HARD, 2>(h, p, steps, st);
+    return p.mode == NNB_MODE_MH ? launch_tc_mode<NNB_MODE_MH, 1, 0>(h, p, steps, st)
+                                 : launch_tc_mode<NNB_MODE_HARD, 1, 0>(h, p, steps, st);
+  // the reference's default architecture at the dimensions of the named workloads: fully unrolled kernels
+  static const bool generic_only = getenv("NNB_TC_GENERIC") != nullptr;
+  if (!generic_only && h->tcflow.L == 1 && h->tcflow.B == 3) {
+    switch (h->tcflow.d) {
+      case 2: return nnb_launch_mcmc_tc_fixed<2>(h, p, steps, st);
+      case 10: return nnb_launch_mcmc_tc_fixed<10>(h, p, steps, st);
+      case 30: return nnb_launch_mcmc_tc_fixed<30>(h, p, steps, st);
+      case 50: return nnb_launch_mcmc_tc_fixed<50>(h, p, steps, st);
+      default: break;
+    }
+  }
+  return p.mode == NNB_MODE_MH ? launch_tc_mode<NNB_MODE_MH, 2, 0>(h, p, steps, st)
+                               : launch_tc_mode<NNB_MODE_HARD, 2, 0>(h, p, steps, st);
 }

@@ -146,26 +146,37 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float*
 // Flow inverse of one tile, in place on y (shared memory, stride ys).  Returns this thread's share of
 // log|det dx/dz| of the chain (the sum over the chain's NPART threads is the log-det).  Ends with a tile barrier:
 // afterwards every thread of the tile sees the complete x.
-template <int NPART>
+template <int NPART, int DD>
 __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const float* __restrict__ wsm, uint32_t wsm_u32,
-                                                 TcTile& t, float* y, int ys, float* ld_slot) {
-  const int d = f.d, L = f.L;
+                                                 TcTile& t, float* y, int ys, float* ld_slot, int* bad_slot,
+                                                 const float* __restrict__ lof, const float* __restrict__ hif,
+                                                 bool box_check, bool& bad) {
+  // DD > 0: x_dim, num_layers = 1 and num_blocks = 3 (the reference's defaults) are compile-time constants: every loop
+  // below unrolls and every shared-memory / TMEM offset becomes an immediate
+  const int d = DD > 0 ? DD : f.d, L = DD > 0 ? 1 : f.L, nB = DD > 0 ? 3 : f.B;
   float ld = 0.f;
-  for (int k = f.B - 1; k >= 0; --k) {
+  bad = false;
+#pragma unroll
+  for (int k = nB - 1; k >= 0; --k) {
     const int nin = blk_nin(d, k), i0 = blk_i0(k), nout = blk_nout(d, k), o0 = blk_o0(k);
     const int K1 = round8(nin), N3 = round16(nout);
-    const int base = f.off[k];
-    // ---- layer 1: A = masked inputs (dims with mask == 1), zero padded to K1 --------------------------
-    for (int c0 = 8 * t.part; c0 < K1; c0 += 8 * NPART) {
-      uint32_t hi[8], lo[8];
+    const int base = DD > 0 ? (k > 0 ? tc_block_floats(d, L, 0) : 0) + (k > 1 ? tc_block_floats(d, L, 1) : 0) : f.off[k];
+    // ---- layer 1: A = masked inputs (dims with mask == 1), zero padded to K1.  Only the first block reads them from
+    // y: the inputs of every later block are exactly the dims the previous block's output epilogue has just produced
+    // (masks alternate, input a of block k-1 == output o of block k), and that epilogue stores them straight into the
+    // A columns -- same thread, same column chunk, no shared-memory round trip and no tile barrier in between.
+    if (k == nB - 1) {
+      for (int c0 = 8 * t.part; c0 < K1; c0 += 8 * NPART) {
+        uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int a = c0 + j;
-        float v = a < nin ? y[(i0 + 2 * a) * ys] : 0.f;
-        tc::split_tf32(v, hi[j], lo[j]);
+        for (int j = 0; j < 8; ++j) {
+          const int a = c0 + j;
+          float v = a < nin ? y[(i0 + 2 * a) * ys] : 0.f;
+          tc::split_tf32(v, hi[j], lo[j]);
+        }
+        tc::tmem_st8(t.lane_tmem + c0, hi);
+        tc::tmem_st8(t.lane_tmem + 32 + c0, lo);
       }
-      tc::tmem_st8(t.lane_tmem + c0, hi);
-      tc::tmem_st8(t.lane_tmem + 32 + c0, lo);
     }
     {
       const uint32_t b_hi = wsm_u32 + 4u * base, b_lo = b_hi + 4u * 32u * K1;
@@ -206,45 +217,58 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
     }
     const float* b3s = wsm + off + 64 * N3;
     const float* b3t = b3s + N3;
-    // x = (z - t) * exp(-log_s), ld -= log_s on the dims with mask == 0   (networks.py:300-309)
+    // x = (z - t) * exp(-log_s), ld -= log_s on the dims with mask == 0   (networks.py:300-309).  The values a dim keeps
+    // (its last update: blocks 1 and 0) are tested against the prior box right here (priors.py:39-43).
+    const bool chk = box_check && k <= 1;
     for (int c0 = 8 * t.part; c0 < nout; c0 += 8 * NPART) {
-      uint32_t rs[8], rt[8];
+      uint32_t rs[8], rt[8], hi[8], lo[8];
       tc::tmem_ld8(t.lane_tmem + 64 + c0, rs);
       tc::tmem_ld8(t.lane_tmem + 96 + c0, rt);
       tc::wait_ld();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int o = c0 + j;
+        float xv = 0.f;
         if (o < nout) {
           const float ls = __uint_as_float(rs[j]) + b3s[o];
           const float tt = __uint_as_float(rt[j]) + b3t[o];
           float* yp = y + (o0 + 2 * o) * ys;
-          *yp = (*yp - tt) * tc_exp(-ls);
+          xv = (*yp - tt) * tc_exp(-ls);
+          *yp = xv;
           ld -= ls;
+          if (chk) bad |= (xv < lof[o0 + 2 * o]) | (xv > hif[o0 + 2 * o]);
         }
+        tc::split_tf32(xv, hi[j], lo[j]);
+      }
+      if (k > 0) {   // A operand of block k-1's first layer
+        tc::tmem_st8(t.lane_tmem + c0, hi);
+        tc::tmem_st8(t.lane_tmem + 32 + c0, lo);
       }
     }
-    if (NPART > 1) {
-      if (k == 0) *ld_slot = ld;   // the chain's threads exchange their log-det shares through shared memory
-      tile_sync(t);                // the next block (or the caller) reads dims updated by the partner thread
+    if (NPART > 1 && k == 0) {
+      ld_slot[0] = ld;                          // the chain's threads exchange their log-det shares and box flags through
+      if (t.part == 1) *bad_slot = bad;         // shared memory (the flag slot carries the accept decision later on)
+      tile_sync(t);                             // every thread of the tile now sees the complete x
     }
   }
   return ld;
 }
 
 // one out-of-line copy of the likelihood / prior switch per kernel (code size)
+template <int DD>
 static __device__ __noinline__ double tc_loglike(const TargetSmem& tg, const float* y) {
   SmemRow row{y};
-  return loglike_any(tg, row, false);
+  return loglike_any<SmemRow, DD>(tg, row, false);
 }
+template <int DD>
 static __device__ __noinline__ double tc_prior(const TargetSmem& tg, const float* y) {
   SmemRow row{y};
-  return prior_any(tg, row, false);
+  return prior_any<SmemRow, DD>(tg, row, false);
 }
 
 // shared-memory carve-up (bytes): [tc weights][target doubles][y: ntiles*d*128 f][zp: ntiles*d*128 f]
-//   [nz: ntiles*d*128 f][ldp: ntiles*NPART*128 f][flag: ntiles*128 i][mbar: 4 x 8][tmem base 8][red 32 x 4]
-template <int MODE, int NPART>
+//   [nz: ntiles*d*128 f][ldp: ntiles*(NPART + 1)*128 f][flag: ntiles*128 i][mbar: 4 x 8][tmem base 8][red 32 x 4]
+template <int MODE, int NPART, int DD>
 __global__ void __launch_bounds__(kTcMaxTiles * 128 * NPART, 1)
 mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, const double* __restrict__ tgt_g,
                McmcParams p) {
@@ -252,7 +276,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   // A CTA owns p.cpc chains (a multiple of 32): full tiles of 128 plus, possibly, a partial last tile, so that
   // the batch can be spread evenly over all SMs (65 536 chains = 148 x 448 - a few).  Threads are laid out
   // tile-major, then part-major; a partial tile simply has fewer warps per part (lane quarters).
-  const int d = f.d;
+  const int d = DD > 0 ? DD : f.d;
   const int cpc = p.cpc;
   const int ntiles = (cpc + 127) >> 7;
   float* wsm = reinterpret_cast<float*>(smem_raw);
@@ -262,7 +286,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   float* zp_all = y_all + (size_t)ntiles * d * 128;
   float* nz_all = zp_all + (size_t)ntiles * d * 128;
   float* ldp_all = nz_all + (size_t)ntiles * d * 128;
-  int* flag_all = reinterpret_cast<int*>(ldp_all + (size_t)ntiles * NPART * 128);
+  int* flag_all = reinterpret_cast<int*>(ldp_all + (size_t)ntiles * (NPART + 1) * 128);
   uint64_t* mbars = reinterpret_cast<uint64_t*>(flag_all + (size_t)ntiles * 128);
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(mbars + 2 * kTcMaxTiles);
 
@@ -315,7 +339,8 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   const bool active = c < n && m < rows;   // idle quarter warps of a partial tile own no chain
   float* y = y_all + (size_t)tile * d * 128 + m;
   float* zp = zp_all + (size_t)tile * d * 128 + m;
-  float* ldp = ldp_all + (size_t)tile * NPART * 128 + m;
+  float* ldp = ldp_all + (size_t)tile * (NPART + 1) * 128 + m;   // [ld: NPART x 128][u: 128]
+  float* u_slot = ldp + NPART * 128;
   int* flag = flag_all + (size_t)tile * 128 + m;
   const unsigned int chain = (unsigned int)(p.chain_offset + (unsigned long long)c);
   unsigned int acc_total = 0, ncall_total = 0;
@@ -360,9 +385,20 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   // The noise of step s+1 does not depend on the adapted scale, so it is produced while step s finishes: jc blocks
   // by the chain's second thread during the accept phase of the first, the rest by both after the CTA has arrived
   // at the grid barrier (overlapping its latency).
-  const int jc = NPART > 1 ? (3 * nj + 4) / 8 : 0;
+  const int jc = NPART > 1 ? (p.tc_jc >= 0 ? (p.tc_jc < nj ? p.tc_jc : nj) : (3 * nj + 4) / 8) : 0;
   const bool philox = p.replay_normals == nullptr;
+  // the accept test's uniform of step `step_abs` (sampler.py:334), drawn ahead of time by the chain's last thread
+  auto gen_uniform = [&](unsigned int step_abs, int sidx) {
+    uint4 r = philox4x32_10(0u, step_abs, chain, kTagUniform, p.seed_lo, p.seed_hi);
+    const float u = uniform01(r.x);
+    *u_slot = u;
+    if (p.dump_uniforms) p.dump_uniforms[(size_t)sidx * ns + (size_t)c] = u;
+  };
+  const bool philox_u = p.replay_uniforms == nullptr;
   if (tile_active && active && philox) gen_normals(part, nj, NPART, p.step_offset + (unsigned int)(p.s0 + 1), p.s0);
+  if (tile_active && active && philox_u && part == NPART - 1) gen_uniform(p.step_offset + (unsigned int)(p.s0 + 1), p.s0);
+  // prior box on the flow's own coordinates (nested sampling): tested inside the output epilogues of the flow
+  const bool fast_box = MODE == NNB_MODE_HARD && tg.desc.prior_kind == NNB_PRIOR_BOX_U && (DD > 0 || f.B >= 2);
 
   for (int s = p.s0 + 1; s <= p.s0 + p.nsteps; ++s) {
     const float scale_f = p.coop ? *reinterpret_cast<volatile float*>(co_scale_s)
@@ -397,36 +433,37 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       __syncwarp();
       if (NPART > 1) tile_sync(t);   // layer 1 reads dims written by the partner thread
       // ---- flow inverse on the tensor cores (all threads of the tile, converged) ----------------------------------
-      const float ld_part = tc_flow_inverse<NPART>(f, wsm, wsm_u32, t, y, 128, ldp + part * 128);
+      bool bad_part;
+      const float ld_part = tc_flow_inverse<NPART, DD>(f, wsm, wsm_u32, t, y, 128, ldp + part * 128, flag, tg.lof, tg.hif,
+                                                   fast_box, bad_part);
       // ---- accept / reject: thread 0 of the chain; thread 1 starts on the next step's noise -------------------------
       if (active && part == 0) {
         float ld_prop = ld_part;
         if (NPART > 1) ld_prop = ld_part + ldp[128];
-        float u01;
-        if (p.replay_uniforms) {
-          u01 = p.replay_uniforms[(size_t)(s - 1) * ns + (size_t)c];
-        } else {
-          uint4 r = philox4x32_10(0u, step_abs, chain, kTagUniform, p.seed_lo, p.seed_hi);
-          u01 = uniform01(r.x);
-          if (p.dump_uniforms) p.dump_uniforms[(size_t)(s - 1) * ns + (size_t)c] = u01;
-        }
+        const float u01 = philox_u ? *u_slot : p.replay_uniforms[(size_t)(s - 1) * ns + (size_t)c];
         double lp = 0.0, logp_prop = 0.0;
         if (MODE == NNB_MODE_HARD) {
           float lr = __fsub_rn(ld_prop, ld_cur);
-          logp_prop = tc_prior(tg, y);
+          if (fast_box) {
+            bool bad = bad_part;
+            if (NPART > 1) bad |= *flag != 0;
+            logp_prop = bad ? -INFINITY : 0.0;
+          } else {
+            logp_prop = tc_prior<DD>(tg, y);
+          }
           if (logp_prop < -1e30) lr = -INFINITY;
           float ratio = expf(lr);
           if (ratio > 1.0f) ratio = 1.0f;
           const bool m1 = u01 < ratio;
           if (m1) {
-            lp = tc_loglike(tg, y);
+            lp = tc_loglike<DD>(tg, y);
             ncall = 1;
             accept = isfinite(lp) && (lp > p.loglstar);
           }
         } else {
-          lp = tc_loglike(tg, y);
+          lp = tc_loglike<DD>(tg, y);
           ncall = 1;
-          logp_prop = tc_prior(tg, y);
+          logp_prop = tc_prior<DD>(tg, y);
           double lr = (double)__fsub_rn(ld_prop, ld_cur) + (lp - logl_cur) + (logp_prop - logp_cur);
           double ratio = exp(lr);
           if (ratio > 1.0) ratio = 1.0;
@@ -514,6 +551,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
     }
     // ---- rest of the next step's noise (overlaps the grid barrier) --------------------------------------------------------
     if (tile_active && active && more && philox) gen_normals(jc + part, nj, NPART, step_abs + 1u, s);
+    if (tile_active && active && more && philox_u && part == NPART - 1) gen_uniform(step_abs + 1u, s);
     if (p.coop) {
       if (threadIdx.x == 0) {
         const unsigned int target = (unsigned int)(si + 1) * gridDim.x;
@@ -554,7 +592,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
 
 __host__ inline size_t tc_smem_bytes(const TcFlowDesc& f, int tdoubles, int ntiles, int npart) {
   return (size_t)f.total_floats * 4 + (size_t)tdoubles * 8 + 3 * (size_t)ntiles * f.d * 128 * 4 +
-         (size_t)ntiles * npart * 128 * 4 + (size_t)ntiles * 128 * 4 + 2 * kTcMaxTiles * 8 + 8 + 32 * 4;
+         (size_t)ntiles * (npart + 1) * 128 * 4 + (size_t)ntiles * 128 * 4 + 2 * kTcMaxTiles * 8 + 8 + 32 * 4;
 }
 
 }  // namespace nnb
