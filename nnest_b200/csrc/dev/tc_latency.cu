@@ -34,7 +34,7 @@ __global__ void rt_kernel(long long* out, int nmma_groups, int n, int ksteps, in
     long long c1 = clock64();
     if (warp == 0) {
       fence_after_sync();
-      if ((threadIdx.x & 31) == 0) {
+      if (elect_one()) {
         for (int g = 0; g < nmma_groups; ++g)
           mma_3xtf32(tb + 64 + 16 * (g & 1), tb, tb + 32, smem_u32(sm) + 4096 * g, smem_u32(sm) + 4096 * g + 2048, ksteps, n, false);
         mma_commit(&mbar);

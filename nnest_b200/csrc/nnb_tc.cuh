@@ -62,6 +62,20 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// exactly one lane of the (converged) warp gets true.  ptxas knows that the guarded region runs on a single thread, so
+// register operands of the tcgen05 instructions inside move to uniform registers without a per-operand waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- descriptors ------------------------------------------------------------------------------------------
 // instruction descriptor: D f32, A/B tf32, both K-major, M = 128, N = n (cute::UMMA::InstrDescriptor bit layout)
 __host__ __device__ inline uint32_t idesc_tf32_m128(uint32_t n) {

@@ -96,7 +96,7 @@ __device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1) {
   tile_sync(t);
   if (t.issuer >= 0) {   // warp-uniform: the whole warp takes the branch so that no lane spins next to the issuing lane
     tc::fence_after_sync();
-    if ((threadIdx.x & 31) == 0) {
+    if (tc::elect_one()) {
       if (t.issuer == 0) issue0(); else issue1();
       tc::mma_commit(t.mbar + t.issuer);
     }

@@ -186,6 +186,50 @@ class Engine(object):
         self.gpu_launches += 1
         return out.value
 
+    # ---- chain diagnostics on the device trace ----------------------------------------------
+    def chain_stats(self, trace_x, steps=None, t_scale=None, t_shift=None, mean=None, std=None):
+        """Acceptance, effective sample size per dimension and mean jump distance (nnest/utils/evaluation.py:17-73, as
+        Sampler._chain_stats uses them) of a device trace float32 [T][d][N]; `steps` restricts it to the first steps + 1
+        points.  mean / std default to those of the (transformed) samples; the ESS divides by `std` as the reference does."""
+        assert trace_x.is_cuda and trace_x.dtype == torch.float32 and trace_x.is_contiguous() and trace_x.dim() == 3
+        T, d, n = trace_x.shape
+        if steps is not None:
+            T = min(T, int(steps) + 1)
+        ka, ts = _darr(np.broadcast_to(1.0 if t_scale is None else t_scale, (d,)))
+        kb, tb = _darr(np.broadcast_to(0.0 if t_shift is None else t_shift, (d,)))
+        moved, jump = C.c_double(0.0), C.c_double(0.0)
+        s1, s2 = np.zeros(d), np.zeros(d)
+        want = mean is None or std is None
+        self._check(self.lib.nnb_chain_stats(self.h, _ptr(trace_x), T, d, n, ts, tb, C.byref(moved), C.byref(jump),
+                                             s1.ctypes.data_as(L._dp) if want else None,
+                                             s2.ctypes.data_as(L._dp) if want else None, _stream()))
+        self.gpu_launches += 2 if want else 1
+        total = float(n) * (T - 1)
+        acceptance = moved.value / total if total else 0.0
+        jump_distance = jump.value / total if total else 0.0
+        if mean is None:
+            mean = s1 / (float(n) * T)
+        if std is None:
+            std = np.sqrt(np.maximum(s2 / (float(n) * T) - (s1 / (float(n) * T)) ** 2, 0.0))
+        km, mu = _darr(np.broadcast_to(mean, (d,)))
+        var = np.broadcast_to(np.asarray(std, dtype=np.float64), (d,))
+        ess = np.ones(d)
+        out = np.zeros((32, d))
+        s, done = 1, False
+        while s < T and not done:                       # evaluation.py:30-37, 32 lags per launch
+            nl = min(32, T - s)
+            self._check(self.lib.nnb_chain_autocorr(self.h, _ptr(trace_x), T, d, n, ts, tb, mu, s, nl,
+                                                    out.ctypes.data_as(L._dp), _stream()))
+            self.gpu_launches += 1
+            for l in range(nl):
+                p = out[l] / (float(n) * (T - s - l)) / var
+                if np.sum(p > 0.05) == 0:
+                    done = True
+                    break
+                ess = ess + np.where(p > 0.05, 2.0 * p * (1.0 - float(s + l) / T), 0.0)
+            s += nl
+        return acceptance, T / ess, jump_distance
+
     # ---- target -----------------------------------------------------------------------------
     def set_target(self, d, like_id, like_params=(), t_scale=None, t_shift=None, compute_f64=False,
                    prior_kind=L.NNB_PRIOR_NONE, prior_lo=None, prior_hi=None):

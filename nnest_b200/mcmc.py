@@ -73,9 +73,11 @@ class MCMCSampler(Sampler):
 
         samples = samples * std + mean                               # transform on (chain, step, dim)
         if mcmc_steps > 1:
-            self._chain_stats(samples)
+            # mcmc.py:119-120; the statistics of the transformed trace are taken on the device copy
+            self._chain_stats(None, trace=self._device_trace, t_scale=std, t_shift=mean)
+        self._device_trace = None
 
-        self.samples = np.concatenate((samples, derived_samples), axis=2)
+        self.samples = np.concatenate((samples, derived_samples), axis=2) if derived_samples.shape[2] else samples
         self.latent_samples = latent_samples
         self.loglikes = loglikes
         self.logger.info("ncall: {:d}\n".format(int(self.total_calls)))

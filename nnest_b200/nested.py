@@ -306,8 +306,7 @@ class NestedSampler(Sampler):
                 if accept_point and it > 0 and it % log_interval == 0 and primary:
                     if chain_stats and batch.get('trace_x') is not None:
                         acceptance, ess, jump_distance = self._chain_stats(
-                            batch['trace_x'].permute(2, 0, 1), mean=np.mean(active_u, axis=0),
-                            std=np.std(active_u, axis=0))
+                            None, trace=batch['trace_x'], mean=np.mean(active_u, axis=0), std=np.std(active_u, axis=0))
                     else:
                         acceptance, ess, jump_distance = np.nan, np.array([np.nan]), np.nan
                     self.logger.info(

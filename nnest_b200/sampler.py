@@ -181,6 +181,13 @@ class Sampler(object):
             self._transform_fn = safe_transform
         self._install_target()
 
+    def _affine(self):
+        """(scale, shift) of the current transform as float64 vectors (identity when there is none)."""
+        d = self.x_dim
+        sc = np.ones(d) if self._t_scale is None else np.broadcast_to(np.asarray(self._t_scale, dtype=np.float64), (d,))
+        sh = np.zeros(d) if self._t_shift is None else np.broadcast_to(np.asarray(self._t_shift, dtype=np.float64), (d,))
+        return sc, sh
+
     def _install_target(self):
         prior = self._prior_obj
         if prior is None:
@@ -297,13 +304,14 @@ class Sampler(object):
         latent_samples = out['trace_z'].cpu().numpy().transpose(2, 0, 1)
         loglikes = out['trace_logl'].cpu().numpy().transpose(1, 0)
         derived_samples = np.empty((st.n, mcmc_steps + 1, 0))
+        self._device_trace = out['trace_x']          # (S+1, d, N) on the device, for the chain statistics
+        ts, tb = self._affine()
         for it in range(1, mcmc_steps + 1):
             if output_interval is not None and it % output_interval == 0:
                 self._save_samples(self.transform(samples[:, :it + 1].reshape(-1, self.x_dim)).reshape(
                     st.n, it + 1, self.x_dim), loglikes[:, :it + 1])
             if stats_interval is not None and it % stats_interval == 0:
-                self._chain_stats(self.transform(samples[:, :it + 1].reshape(-1, self.x_dim)).reshape(
-                    st.n, it + 1, self.x_dim), step=it)
+                self._chain_stats(None, step=it, trace=self._device_trace, t_scale=ts, t_shift=tb)
         return samples, latent_samples, derived_samples, loglikes, out['scale'], ncall
 
     def _mcmc_refill(self, mcmc_steps, init_samples, init_loglikes, loglstar, step_size, dynamic_step_size,
@@ -320,25 +328,24 @@ class Sampler(object):
     def _plot_trace(self, samples, latent_samples):
         pass    # plotting is outside the accelerated path
 
-    def _chain_stats(self, samples, mean=None, std=None, step=None):
-        """Acceptance, ESS and jump distance with the reference's definitions (sampler.py:474-492); `samples` may be
-        a numpy array or a device tensor of shape (chains, steps, dim)."""
-        if isinstance(samples, np.ndarray) and samples.size >= (1 << 22) and torch.cuda.is_available():
-            # large traces: the O(chains x steps x lags) statistics run on the device (nnest/utils/evaluation.py is a
-            # Python double loop over chains and steps in the reference)
+    def _chain_stats(self, samples, mean=None, std=None, step=None, trace=None, t_scale=None, t_shift=None):
+        """Acceptance, ESS and jump distance with the reference's definitions (sampler.py:474-492).  With `trace` (the
+        device trace float32 [T][d][N] nnb_mcmc_run wrote) the statistics of trace * t_scale + t_shift are computed by
+        the CUDA kernels behind nnb_chain_stats / nnb_chain_autocorr and `samples` is ignored; host arrays
+        (chains, steps, dim) go through the vectorised NumPy restatement in utils/evaluation.py."""
+        if trace is not None:
+            acceptance, ess, jump_distance = self.engine.chain_stats(trace, steps=step, t_scale=t_scale,
+                                                                     t_shift=t_shift, mean=mean, std=std)
+        else:
+            acceptance = acceptance_rate(samples)
+            flat = samples.reshape(-1, samples.shape[2])
             if mean is None:
-                mean = samples.reshape(-1, samples.shape[2]).mean(0, dtype=np.float64)
+                mean = flat.mean(0) if isinstance(flat, np.ndarray) else flat.double().mean(0).cpu().numpy()
             if std is None:
-                std = samples.reshape(-1, samples.shape[2]).std(0, dtype=np.float64)
-            samples = torch.from_numpy(np.ascontiguousarray(samples)).to(self.device)
-        acceptance = acceptance_rate(samples)
-        flat = samples.reshape(-1, samples.shape[2])
-        if mean is None:
-            mean = flat.mean(0) if isinstance(flat, np.ndarray) else flat.double().mean(0).cpu().numpy()
-        if std is None:
-            std = flat.std(0) if isinstance(flat, np.ndarray) else flat.double().std(0, unbiased=False).cpu().numpy()
-        ess = effective_sample_size(samples, mean, std)
-        jump_distance = mean_jump_distance(samples)
+                std = flat.std(0) if isinstance(flat, np.ndarray) else \
+                    flat.double().std(0, unbiased=False).cpu().numpy()
+            ess = effective_sample_size(samples, mean, std)
+            jump_distance = mean_jump_distance(samples)
         if step is None:
             self.logger.info('Acceptance [%5.4f] min ESS [%5.4f] max ESS [%5.4f] average jump [%5.4f]' %
                              (acceptance, np.min(ess), np.max(ess), jump_distance))
