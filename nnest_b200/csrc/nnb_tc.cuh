@@ -62,6 +62,21 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// named barrier + population count of `pred` over the participating threads (every participant gets the count)
+__device__ __forceinline__ uint32_t named_bar_popc(uint32_t id, uint32_t nthreads, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %3, 0;\n"
+      "bar.red.popc.u32 %0, %1, %2, p;\n"
+      "}\n"
+      : "=r"(r)
+      : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
+      : "memory");
+  return r;
+}
+
 // exactly one lane of the (converged) warp gets true.  ptxas knows that the guarded region runs on a single thread, so
 // register operands of the tcgen05 instructions inside move to uniform registers without a per-operand waterfall loop.
 __device__ __forceinline__ bool elect_one() {

@@ -255,13 +255,19 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
 }
 
 // one out-of-line copy of the likelihood / prior switch per kernel (code size)
+// (the target is re-bound from its descriptor inside the call: passing the bound struct by reference would park its
+// pointers in local memory and reload them for every coordinate)
 template <int DD>
-static __device__ __noinline__ double tc_loglike(const TargetSmem& tg, const float* y) {
+static __device__ __noinline__ double tc_loglike(TargetDesc td, const double* td_s, const float* y) {
+  TargetSmem tg;
+  target_bind(tg, td, td_s);
   SmemRow row{y};
   return loglike_any<SmemRow, DD>(tg, row, false);
 }
 template <int DD>
-static __device__ __noinline__ double tc_prior(const TargetSmem& tg, const float* y) {
+static __device__ __noinline__ double tc_prior(TargetDesc td, const double* td_s, const float* y) {
+  TargetSmem tg;
+  target_bind(tg, td, td_s);
   SmemRow row{y};
   return prior_any<SmemRow, DD>(tg, row, false);
 }
@@ -354,16 +360,24 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   const int nj = (d + 3) / 4;
   const size_t ns = (size_t)n;
   float* nz = nz_all + (size_t)tile * d * 128 + m;
-  // cooperative (persistent) mode: every CTA keeps its own copy of (scale, accept, reject); they stay identical
+  // cooperative (persistent) mode: every tile leader keeps its own copy of (scale, accept, reject); they stay identical
   // because each is updated from the same grid-wide accept count after the per-step grid barrier
   double co_scale = 0.0;
-  int co_accept = 0, co_reject = 0;
-  float* co_scale_s = reinterpret_cast<float*>(tmem_base_s + 1);
+  // CTA-level rendezvous words of the cooperative mode (red region, 32 words):
+  //   [0] scale (float) of the step about to start   [1] tiles arrived   [2] accepted proposals of the arrived tiles
+  //   [3] epoch = steps whose grid-wide count has been consumed          [4] accept  [5] reject  [6..7] scale (double)
+  unsigned int* co_words = tmem_base_s + 2;
+  float* co_scale_s = reinterpret_cast<float*>(co_words);
+  const int my_tiles = (int)(((n - (long long)blockIdx.x * cpc < cpc ? n - (long long)blockIdx.x * cpc : cpc) + 127) >> 7);
   if (p.coop) {
-    co_scale = *reinterpret_cast<volatile double*>(&p.ctrl->scale);
-    co_accept = p.ctrl->accept;
-    co_reject = p.ctrl->reject;
-    if (threadIdx.x == 0) *co_scale_s = (float)co_scale;
+    if (threadIdx.x == 0) {
+      co_scale = *reinterpret_cast<volatile double*>(&p.ctrl->scale);
+      *co_scale_s = (float)co_scale;
+      co_words[1] = co_words[2] = co_words[3] = 0u;
+      co_words[4] = (unsigned int)p.ctrl->accept;
+      co_words[5] = (unsigned int)p.ctrl->reject;
+      *reinterpret_cast<double*>(co_words + 6) = co_scale;
+    }
     __syncthreads();
   }
 
@@ -401,15 +415,15 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   const bool fast_box = MODE == NNB_MODE_HARD && tg.desc.prior_kind == NNB_PRIOR_BOX_U && (DD > 0 || f.B >= 2);
 
   for (int s = p.s0 + 1; s <= p.s0 + p.nsteps; ++s) {
-    const float scale_f = p.coop ? *reinterpret_cast<volatile float*>(co_scale_s)
-                                 : (float)(*reinterpret_cast<volatile double*>(&p.ctrl->scale));
     const unsigned int step_abs = p.step_offset + (unsigned int)s;
     const bool more = s < p.s0 + p.nsteps;
     bool accept = false;
-    unsigned int ncall = 0;
+    unsigned int ncall = 0, tile_cnt = 0;
     bool acc_chain = false;
     if (tile_active) {
-      if (NPART > 1) tile_sync(t);   // nz complete (written by both threads of the chain)
+      if (NPART > 1 || p.coop) tile_sync(t);   // nz complete (written by both threads of the chain); scale published
+      const float scale_f = p.coop ? *reinterpret_cast<volatile float*>(co_scale_s)
+                                   : (float)(*reinterpret_cast<volatile double*>(&p.ctrl->scale));
       // ---- proposal z' = z + scale * N(0, I) (sampler.py:310-316), dims dealt to the chain's threads ----------------
       if (active) {
         const float* pz = p.z + (size_t)c + (size_t)part * ns;
@@ -449,21 +463,21 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
             if (NPART > 1) bad |= *flag != 0;
             logp_prop = bad ? -INFINITY : 0.0;
           } else {
-            logp_prop = tc_prior<DD>(tg, y);
+            logp_prop = tc_prior<DD>(td, td_s, y);
           }
           if (logp_prop < -1e30) lr = -INFINITY;
           float ratio = expf(lr);
           if (ratio > 1.0f) ratio = 1.0f;
           const bool m1 = u01 < ratio;
           if (m1) {
-            lp = tc_loglike<DD>(tg, y);
+            lp = tc_loglike<DD>(td, td_s, y);
             ncall = 1;
             accept = isfinite(lp) && (lp > p.loglstar);
           }
         } else {
-          lp = tc_loglike<DD>(tg, y);
+          lp = tc_loglike<DD>(td, td_s, y);
           ncall = 1;
-          logp_prop = tc_prior<DD>(tg, y);
+          logp_prop = tc_prior<DD>(td, td_s, y);
           double lr = (double)__fsub_rn(ld_prop, ld_cur) + (lp - logl_cur) + (logp_prop - logp_cur);
           double ratio = exp(lr);
           if (ratio > 1.0) ratio = 1.0;
@@ -481,7 +495,10 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       }
       __syncwarp();
       acc_chain = accept;
-      if (NPART > 1) {
+      if (p.coop) {   // the tile barrier doubles as the count of the tile's accepted proposals
+        tile_cnt = tc::named_bar_popc(t.bar_id, t.bar_threads, accept);
+        if (NPART > 1) acc_chain = active && (*flag != 0);
+      } else if (NPART > 1) {
         tile_sync(t);
         acc_chain = active && (*flag != 0);
       }
@@ -519,14 +536,23 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
 
     // ---- global accept count of the step -> scale adaptation (sampler.py:418-430) ------------------------------------
     const int si = s - p.s0 - 1;
+    bool cta_poller = false;
     if (p.coop) {
-      // arrive at the grid barrier (all CTAs are co-resident: cooperative launch).  step_counts[si] was zeroed by
-      // the host; `ticket` counts CTA arrivals monotonically.
-      unsigned int blk = block_count(accept);
-      if (threadIdx.x == 0) {
-        if (blk) atomicAdd(&p.step_counts[si], blk);
-        __threadfence();
-        atomicAdd(&p.ctrl->ticket, 1u);
+      // Tiles rendezvous inside the CTA through shared-memory atomics (no CTA-wide barrier: the tiles of an SM drift apart
+      // freely inside a step); the LAST tile of the CTA to finish the step carries the CTA's count to the grid barrier
+      // (all CTAs are co-resident: cooperative launch) and becomes the CTA's poller for this step.  step_counts[si] was
+      // zeroed by the host; `ticket` counts CTA arrivals monotonically.
+      if (tile_active && tit == 0) {
+        if (tile_cnt) atomicAdd(&co_words[2], tile_cnt);
+        __threadfence_block();
+        if (atomicAdd(&co_words[1], 1u) == (unsigned int)(my_tiles - 1)) {
+          co_words[1] = 0u;
+          const unsigned int blk = atomicExch(&co_words[2], 0u);
+          if (blk) atomicAdd(&p.step_counts[si], blk);
+          __threadfence();
+          atomicAdd(&p.ctrl->ticket, 1u);
+          cta_poller = true;
+        }
       }
     } else if (p.dynamic) {
       unsigned int blk = block_count(accept);
@@ -552,20 +578,32 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
     // ---- rest of the next step's noise (overlaps the grid barrier) --------------------------------------------------------
     if (tile_active && active && more && philox) gen_normals(jc + part, nj, NPART, step_abs + 1u, s);
     if (tile_active && active && more && philox_u && part == NPART - 1) gen_uniform(step_abs + 1u, s);
-    if (p.coop) {
-      if (threadIdx.x == 0) {
+    if (p.coop && tile_active && tit == 0) {
+      // The CTA's poller waits for the grid-wide count and updates the CTA's copy of (scale, accept, reject) -- identical
+      // in every CTA; the other tile leaders wait for the epoch word in shared memory.  The tile barrier at the top of the
+      // next step publishes the new scale to the tile's threads.
+      volatile unsigned int* vw = co_words;
+      if (cta_poller) {
         const unsigned int target = (unsigned int)(si + 1) * gridDim.x;
         while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < target) __nanosleep(20);
         __threadfence();
         const unsigned int na = *reinterpret_cast<volatile unsigned int*>(&p.step_counts[si]);
         if (p.dynamic) {
-          if (2ull * na > (unsigned long long)n) co_accept += 1; else co_reject += 1;
-          if (co_accept > co_reject) co_scale *= exp(1.0 / (1 + co_accept));
-          if (co_accept < co_reject) co_scale /= exp(1.0 / (1 + co_reject));
-          *co_scale_s = (float)co_scale;
+          int a = (int)vw[4], r = (int)vw[5];
+          double sc = *reinterpret_cast<volatile double*>(co_words + 6);
+          if (2ull * na > (unsigned long long)n) a += 1; else r += 1;
+          if (a > r) sc *= exp(1.0 / (1 + a));
+          if (a < r) sc /= exp(1.0 / (1 + r));
+          vw[4] = (unsigned int)a;
+          vw[5] = (unsigned int)r;
+          *reinterpret_cast<volatile double*>(co_words + 6) = sc;
+          *reinterpret_cast<volatile float*>(co_scale_s) = (float)sc;
         }
+        __threadfence_block();
+        vw[3] = (unsigned int)(si + 1);
+      } else {
+        while (vw[3] < (unsigned int)(si + 1)) __nanosleep(20);
       }
-      __syncthreads();
     }
   }
   if (active && part == 0) {
@@ -573,10 +611,11 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
     p.logl[c] = logl_cur;
     p.logp[c] = logp_cur;
   }
+  __syncthreads();
   if (p.coop && blockIdx.x == 0 && threadIdx.x == 0) {   // publish the final scale bookkeeping
-    p.ctrl->scale = co_scale;
-    p.ctrl->accept = co_accept;
-    p.ctrl->reject = co_reject;
+    p.ctrl->scale = *reinterpret_cast<volatile double*>(co_words + 6);
+    p.ctrl->accept = (int)co_words[4];
+    p.ctrl->reject = (int)co_words[5];
   }
   // totals: one atomic per warp (the counts of non-zero lanes only)
   unsigned int ta = __reduce_add_sync(0xffffffffu, acc_total);

@@ -41,6 +41,13 @@ static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t s
     }
     NNB_CUDA(h, cudaMemsetAsync(h->d_step_counts, 0, sizeof(unsigned int) * steps, st));
     p.s0 = 0; p.nsteps = steps; p.coop = 1; p.step_counts = h->d_step_counts;
+    long long tiles = 0;   // tiles holding at least one chain
+    for (int b = 0; b < grid; ++b) {
+      const long long left = p.n - (long long)b * cpc;
+      const long long mine = left < cpc ? left : cpc;
+      tiles += (mine + 127) / 128;
+    }
+    p.total_tiles = (int)tiles;
     void* args[] = {(void*)&h->tcflow, (void*)&h->d_weights_tc, (void*)&h->tdesc, (void*)&h->d_target, (void*)&p};
     NNB_CUDA(h, cudaLaunchCooperativeKernel((const void*)mcmc_tc_kernel<MODE, NPART, DD>, dim3(grid), dim3(block), args, sm, st));
     h->last_launches = 1;
