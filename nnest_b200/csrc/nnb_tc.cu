@@ -64,22 +64,25 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
 }
 
 int nnb_launch_mcmc_tc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st) {
-  // two threads per chain unless NNB_TC_NPART=1 (development switch)
-  static const int npart = [] { const char* e = getenv("NNB_TC_NPART"); return (e && e[0] == '1') ? 1 : 2; }();
-  if (npart == 1)
-    return p.mode == NNB_MODE_MH ? launch_tc_mode<NNB_MODE_MH, 1, 0>(h, p, steps, st)
-                                 : launch_tc_mode<NNB_MODE_HARD, 1, 0>(h, p, steps, st);
+  // Threads per chain.  With at least two full tiles of chains per SM one thread per chain (128 registers, no spills,
+  // fewer tile barriers) has the higher throughput; with fewer chains the kernel is latency bound and two threads per
+  // chain (which split every per-column phase) shorten the critical path.  NNB_TC_NPART=1|2 overrides (development).
+  static const int npart_env = [] { const char* e = getenv("NNB_TC_NPART"); return e ? atoi(e) : 0; }();
+  const int npart = (npart_env == 1 || npart_env == 2) ? npart_env : (p.n >= 2ll * 128 * h->sm_count ? 1 : 2);
   // the reference's default architecture at the dimensions of the named workloads: fully unrolled kernels
   static const bool generic_only = getenv("NNB_TC_GENERIC") != nullptr;
   if (!generic_only && h->tcflow.L == 1 && h->tcflow.B == 3) {
     switch (h->tcflow.d) {
-      case 2: return nnb_launch_mcmc_tc_fixed<2>(h, p, steps, st);
-      case 10: return nnb_launch_mcmc_tc_fixed<10>(h, p, steps, st);
-      case 30: return nnb_launch_mcmc_tc_fixed<30>(h, p, steps, st);
-      case 50: return nnb_launch_mcmc_tc_fixed<50>(h, p, steps, st);
+      case 2: return nnb_launch_mcmc_tc_fixed<2>(h, p, steps, st, npart);
+      case 10: return nnb_launch_mcmc_tc_fixed<10>(h, p, steps, st, npart);
+      case 30: return nnb_launch_mcmc_tc_fixed<30>(h, p, steps, st, npart);
+      case 50: return nnb_launch_mcmc_tc_fixed<50>(h, p, steps, st, npart);
       default: break;
     }
   }
+  if (npart == 1)
+    return p.mode == NNB_MODE_MH ? launch_tc_mode<NNB_MODE_MH, 1, 0>(h, p, steps, st)
+                                 : launch_tc_mode<NNB_MODE_HARD, 1, 0>(h, p, steps, st);
   return p.mode == NNB_MODE_MH ? launch_tc_mode<NNB_MODE_MH, 2, 0>(h, p, steps, st)
                                : launch_tc_mode<NNB_MODE_HARD, 2, 0>(h, p, steps, st);
 }

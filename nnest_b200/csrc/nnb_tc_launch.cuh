@@ -73,4 +73,4 @@ static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t s
 
 // x_dim-specialised launchers (one translation unit each so that they compile in parallel)
 template <int DD>
-int nnb_launch_mcmc_tc_fixed(nnb_handle* h, McmcParams p, int steps, cudaStream_t st);
+int nnb_launch_mcmc_tc_fixed(nnb_handle* h, McmcParams p, int steps, cudaStream_t st, int npart);
