@@ -139,7 +139,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.QUERY,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -369,15 +369,17 @@ def run_gpu(args, wl):
             peak, peak_src = fp32_peak, 'FP32 FMA pipe: 148 SMs x 128 lanes x 2 x max SM clock (not in MEASURED_PEAKS.json)'
         roofline = {
             'bound': 'tensor' if used_tc else 'fp32-fma', 'achieved': achieved_tflops, 'peak': peak, 'unit': 'TFLOP/s',
-            'frac': achieved_tflops / peak, 'traffic': 17.3e6 * (n * S) / (65536.0 * 150) if used_tc else None,
-            'kernel': 'mcmc_tc_kernel<MODE,2> (tcgen05 3xTF32)' if used_tc else 'mcmc_kernel<16,MODE> (FP32 FMA)',
+            'frac': achieved_tflops / peak, 'traffic': 10.78e6 * (n * S) / (65536.0 * 150) if used_tc else None,
+            'kernel': 'mcmc_tc_kernel<MODE,NPART,D> (tcgen05 3xTF32)' if used_tc else 'mcmc_kernel<16,MODE> (FP32 FMA)',
             'launches_per_step': kernel_launches, 'launch_ms': run_ms / max(kernel_launches, 1),
             'algorithmic_flop_per_proposal': flops, 'peak_source': peak_src,
             'frac_of_fp32_fma_peak': achieved_tflops / fp32_peak,
             'note': 'algorithmic flops = dense nn.Linear count of one flow inverse per proposal, 4*B*H*(2d+L*H); the '
                     'tensor pipe executes them as 3xTF32 (x3) on mask-reduced operands (x0.6).  The kernel is bound by '
-                    'the per-element epilogues (tanh/exp/RNG/split on the FP32+ALU+MUFU pipes: ncu issue slots 57% busy, '
-                    'tensor pipe 5%), not by the MMA rate; traffic = ncu dram bytes of one refill launch scaled to this size',
+                    'the per-element work around the MMAs (Philox/Box-Muller, tanh/exp, hi/lo split, likelihood: FP32, ALU '
+                    'and MUFU issue slots) and by the latency of nine dependent MMA round trips per step at 16 warps per '
+                    'SM, not by the MMA rate: ncu (profiles/r1_final2_*) issue slots 45% busy, tensor pipe 8.6%, DRAM '
+                    '0.04%; traffic = ncu dram bytes of one refill launch (c4) scaled to this size',
         }
         cpu = cpu_baseline_quick(wl) if world == 1 and not args.no_cpu_baseline else None
         print(json.dumps({
@@ -401,7 +403,7 @@ def run_gpu(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
