@@ -71,11 +71,12 @@ def _unit_stale(unit, manifest=None):
 
 
 def up_to_date():
+    """libnnb.so matches the sources (content digests; the object files are not needed once the library is linked, so
+    they do not have to travel with the tree)."""
     if not os.path.exists(LIB):
         return False
     manifest = _manifest()
-    return not any(_unit_stale(u, manifest) for u in UNITS) and manifest.get('__lib__') == \
-        ' '.join(manifest.get(u, '?') for u in UNITS)
+    return manifest.get('__lib__') == ' '.join(_digest(u) for u in UNITS)
 
 
 def _compile(unit):

@@ -114,8 +114,10 @@ __device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1) {
 // (NPART = 2: each gets one tanh chunk and one relu chunk).  A rolled loop keeps the code small.
 template <int NPART>
 __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float* __restrict__ bias) {
-#pragma unroll 1
-  for (int c = t.part; c < 4; c += NPART) {
+  // one thread per chain: the tanh and relu chunks are independent work for the scheduler (unrolled by two); two threads per
+  // chain: a rolled loop keeps the code (and the 64-register budget) small
+#pragma unroll(NPART == 1 ? 2 : 1)
+  for (int c = (NPART == 1 ? 0 : t.part); c < 4; c += NPART) {
     uint32_t r[8], hi[8], lo[8];
     tc::tmem_ld8(t.lane_tmem + 64 + 8 * c, r);
     tc::wait_ld();
@@ -166,7 +168,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
     // (masks alternate, input a of block k-1 == output o of block k), and that epilogue stores them straight into the
     // A columns -- same thread, same column chunk, no shared-memory round trip and no tile barrier in between.
     if (k == nB - 1) {
-      for (int c0 = 8 * t.part; c0 < K1; c0 += 8 * NPART) {
+      for (int c0 = (NPART == 1 ? 0 : 8 * t.part); c0 < K1; c0 += 8 * NPART) {
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -220,7 +222,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
     // x = (z - t) * exp(-log_s), ld -= log_s on the dims with mask == 0   (networks.py:300-309).  The values a dim keeps
     // (its last update: blocks 1 and 0) are tested against the prior box right here (priors.py:39-43).
     const bool chk = box_check && k <= 1;
-    for (int c0 = 8 * t.part; c0 < nout; c0 += 8 * NPART) {
+    for (int c0 = (NPART == 1 ? 0 : 8 * t.part); c0 < nout; c0 += 8 * NPART) {
       uint32_t rs[8], rt[8], hi[8], lo[8];
       tc::tmem_ld8(t.lane_tmem + 64 + c0, rs);
       tc::tmem_ld8(t.lane_tmem + 96 + c0, rt);
@@ -335,7 +337,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   t.part = tit >> 7;
   t.issuer = tit < 32 ? 0 : (tit < 64 && rows > 32 ? 1 : -1);
   t.single = rows <= 32;   // a 32-chain tile has only one warp per part
-  const int part = t.part;
+  const int part = NPART == 1 ? 0 : t.part;
   const uint32_t wsm_u32 = tc::smem_u32(wsm);
 
   const long long n = p.n;
@@ -383,6 +385,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
 
   // raw N(0,1) draws of Philox blocks j = j0, j0 + jstep, ... < j1 of step `step_abs` into nz (and the dump buffer)
   auto gen_normals = [&](int j0, int j1, int jstep, unsigned int step_abs, int sidx) {
+#pragma unroll(DD > 0 ? 2 : 1)   // two independent Philox chains in flight (each is a serial chain of ten rounds)
     for (int j = j0; j < j1; j += jstep) {
       float nrm[4];
       philox_normals4(j, step_abs, chain, kTagNormal, p.seed_lo, p.seed_hi, nrm);
