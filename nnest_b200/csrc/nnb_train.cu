@@ -118,10 +118,17 @@ extern "C" int nnb_mean_nn_distance(nnb_handle* h, const double* x, int64_t n, i
   if (!h->d_train_ctrl) NNB_CUDA(h, cudaMalloc(&h->d_train_ctrl, sizeof(TrainCtrl)));
   if (!h->h_train_ctrl) NNB_CUDA(h, cudaMallocHost(&h->h_train_ctrl, sizeof(TrainCtrl)));
   NNB_CUDA(h, cudaMemsetAsync(h->d_train_ctrl, 0, sizeof(TrainCtrl), st));
-  const size_t smem = (size_t)2 * d * 128 * sizeof(double);
-  NNB_CUDA(h, nnb_set_smem(nn_min_dist_kernel, smem));
   const int grid = (int)((n + 127) / 128);
-  nn_min_dist_kernel<<<grid, 128, smem, st>>>(x, n, d, &((TrainCtrl*)h->d_train_ctrl)->train_loss);
+  double* acc = &((TrainCtrl*)h->d_train_ctrl)->train_loss;
+  if (d <= 16) {
+    nn_min_dist_kernel<16><<<grid, 128, 128 * 16 * sizeof(double), st>>>(x, n, d, acc);
+  } else if (d <= 32) {
+    nn_min_dist_kernel<32><<<grid, 128, 128 * 32 * sizeof(double), st>>>(x, n, d, acc);
+  } else {
+    const size_t smem = (size_t)2 * d * 128 * sizeof(double);
+    NNB_CUDA(h, nnb_set_smem(nn_min_dist_kernel<0>, smem));
+    nn_min_dist_kernel<0><<<grid, 128, smem, st>>>(x, n, d, acc);
+  }
   NNB_CUDA(h, cudaGetLastError());
   NNB_CUDA(h, cudaMemcpyAsync(h->h_train_ctrl, h->d_train_ctrl, sizeof(TrainCtrl), cudaMemcpyDeviceToHost, st));
   NNB_CUDA(h, cudaStreamSynchronize(st));

@@ -439,31 +439,62 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
 }
 
 // ---- mean nearest-neighbour distance (training jitter, trainer.py:147-150) ------------------------------------------------
-// One query row per thread (coordinates as columns of a shared-memory matrix), candidates streamed through shared
-// memory in tiles of 128 rows; float64 like the reference's cKDTree on float64 samples.
+// One query row per thread, candidates streamed through shared memory in tiles of 128 rows; float64 like the reference's
+// cKDTree on float64 samples.  DREG > 0: the query lives in registers (d <= DREG, zero padded) and a candidate coordinate
+// is one broadcast shared-memory load per two dimensions; DREG == 0: any d, query coordinates as shared-memory columns.
+template <int DREG>
 __global__ void __launch_bounds__(128, 2) nn_min_dist_kernel(const double* __restrict__ x, long long n, int d,
                                                              double* __restrict__ sum_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* q = reinterpret_cast<double*>(smem_raw);   // [d][128]
-  double* c = q + (size_t)d * 128;                   // [128][d]
   const int tid = threadIdx.x;
   const long long row = (long long)blockIdx.x * 128 + tid;
   const bool valid = row < n;
-  for (int i = 0; i < d; ++i) q[i * 128 + tid] = valid ? x[row * d + i] : 0.0;
   double best = INFINITY;
-  for (long long c0 = 0; c0 < n; c0 += 128) {
-    const int m = (int)((n - c0) < 128 ? (n - c0) : 128);
-    __syncthreads();
-    for (int e = tid; e < m * d; e += 128) c[e] = x[c0 * d + e];
-    __syncthreads();
-    for (int j = 0; j < m; ++j) {
-      const double* cj = c + j * d;
-      double s = 0.0;
-      for (int i = 0; i < d; ++i) {
-        const double t = q[i * 128 + tid] - cj[i];
-        s = fma(t, t, s);
+  if (DREG > 0) {
+    double* c = reinterpret_cast<double*>(smem_raw);   // [128][DREG]
+    double q[DREG > 0 ? DREG : 1];
+#pragma unroll
+    for (int i = 0; i < DREG; ++i) q[i] = (valid && i < d) ? x[row * d + i] : 0.0;
+    for (long long c0 = 0; c0 < n; c0 += 128) {
+      const int m = (int)((n - c0) < 128 ? (n - c0) : 128);
+      __syncthreads();
+      for (int e = tid; e < m * DREG; e += 128) {
+        const int j = e / DREG, i = e - j * DREG;
+        c[e] = i < d ? x[(c0 + j) * d + i] : 0.0;
       }
-      if (c0 + j != row && s < best) best = s;
+      __syncthreads();
+      for (int j = 0; j < m; ++j) {
+        const double2* cj = reinterpret_cast<const double2*>(c + j * DREG);
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < DREG / 2; ++i) {
+          const double2 v = cj[i];
+          const double t0 = q[2 * i] - v.x, t1 = q[2 * i + 1] - v.y;
+          s0 = fma(t0, t0, s0);
+          s1 = fma(t1, t1, s1);
+        }
+        const double s = s0 + s1;
+        if (c0 + j != row && s < best) best = s;
+      }
+    }
+  } else {
+    double* q = reinterpret_cast<double*>(smem_raw);   // [d][128]
+    double* c = q + (size_t)d * 128;                   // [128][d]
+    for (int i = 0; i < d; ++i) q[i * 128 + tid] = valid ? x[row * d + i] : 0.0;
+    for (long long c0 = 0; c0 < n; c0 += 128) {
+      const int m = (int)((n - c0) < 128 ? (n - c0) : 128);
+      __syncthreads();
+      for (int e = tid; e < m * d; e += 128) c[e] = x[c0 * d + e];
+      __syncthreads();
+      for (int j = 0; j < m; ++j) {
+        const double* cj = c + j * d;
+        double s = 0.0;
+        for (int i = 0; i < d; ++i) {
+          const double t = q[i * 128 + tid] - cj[i];
+          s = fma(t, t, s);
+        }
+        if (c0 + j != row && s < best) best = s;
+      }
     }
   }
   double v = valid && n > 1 ? sqrt(best) : 0.0;

@@ -189,3 +189,46 @@ def test_trainer_uses_fused_kernel_and_fits(tmp_path):
     zt, _ = t.netG.forward(torch.from_numpy(x.astype(np.float32)).cuda())
     assert np.abs(z.cpu().numpy() - zt.detach().cpu().numpy()).max() < 1e-4
     assert t.best_validation_epoch >= 1
+
+
+def test_ragged_and_degenerate_sizes(engine):
+    """batch larger than the dataset, a dataset smaller than one CTA tile, no validation set, an empty epoch."""
+    g = load('train_d2.npz')
+    a = arch(g)
+    w0 = flat_of(g, 'sd')
+    kw = opt_kw(g)
+    # (i) batch_size > n_train: one Adam step on all 37 samples == the oracle's
+    x = g['x_train'][:37]
+    w = dev(w0)
+    m, v = torch.zeros_like(w), torch.zeros_like(w)
+    tl, vs, grid = engine.train_epoch(a, w, m, v, 0, dev(x), None, 100, **kw)
+    assert grid == 1 and vs == 0.0
+    opt = otrain.Adam(w0.size, lr=kw['lr'], betas=kw['betas'], eps=kw['eps'], weight_decay=kw['weight_decay'])
+    wr, tlr = otrain.train_epoch(w0.astype(np.float64), opt, x, 100, *a)
+    assert abs(tl / 37 - tlr) <= 2e-5 * abs(tlr)
+    assert np.abs(w.cpu().numpy() - wr).max() < 2e-3 * np.abs(wr - w0).max()
+    # (ii) batch_size 1: 5 steps
+    w = dev(w0)
+    m, v = torch.zeros_like(w), torch.zeros_like(w)
+    engine.train_epoch(a, w, m, v, 0, dev(x[:5]), dev(g['x_valid']), 1, **kw)
+    opt = otrain.Adam(w0.size, lr=kw['lr'], betas=kw['betas'], eps=kw['eps'], weight_decay=kw['weight_decay'])
+    wr, _ = otrain.train_epoch(w0.astype(np.float64), opt, x[:5], 1, *a)
+    assert np.abs(w.cpu().numpy() - wr).max() < 2e-3 * np.abs(wr - w0).max()
+    # (iii) empty training set: nothing changes, validation still evaluated
+    w = dev(w0)
+    m, v = torch.zeros_like(w), torch.zeros_like(w)
+    tl, vs, _ = engine.train_epoch(a, w, m, v, 0, None, dev(g['x_valid']), 100, **kw)
+    assert tl == 0.0 and vs > 0.0 and np.array_equal(w.cpu().numpy(), w0) and float(m.abs().max()) == 0.0
+
+
+def test_trainer_tiny_dataset_and_large_batch(tmp_path):
+    """Trainer.train with fewer samples than batch_size and with a validation split of one sample."""
+    from nnest_b200 import Trainer
+    np.random.seed(1)
+    torch.manual_seed(1)
+    x = np.random.normal(size=(9, 3))
+    t = Trainer(3, flow='nvp', log_dir=str(tmp_path), log_level=logging.WARNING, batch_size=100)
+    t.train(x, max_iters=5, jitter=0.0)
+    assert np.isfinite(t.best_validation_loss)
+    z, ld = t.forward(x.astype(np.float32))
+    assert torch.isfinite(z).all() and torch.isfinite(ld).all()
