@@ -383,6 +383,11 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
     __syncthreads();
   }
 
+  // one thread per chain: the current latent point stays in shared memory for all steps of the launch
+  constexpr bool kZcur = NPART == 1;
+  if (kZcur && active)
+    for (int i = 0; i < d; ++i) zp[i * 128] = p.z[(size_t)c + (size_t)i * ns];
+
   // raw N(0,1) draws of Philox blocks j = j0, j0 + jstep, ... < j1 of step `step_abs` into nz (and the dump buffer)
   auto gen_normals = [&](int j0, int j1, int jstep, unsigned int step_abs, int sidx) {
 #pragma unroll(DD > 0 ? 2 : 1)   // two independent Philox chains in flight (each is a serial chain of ten rounds)
@@ -429,19 +434,28 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
                                    : (float)(*reinterpret_cast<volatile double*>(&p.ctrl->scale));
       // ---- proposal z' = z + scale * N(0, I) (sampler.py:310-316), dims dealt to the chain's threads ----------------
       if (active) {
-        const float* pz = p.z + (size_t)c + (size_t)part * ns;
-        if (philox) {
-          for (int i = part; i < d; i += NPART, pz += NPART * ns) {
-            float v = __fadd_rn(*pz, __fmul_rn(nz[i * 128], scale_f));
-            y[i * 128] = v;
-            zp[i * 128] = v;
+        if (kZcur) {   // one thread per chain: the current z lives in shared memory (zp), no global traffic per step
+          if (philox) {
+            for (int i = 0; i < d; ++i) y[i * 128] = __fadd_rn(zp[i * 128], __fmul_rn(nz[i * 128], scale_f));
+          } else {
+            const float* nr = p.replay_normals + ((size_t)(s - 1) * ns + (size_t)c) * d;
+            for (int i = 0; i < d; ++i) y[i * 128] = __fadd_rn(zp[i * 128], __fmul_rn(nr[i], scale_f));
           }
         } else {
-          const float* nr = p.replay_normals + ((size_t)(s - 1) * ns + (size_t)c) * d;
-          for (int i = part; i < d; i += NPART, pz += NPART * ns) {
-            float v = __fadd_rn(*pz, __fmul_rn(nr[i], scale_f));
-            y[i * 128] = v;
-            zp[i * 128] = v;
+          const float* pz = p.z + (size_t)c + (size_t)part * ns;
+          if (philox) {
+            for (int i = part; i < d; i += NPART, pz += NPART * ns) {
+              float v = __fadd_rn(*pz, __fmul_rn(nz[i * 128], scale_f));
+              y[i * 128] = v;
+              zp[i * 128] = v;
+            }
+          } else {
+            const float* nr = p.replay_normals + ((size_t)(s - 1) * ns + (size_t)c) * d;
+            for (int i = part; i < d; i += NPART, pz += NPART * ns) {
+              float v = __fadd_rn(*pz, __fmul_rn(nr[i], scale_f));
+              y[i * 128] = v;
+              zp[i * 128] = v;
+            }
           }
         }
       } else {
@@ -506,7 +520,27 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
         acc_chain = active && (*flag != 0);
       }
       // ---- state / trace update, dims dealt to the chain's threads (sampler.py:433-444) -------------------------------
-      if (active) {
+      if (active && kZcur) {
+        // z' is recomputed from the same operands as the proposal (bit-identical); this step's noise is still intact
+        // because the next step's is drawn after this point
+        float* px = p.x + (size_t)c;
+        if (acc_chain) {
+          const float* nr = philox ? nullptr : p.replay_normals + ((size_t)(s - 1) * ns + (size_t)c) * d;
+          for (int i = 0; i < d; ++i, px += ns) {
+            zp[i * 128] = __fadd_rn(zp[i * 128], __fmul_rn(philox ? nz[i * 128] : nr[i], scale_f));
+            *px = y[i * 128];
+          }
+        }
+        if (p.trace_z) {
+          float* tz = p.trace_z + (size_t)s * d * ns + (size_t)c;
+          float* tx = p.trace_x + (size_t)s * d * ns + (size_t)c;
+          px = p.x + (size_t)c;
+          for (int i = 0; i < d; ++i, tz += ns, tx += ns, px += ns) {
+            *tz = zp[i * 128];
+            *tx = acc_chain ? y[i * 128] : *px;
+          }
+        }
+      } else if (active) {
         float* pz = p.z + (size_t)c + (size_t)part * ns;
         float* px = p.x + (size_t)c + (size_t)part * ns;
         if (acc_chain) {
@@ -609,6 +643,8 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       }
     }
   }
+  if (kZcur && active)
+    for (int i = 0; i < d; ++i) p.z[(size_t)c + (size_t)i * ns] = zp[i * 128];
   if (active && part == 0) {
     p.logdet[c] = ld_cur;
     p.logl[c] = logl_cur;
