@@ -64,11 +64,12 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
 }
 
 int nnb_launch_mcmc_tc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st) {
-  // Threads per chain.  With at least 1.5 tiles of chains per SM one thread per chain (128 registers, the current latent
-  // point resident in shared memory, fewer tile barriers) has the higher throughput; with fewer chains the kernel is latency bound and two threads per
-  // chain (which split every per-column phase) shorten the critical path.  NNB_TC_NPART=1|2 overrides (development).
+  // Threads per chain.  One thread per chain (128 registers, the current latent point resident in shared memory, fewer
+  // tile barriers) measured faster than two threads per chain at every batch size tried on the B200 (1 k - 131 k chains),
+  // so it is the default; NNB_TC_NPART=2 selects the two-thread layout (the chain's threads split every per-column
+  // phase and the second one draws the next step's noise during the accept test).
   static const int npart_env = [] { const char* e = getenv("NNB_TC_NPART"); return e ? atoi(e) : 0; }();
-  const int npart = (npart_env == 1 || npart_env == 2) ? npart_env : (2 * p.n >= 3ll * 128 * h->sm_count ? 1 : 2);
+  const int npart = npart_env == 2 ? 2 : 1;
   // the reference's default architecture at the dimensions of the named workloads: fully unrolled kernels
   static const bool generic_only = getenv("NNB_TC_GENERIC") != nullptr;
   if (!generic_only && h->tcflow.L == 1 && h->tcflow.B == 3) {
