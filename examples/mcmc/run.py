@@ -21,6 +21,13 @@ sys.path.insert(0, os.path.realpath(os.path.join(os.path.dirname(os.path.abspath
 
 def main(args):
     import torch
+    import torch.distributed as dist
+    world, rank = 1, 0
+    if 'LOCAL_RANK' in os.environ:        # one process per GPU under torchrun: every rank runs its own shard of chains
+        local = int(os.environ['LOCAL_RANK'])
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        rank, world = dist.get_rank(), dist.get_world_size()
     from nnest_b200 import MCMCSampler
     from nnest_b200.likelihoods import Gaussian
     from nnest_b200.priors import UniformPrior
@@ -33,24 +40,39 @@ def main(args):
     sampler = MCMCSampler(d, Gaussian(d, rho, lim=args.lim), prior=UniformPrior(d, -args.lim, args.lim), flow='nvp',
                           hidden_dim=args.hidden_dim, num_blocks=args.num_blocks, num_layers=args.num_layers,
                           batch_size=args.batch_size, log_dir=os.path.join(args.log_dir, 'gaussian'),
-                          log_level=logging.INFO, seed=args.seed)
+                          log_level=logging.INFO if rank == 0 else logging.WARNING, seed=args.seed)
     t0 = time.time()
     sampler.run(args.mcmc_steps, args.mcmc_num_chains, training, stats_interval=None, train_iters=args.train_iters)
     elapsed = time.time() - t0
     burn = args.mcmc_steps // 2
     tail = sampler.samples[:, burn::args.thin, :d]
-    flat = np.asarray(tail, dtype=np.float64).reshape(-1, d)
-    mean = flat.mean(0)
-    c = np.cov(flat.T)
-    n_eff_chains = tail.shape[0]
-    out = dict(x_dim=d, corr=rho, chains=args.mcmc_num_chains, steps=args.mcmc_steps, seconds=elapsed,
-               proposals=args.mcmc_num_chains * args.mcmc_steps, ncall=int(sampler.total_calls),
-               acceptance=float(sampler.total_accepted) / max(1.0, float(sampler.total_accepted + sampler.total_rejected)),
-               max_abs_mean=float(np.abs(mean).max()), mean_sigma_over_sqrt_chains=float(1.0 / np.sqrt(n_eff_chains)),
+    flat = torch.from_numpy(np.ascontiguousarray(tail, dtype=np.float64).reshape(-1, d)).cuda()
+    # moments over the chains of ALL ranks: sums are all-reduced (no sample ever leaves its GPU's host)
+    stats = torch.cat([flat.sum(0), (flat.T @ flat).reshape(-1),
+                       torch.tensor([flat.shape[0], float(sampler.total_accepted), float(sampler.total_rejected),
+                                     float(sampler.total_calls)], dtype=torch.float64, device='cuda')])
+    t_max = torch.tensor([elapsed], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(stats)
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    stats = stats.cpu().numpy()
+    cnt, acc, rej, ncall = stats[d + d * d:]
+    mean = stats[:d] / cnt
+    c = stats[d:d + d * d].reshape(d, d) / cnt - np.outer(mean, mean)
+    n_chains = args.mcmc_num_chains * world
+    out = dict(x_dim=d, corr=rho, gpus=world, chains=n_chains, chains_per_gpu=args.mcmc_num_chains,
+               steps=args.mcmc_steps, seconds=float(t_max.item()), proposals=n_chains * args.mcmc_steps,
+               ncall=int(ncall), acceptance=acc / max(1.0, acc + rej),
+               max_abs_mean=float(np.abs(mean).max()), mean_sigma_over_sqrt_chains=float(1.0 / np.sqrt(n_chains)),
                var_mean=float(np.diag(c).mean()), var_expected=1.0,
                offdiag_mean=float((c.sum() - np.trace(c)) / (d * (d - 1))), offdiag_expected=rho,
                max_abs_cov_err=float(np.abs(c - cov).max()))
+    if rank != 0:
+        dist.destroy_process_group()
+        return
     print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -622,7 +622,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       volatile unsigned int* vw = co_words;
       if (cta_poller) {
         const unsigned int target = (unsigned int)(si + 1) * gridDim.x;
-        while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < target) __nanosleep(20);
+        while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < target) __nanosleep(64);
         __threadfence();
         const unsigned int na = *reinterpret_cast<volatile unsigned int*>(&p.step_counts[si]);
         if (p.dynamic) {
@@ -639,7 +639,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
         __threadfence_block();
         vw[3] = (unsigned int)(si + 1);
       } else {
-        while (vw[3] < (unsigned int)(si + 1)) __nanosleep(20);
+        while (vw[3] < (unsigned int)(si + 1)) __nanosleep(128);   // polling costs issue slots the other tiles need
       }
     }
   }
