@@ -1,7 +1,6 @@
 // nnb_train.cu -- host side of the fused flow-fitting kernel (nnb_train.cuh): nnb_train_epoch, nnb_mean_nn_distance.
 #include <cuda_runtime.h>
 
-#include <cstdlib>
 #include <string>
 
 #include "nnb_host.h"
@@ -54,20 +53,12 @@ extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* str
   if (a->n_valid < 0 || (a->n_valid > 0 && !a->x_valid)) return nnb_fail(h, NNB_ERR_ARG, "x_valid");
   NNB_CUDA(h, cudaSetDevice(h->device));
 
-  // A mini-batch is cut into slices of at most 128 samples (one per thread); with more than 32 samples it is spread over
-  // several CTAs, up to one per SM -- the per-sample phases are latency bound, so narrower slices cost nothing there and
-  // shorten the batch contractions of the weight gradients.
   long long work = a->do_train ? (long long)a->batch_size : (long long)a->n_valid;
   if (a->do_train && a->n_train < work) work = a->n_train;
-  if (work < 1) work = 1;
-  long long g = (work + 31) / 32;
+  long long g = (work + kTrainThreads - 1) / kTrainThreads;
+  if (g < 1) g = 1;
   if (g > h->sm_count) g = h->sm_count;
   if (g > 1 && !h->coop_supported) g = 1;
-  static const bool one_cta = getenv("NNB_TRAIN_ONE_CTA") != nullptr;   // development switch
-  if (one_cta) g = 1;
-  long long slice = (work + g - 1) / g;
-  slice = (slice + 3) / 4 * 4;
-  if (slice > kTrainThreads) slice = kTrainThreads;
   const int grid = (int)g;
   const int Psm = train_psm(d, H, L, B);
 
@@ -101,7 +92,6 @@ extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* str
   p.ctrl = (TrainCtrl*)h->d_train_ctrl;
   p.grad_out = a->grad_out;
   p.do_train = a->do_train ? 1 : 0;
-  p.slice = (int)slice;
 
   const size_t smem = train_smem_bytes(d, H, L, B);
   int rc;

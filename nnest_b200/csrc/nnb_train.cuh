@@ -59,7 +59,6 @@ struct TrainParams {
   TrainCtrl* ctrl;
   float* grad_out;              // optional [P]: data gradient of the LAST mini-batch (natural layout)
   int do_train;
-  int slice;                    // samples a CTA takes per pass over a mini-batch (multiple of 4, <= 128)
 };
 
 __host__ __device__ inline int train_net_floats(int d, int H, int L) { return H * d + H + L * (H * H + H) + d * H + d; }
@@ -141,15 +140,15 @@ __device__ __forceinline__ void axpy_row(const float* __restrict__ row, float v,
 // G[base + o*so + i*si] += sum_b D[o][b] * A[i][b]  (i < nI);  G[bbase + o*sb] += sum_b D[o][b]   (bias = row nI of A == 1)
 __device__ __forceinline__ void train_stage_gemm(float* __restrict__ G, const float* __restrict__ A,
                                                  const float* __restrict__ D, int nO, int nI, int base, int so, int si,
-                                                 int bbase, int sb, int nb4) {
+                                                 int bbase, int sb) {
   const int nI1 = nI + 1, total = nO * nI1;
   for (int e = threadIdx.x; e < total; e += kTrainThreads) {
     const int o = e / nI1, i = e - o * nI1;
     const float4* a4 = reinterpret_cast<const float4*>(A + i * kStageStride);
     const float4* d4 = reinterpret_cast<const float4*>(D + o * kStageStride);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 4
-    for (int b = 0; b < nb4; ++b) {   // only the slice's sample columns hold data
+#pragma unroll 8
+    for (int b = 0; b < kTrainThreads / 4; ++b) {
       const float4 a = a4[b], q = d4[b];
       s0 = fmaf(a.x, q.x, s0);
       s1 = fmaf(a.y, q.y, s1);
@@ -234,7 +233,6 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
   __syncthreads();
 
   unsigned int phase = 0;
-  const int slice = p.slice, nb4 = p.slice >> 2;
   const long long bs = p.batch_size;
   const long long nmb = p.do_train ? (p.n_train + bs - 1) / bs : 0;
   for (long long mb = 0; mb < nmb; ++mb) {
@@ -242,9 +240,9 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
     const float inv_bs = 1.0f / (float)cnt;
     for (int q = tid; q < Psm; q += kTrainThreads) G[q] = 0.f;
     float loss_t = 0.f;
-    for (long long s0 = (long long)blockIdx.x * slice; s0 < cnt; s0 += (long long)gridDim.x * slice) {
+    for (long long s0 = (long long)blockIdx.x * kTrainThreads; s0 < cnt; s0 += (long long)gridDim.x * kTrainThreads) {
       const long long s = s0 + tid;
-      const bool valid = tid < slice && s < cnt;
+      const bool valid = s < cnt;
       const float vscale = valid ? 1.0f : 0.0f;
       // ---- load the sample: x[perm[pos]] + jitter * N(0, I)    (trainer.py:390) ---------------------------------
       if (valid) {
@@ -309,8 +307,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
         As[H * kStageStride + tid] = 1.0f;
         At[H * kStageStride + tid] = 1.0f;
         __syncthreads();
-        train_stage_gemm(G, As, Ds, nout, H, sbase + w3off + o0 * H, 2 * H, 1, sbase + b3off + o0, 2, nb4);
-        train_stage_gemm(G, At, Dt, nout, H, tbase + w3off + o0 * H, 2 * H, 1, tbase + b3off + o0, 2, nb4);
+        train_stage_gemm(G, As, Ds, nout, H, sbase + w3off + o0 * H, 2 * H, 1, sbase + b3off + o0, 2);
+        train_stage_gemm(G, At, Dt, nout, H, tbase + w3off + o0 * H, 2 * H, 1, tbase + b3off + o0, 2);
         // hidden layers, last to first
 #pragma unroll
         for (int l = L - 1; l >= 0; --l) {
@@ -335,8 +333,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
           As[H * kStageStride + tid] = 1.0f;
           At[H * kStageStride + tid] = 1.0f;
           __syncthreads();
-          train_stage_gemm(G, As, Ds, H, H, sbase + wl, H, 1, sbase + wl + H * H, 1, nb4);
-          train_stage_gemm(G, At, Dt, H, H, tbase + wl, H, 1, tbase + wl + H * H, 1, nb4);
+          train_stage_gemm(G, As, Ds, H, H, sbase + wl, H, 1, sbase + wl + H * H, 1);
+          train_stage_gemm(G, At, Dt, H, H, tbase + wl, H, 1, tbase + wl + H * H, 1);
         }
         // input layer
         {
@@ -361,8 +359,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
           As[nin * kStageStride + tid] = 1.0f;
           __syncthreads();
           // both nets share the input: A = As for both
-          train_stage_gemm(G, As, Ds, H, nin, sbase + i0 * H, 1, 2 * H, sbase + b1off, 1, nb4);
-          train_stage_gemm(G, As, Dt, H, nin, tbase + i0 * H, 1, 2 * H, tbase + b1off, 1, nb4);
+          train_stage_gemm(G, As, Ds, H, nin, sbase + i0 * H, 1, 2 * H, sbase + b1off, 1);
+          train_stage_gemm(G, As, Dt, H, nin, tbase + i0 * H, 1, 2 * H, tbase + b1off, 1);
         }
       }
       __syncthreads();
