@@ -8,10 +8,10 @@
 //     spread over ceil(batch/128) CTAs (at most one per SM).  With the reference's default batch_size = 100 that
 //     is ONE CTA walking the whole epoch with weights, gradient and sample vectors resident in shared memory --
 //     no launches, no host round trips between iterations.
-//   * memory-free backward: a coupling block is invertible, so the backward pass walks the blocks in reverse,
-//     recomputes the s/t MLP activations of block k from the pass-through half of its OUTPUT (bit-identical to
-//     the forward pass) and recovers the block input as (y - t) * exp(-s).  Only the current vector and its
-//     gradient are kept per sample (2 d floats in shared memory).
+//   * light-weight backward: a coupling block is invertible, so the backward pass walks the blocks in reverse and
+//     recovers each block's input as (y - t) * exp(-s) instead of storing it; the hidden activations of the s/t MLPs
+//     are kept from the forward pass in per-thread local memory (L1 resident, 2 (L+1) H floats per block).  Per sample
+//     only the current vector and its gradient live in shared memory (2 d floats).
 //   * weight gradients are batch contractions dW[o][i] = sum_b dpre[b][o] * in[b][i]: every thread stages its
 //     sample's `in` / `dpre` vectors as columns of two shared-memory matrices ([feature][sample], rows 16-byte
 //     aligned), then each (o, i) pair is owned by one thread, which runs down the sample axis with float4 loads.
@@ -173,9 +173,12 @@ __device__ __forceinline__ void train_grid_barrier(TrainCtrl* c, unsigned int& p
   __syncthreads();
 }
 
-// forward flow of the thread's sample, in place on the column y; returns -log p(x)
-template <int H, int L>
-__device__ __forceinline__ float train_forward_nll(const float* __restrict__ W, int d, int B, int netPp, float* y) {
+// forward flow of the thread's sample, in place on the column y; returns -log p(x).  KEEP: the hidden activations of
+// every block are kept for the backward pass in `acts` (per-thread local memory, L1 resident: 2 (L+1) H floats per block
+// -- cheaper to reload than to recompute)
+template <int H, int L, bool KEEP>
+__device__ __forceinline__ float train_forward_nll(const float* __restrict__ W, int d, int B, int netPp, float* y,
+                                                   float (*acts)[2][L + 1][H]) {
   float ld = 0.f;
   const int w3 = H * d + H + L * (H * H + H), b3 = w3 + d * H;
   for (int k = 0; k < B; ++k) {
@@ -185,6 +188,15 @@ __device__ __forceinline__ float train_forward_nll(const float* __restrict__ W, 
     float hs[L + 1][H], ht[L + 1][H];
     train_mlp_hidden<H, L, 0>(ws, d, nin, i0, y, hs);
     train_mlp_hidden<H, L, 1>(wt, d, nin, i0, y, ht);
+    if (KEEP) {
+#pragma unroll
+      for (int l = 0; l <= L; ++l)
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+          acts[k][0][l][j] = hs[l][j];
+          acts[k][1][l][j] = ht[l][j];
+        }
+    }
     for (int o = 0; o < nout; ++o) {
       const int i = o0 + 2 * o;
       const float s = dot_row<H>(ws + w3 + i * H, hs[L]) + ws[b3 + i];
@@ -233,6 +245,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
   __syncthreads();
 
   unsigned int phase = 0;
+  float acts[NNB_MAX_BLOCKS][2][L + 1][H];   // local memory: hidden activations of the forward pass, per block
   const long long bs = p.batch_size;
   const long long nmb = p.do_train ? (p.n_train + bs - 1) / bs : 0;
   for (long long mb = 0; mb < nmb; ++mb) {
@@ -269,7 +282,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
         for (int i = 0; i < d; ++i) y[i * kTrainThreads] = 0.f;
       }
       // ---- forward: z = f(x), loss contribution, dL/dz = z / batch ------------------------------------------------------
-      const float nll = train_forward_nll<H, L>(W, d, B, netPp, y);
+      const float nll = train_forward_nll<H, L, true>(W, d, B, netPp, y, acts);
       if (valid) loss_t += nll * inv_bs;
       for (int i = 0; i < d; ++i) gy[i * kTrainThreads] = y[i * kTrainThreads] * inv_bs * vscale;
       // ---- backward, blocks in reverse; y = output of block k on entry, its input on exit -----------------------------
@@ -279,8 +292,13 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
         const float* ws = W + sbase;
         const float* wt = W + tbase;
         float hs[L + 1][H], ht[L + 1][H];
-        train_mlp_hidden<H, L, 0>(ws, d, nin, i0, y, hs);
-        train_mlp_hidden<H, L, 1>(wt, d, nin, i0, y, ht);
+#pragma unroll
+        for (int l = 0; l <= L; ++l)
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            hs[l][j] = acts[k][0][l][j];
+            ht[l][j] = acts[k][1][l][j];
+          }
         float dhs[H], dht[H];
 #pragma unroll
         for (int j = 0; j < H; ++j) dhs[j] = dht[j] = 0.f;
@@ -394,17 +412,37 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
       const float bc1 = (float)(1.0 - pow((double)p.beta1, step));
       const float bc2s = (float)sqrt(1.0 - pow((double)p.beta2, step));
       const float step_size = p.lr / bc1;
-      for (int q = tid; q < p.P; q += kTrainThreads) {
-        const int w = train_perm_index<H>(q, d, netP, netPp);
-        const float wv = W[w];
-        const float g = fmaf(p.weight_decay, wv, G[w]);
-        float m = m_ptr[q], v = v_ptr[q];
-        m = m + (g - m) * (1.0f - p.beta1);                 // exp_avg.lerp_(grad, 1 - beta1)
-        v = fmaf(g * g, 1.0f - p.beta2, v * p.beta2);        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-        m_ptr[q] = m;
-        v_ptr[q] = v;
-        const float denom = sqrtf(v) / bc2s + p.eps;
-        W[w] = wv - step_size * (m / denom);
+      // walk the parameters in shared-memory order (no integer division to map indices: H is a power of two) and
+      // fetch the moments of four parameters before touching any of them, so that their L2 latencies overlap
+      float* __restrict__ mp = m_ptr;
+      float* __restrict__ vp = v_ptr;
+      for (int net = 0; net < 2 * B; ++net) {
+        const int qbase = net * netP, wbase = net * netPp;
+        for (int r0 = tid; r0 < netP; r0 += 4 * kTrainThreads) {
+          int qi[4];
+          float mv[4], vv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * kTrainThreads;
+            // first layer: shared memory holds W1T[i][j] (r = i H + j), the caller's vector W1[j][i] (j d + i)
+            qi[u] = r < netP ? qbase + (r < H * d ? (r % H) * d + r / H : r) : -1;
+            mv[u] = qi[u] >= 0 ? mp[qi[u]] : 0.f;
+            vv[u] = qi[u] >= 0 ? vp[qi[u]] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (qi[u] < 0) continue;
+            const int w = wbase + r0 + u * kTrainThreads;
+            const float wv = W[w];
+            const float g = fmaf(p.weight_decay, wv, G[w]);
+            const float m = mv[u] + (g - mv[u]) * (1.0f - p.beta1);     // exp_avg.lerp_(grad, 1 - beta1)
+            const float v = fmaf(g * g, 1.0f - p.beta2, vv[u] * p.beta2);   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+            mp[qi[u]] = m;
+            vp[qi[u]] = v;
+            const float denom = sqrtf(v) / bc2s + p.eps;
+            W[w] = wv - step_size * (m / denom);
+          }
+        }
       }
     }
     __syncthreads();
@@ -418,7 +456,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
       const bool valid = s < p.n_valid;
       const float* xr = p.x_valid + (valid ? s : 0) * d;
       for (int i = 0; i < d; ++i) y[i * kTrainThreads] = valid ? xr[i] : 0.f;
-      const float nll = train_forward_nll<H, L>(W, d, B, netPp, y);
+      const float nll = train_forward_nll<H, L, false>(W, d, B, netPp, y, nullptr);
       if (valid) loss_t += nll;
     }
     double v = (double)loss_t;
