@@ -195,3 +195,31 @@ def test_mcmc_sampler_gaussian_posterior(tmp_path):
     # the recorded loglikes are the float64 likelihood of the recorded (transformed) samples
     chk = s._like(s.samples[:4, -1, :].astype(np.float64))
     assert np.allclose(chk, s.loglikes[:4, -1], rtol=1e-5, atol=1e-5)
+
+
+def test_resume_from_checkpoint(tmp_path):
+    """Checkpoint / resume (nested.py:166-195, 249-260, 473-484): a run stopped by max_iters leaves checkpoint_<it>.txt
+    plus the .npy arrays; a second sampler on the same run directory picks the highest checkpoint up and finishes with
+    an evidence consistent with the reference's Rosenbrock-2D value."""
+    from nnest_b200 import NestedSampler
+    from nnest_b200.likelihoods import Rosenbrock
+    np.random.seed(3)
+    torch.manual_seed(3)
+    kw = dict(transform=lambda x: 5 * x, num_live_points=400, flow='nvp', log_dir=str(tmp_path), log_level=logging.WARNING)
+    s1 = NestedSampler(2, Rosenbrock(2), **kw)
+    s1.run(mcmc_num_chains=100, train_iters=30, max_iters=900, log_interval=300, strategy=['mcmc'])
+    run_dir = s1.logs['run_dir']
+    ck = sorted(int(f.split('checkpoint_')[1].split('.txt')[0]) for f in os.listdir(os.path.join(run_dir, 'checkpoint'))
+                if f.startswith('checkpoint_'))
+    assert ck[0] == 0 and ck[-1] >= 600
+    assert s1.niter <= 903
+    # the run directory exists -> resume there (append_run_num only matters for new directories)
+    s2 = NestedSampler(2, Rosenbrock(2), **dict(kw, log_dir=run_dir))
+    assert not s2.logs['created']
+    s2.run(mcmc_num_chains=100, train_iters=30, log_interval=300, strategy=['mcmc'])
+    assert s2.niter > s1.niter
+    assert np.abs(s2.logz + 5.80) <= 0.2 + 3 * s2.logzerr
+    saved = np.load(os.path.join(run_dir, 'checkpoint', 'saved_logl.npy'))
+    assert np.all(np.diff(saved) >= 0)                       # dead points leave in order of increasing likelihood
+    assert s2.samples.shape[0] == len(s2.loglikes) == len(s2.weights)
+    assert abs(s2.weights.sum() - 1.0) < 1e-6
