@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 6
+#define NNB_ABI_VERSION 7
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -201,7 +201,13 @@ typedef struct {
   int* impl_out;         /* [host] NNB_IMPL_FFMA or NNB_IMPL_TCGEN05: the variant that ran */
 } nnb_mcmc_args;
 
-int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream); /* synchronous at return */
+int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream);
+/*
+ * nnb_mcmc_run synchronises the stream before returning when any of scale_out / ncall_out / naccept_out is given; with
+ * all three NULL it only enqueues the work (several refills can be queued back to back) and the figures of the LAST
+ * run are fetched with nnb_mcmc_result, which synchronises.
+ */
+int nnb_mcmc_result(nnb_handle* h, double* scale_out, int64_t* ncall_out, int64_t* naccept_out, void* stream);
 
 /*
  * Live-point replacement (replaces the consume loop of NestedSampler.run, nnest/nested.py:429-439,

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libnnb.so')
 
-NNB_ABI_VERSION = 6
+NNB_ABI_VERSION = 7
 NNB_MAX_DIM = 128
 NNB_MAX_BLOCKS = 16
 
@@ -76,6 +76,7 @@ SYMBOLS = {
                               C.c_int64, C.c_void_p]),
     'nnb_mcmc_init': (C.c_int, [C.c_void_p, C.POINTER(nnb_mcmc_init_args), C.c_void_p]),
     'nnb_mcmc_run': (C.c_int, [C.c_void_p, C.POINTER(nnb_mcmc_args), C.c_void_p]),
+    'nnb_mcmc_result': (C.c_int, [C.c_void_p, _dp, _ip, _ip, C.c_void_p]),
     'nnb_consume_scan': (C.c_int64, [_fp, _fp, _dp, C.c_int64, C.c_int, C.c_double, _ip]),
     'nnb_ns_consume': (C.c_int64, [_dp, C.c_int64, _fp, _fp, _dp, C.c_int64, C.c_int, _ip, C.c_int64, _ip, _ip, _ip, _dp,
                                    _dp, C.POINTER(C.c_int)]),

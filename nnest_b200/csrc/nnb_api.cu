@@ -275,6 +275,13 @@ static int check_mcmc_ready(nnb_handle* h) {
   return NNB_OK;
 }
 
+// zero the control block, scale = `scale` (one thread; keeps asynchronous calls free of host-side staging buffers)
+static __global__ void ctrl_init_kernel(Ctrl* c, double scale) {
+  Ctrl z{};
+  z.scale = scale;
+  *c = z;
+}
+
 extern "C" int nnb_mcmc_init(nnb_handle* h, const nnb_mcmc_init_args* a, void* stream) {
   if (!h || !a) return NNB_ERR_ARG;
   int rc = check_mcmc_ready(h);
@@ -284,8 +291,7 @@ extern "C" int nnb_mcmc_init(nnb_handle* h, const nnb_mcmc_init_args* a, void* s
   if (a->init_u && a->init_z) return fail(h, NNB_ERR_ARG, "give at most one of init_u / init_z");
   NNB_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  std::memset(h->h_ctrl, 0, sizeof(Ctrl));
-  NNB_CUDA(h, cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
+  ctrl_init_kernel<<<1, 1, 0, st>>>(h->d_ctrl, 0.0);
   InitParams p{};
   p.n = a->n_chains; p.z = a->z; p.x = a->x; p.logl = a->logl; p.logdet = a->logdet; p.logp = a->logp;
   p.init_u = a->init_u; p.init_z = a->init_z; p.init_logl = a->init_logl;
@@ -321,9 +327,9 @@ extern "C" int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream)
   cudaStream_t st = (cudaStream_t)stream;
   const int d = h->flow.d;
   const long long n = a->n_chains;
-  std::memset(h->h_ctrl, 0, sizeof(Ctrl));
-  h->h_ctrl->scale = a->step_size > 0.0 ? a->step_size : 2.0 / std::sqrt((double)d);  // sampler.py:248-249
-  NNB_CUDA(h, cudaMemcpyAsync(h->d_ctrl, h->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
+  // control block: zero counters, scale = step_size (default 2 / sqrt(d), sampler.py:248-249).  Set by a one-thread kernel
+  // rather than a copy from the pinned mirror, so that asynchronous calls can be queued back to back
+  ctrl_init_kernel<<<1, 1, 0, st>>>(h->d_ctrl, a->step_size > 0.0 ? a->step_size : 2.0 / std::sqrt((double)d));
   if (a->trace_x) {  // row 0 = state at entry (sampler.py:286-289)
     NNB_CUDA(h, cudaMemcpyAsync(a->trace_x, a->x, sizeof(float) * d * n, cudaMemcpyDeviceToDevice, st));
     NNB_CUDA(h, cudaMemcpyAsync(a->trace_z, a->z, sizeof(float) * d * n, cudaMemcpyDeviceToDevice, st));
@@ -354,13 +360,23 @@ extern "C" int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream)
     }
     if (rc) return rc;
   }
-  NNB_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-  NNB_CUDA(h, cudaStreamSynchronize(st));
-  if (a->scale_out) *a->scale_out = h->h_ctrl->scale;
-  if (a->ncall_out) *a->ncall_out = (int64_t)h->h_ctrl->ncall;
-  if (a->naccept_out) *a->naccept_out = (int64_t)h->h_ctrl->naccept;
   if (a->launches_out) *a->launches_out = a->steps > 0 ? h->last_launches : 0;
   if (a->impl_out) *a->impl_out = use_tc ? NNB_IMPL_TCGEN05 : NNB_IMPL_FFMA;
+  NNB_CUDA(h, cudaGetLastError());
+  // no result requested: the call stays asynchronous (results of the last run: nnb_mcmc_result)
+  if (!a->scale_out && !a->ncall_out && !a->naccept_out) return NNB_OK;
+  return nnb_mcmc_result(h, a->scale_out, a->ncall_out, a->naccept_out, stream);
+}
+
+extern "C" int nnb_mcmc_result(nnb_handle* h, double* scale_out, int64_t* ncall_out, int64_t* naccept_out, void* stream) {
+  if (!h) return NNB_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  NNB_CUDA(h, cudaSetDevice(h->device));
+  NNB_CUDA(h, cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  NNB_CUDA(h, cudaStreamSynchronize(st));
+  if (scale_out) *scale_out = h->h_ctrl->scale;
+  if (ncall_out) *ncall_out = (int64_t)h->h_ctrl->ncall;
+  if (naccept_out) *naccept_out = (int64_t)h->h_ctrl->naccept;
   return NNB_OK;
 }
 

@@ -294,9 +294,11 @@ class Engine(object):
         return st, nbad.value, ncall.value
 
     def mcmc_run(self, st, steps, mode=L.NNB_MODE_HARD, loglstar=0.0, step_size=0.0, dynamic_step_size=False,
-                 seed=0, chain_offset=0, step_offset=0, trace=False, replay=None, dump_noise=False, impl=None):
+                 seed=0, chain_offset=0, step_offset=0, trace=False, replay=None, dump_noise=False, impl=None,
+                 sync=True):
         """Advances `st` in place by `steps` steps.  Returns a dict with scale, ncall, naccept and, if
-        requested, the trace tensors (steps+1, d, n) / (steps+1, n) and the dumped noise."""
+        requested, the trace tensors (steps+1, d, n) / (steps+1, n) and the dumped noise.  sync=False only enqueues
+        the work (no scale / ncall / naccept in the result; `mcmc_result()` fetches those of the last run)."""
         n, d = st.n, st.d
         a = L.nnb_mcmc_args()
         a.n_chains, a.steps, a.mode = n, steps, mode
@@ -321,9 +323,18 @@ class Engine(object):
             out['uniforms'] = torch.empty((steps, n), dtype=torch.float32, device=self.device)
             a.dump_normals, a.dump_uniforms = out['normals'].data_ptr(), out['uniforms'].data_ptr()
         scale, ncall, nacc, nl, impl_ran = C.c_double(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int(0)
-        a.scale_out, a.ncall_out, a.naccept_out = C.pointer(scale), C.pointer(ncall), C.pointer(nacc)
+        if sync:
+            a.scale_out, a.ncall_out, a.naccept_out = C.pointer(scale), C.pointer(ncall), C.pointer(nacc)
         a.launches_out, a.impl_out = C.pointer(nl), C.pointer(impl_ran)
         self._check(self.lib.nnb_mcmc_run(self.h, C.byref(a), _stream()))
         self.gpu_launches += nl.value
-        out.update(scale=scale.value, ncall=ncall.value, naccept=nacc.value, launches=nl.value, impl=impl_ran.value)
+        out.update(launches=nl.value, impl=impl_ran.value)
+        if sync:
+            out.update(scale=scale.value, ncall=ncall.value, naccept=nacc.value)
         return out
+
+    def mcmc_result(self):
+        """scale, ncall, naccept of the last mcmc_run (synchronises the stream)."""
+        scale, ncall, nacc = C.c_double(0), C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.nnb_mcmc_result(self.h, C.byref(scale), C.byref(ncall), C.byref(nacc), _stream()))
+        return dict(scale=scale.value, ncall=ncall.value, naccept=nacc.value)
