@@ -15,10 +15,10 @@ int launch_train(nnb_handle* h, TrainParams& p, int grid, size_t smem, cudaStrea
   NNB_CUDA(h, nnb_set_smem(train_epoch_kernel<H, L>, smem));
   if (grid > 1) {
     void* args[] = {(void*)&p};
-    NNB_CUDA(h, cudaLaunchCooperativeKernel((const void*)train_epoch_kernel<H, L>, dim3(grid), dim3(kTrainThreads), args,
+    NNB_CUDA(h, cudaLaunchCooperativeKernel((const void*)train_epoch_kernel<H, L>, dim3(grid), dim3(kTrainCta), args,
                                             smem, st));
   } else {
-    train_epoch_kernel<H, L><<<1, kTrainThreads, smem, st>>>(p);
+    train_epoch_kernel<H, L><<<1, kTrainCta, smem, st>>>(p);
     NNB_CUDA(h, cudaGetLastError());
   }
   return NNB_OK;

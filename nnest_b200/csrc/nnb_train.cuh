@@ -4,7 +4,7 @@
 // backward pass, Adam step (torch.optim.Adam semantics incl. L2 weight decay); then the validation loss.
 //
 // Design (sm_100a, FP32):
-//   * persistent kernel, 128 threads per CTA, one sample per thread in the per-sample phases; a mini-batch is
+//   * persistent kernel, 256 threads per CTA, 128 of them own one sample each in the per-sample phases; a mini-batch is
 //     spread over ceil(batch/128) CTAs (at most one per SM).  With the reference's default batch_size = 100 that
 //     is ONE CTA walking the whole epoch with weights, gradient and sample vectors resident in shared memory --
 //     no launches, no host round trips between iterations.
@@ -27,7 +27,8 @@
 
 namespace nnb {
 
-constexpr int kTrainThreads = 128;
+constexpr int kTrainThreads = 128;   // samples per slice = worker threads (one sample each)
+constexpr int kTrainCta = 256;       // threads per CTA
 constexpr int kStageStride = 132;   // floats per staged row: 128 samples + 4 (rows 16-byte aligned, bank-conflict free)
 enum { kTagTrain = 3 };
 
@@ -142,7 +143,7 @@ __device__ __forceinline__ void train_stage_gemm(float* __restrict__ G, const fl
                                                  const float* __restrict__ D, int nO, int nI, int base, int so, int si,
                                                  int bbase, int sb) {
   const int nI1 = nI + 1, total = nO * nI1;
-  for (int e = threadIdx.x; e < total; e += kTrainThreads) {
+  for (int e = threadIdx.x; e < total; e += kTrainCta) {
     const int o = e / nI1, i = e - o * nI1;
     const float4* a4 = reinterpret_cast<const float4*>(A + i * kStageStride);
     const float4* d4 = reinterpret_cast<const float4*>(D + o * kStageStride);
@@ -211,7 +212,7 @@ __device__ __forceinline__ float train_forward_nll(const float* __restrict__ W, 
 }
 
 template <int H, int L>
-__global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainParams p) {
+__global__ void __launch_bounds__(kTrainCta, 1) train_epoch_kernel(TrainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int d = p.d, B = p.B, netP = p.netP, netPp = round4(netP), Psm = 2 * B * netPp;
   float* W = reinterpret_cast<float*>(smem_raw);
@@ -226,18 +227,21 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
   float* Ds = At + IM * kStageStride;
   float* Dt = Ds + OM * kStageStride;
   const int tid = threadIdx.x;
-  float* y = y_all + tid;
-  float* gy = gy_all + tid;
+  // warps 0-3 own one sample each ("workers"); warps 4-7 only join the CTA-wide phases (weight-gradient contractions,
+  // Adam, copies), which are latency bound with four warps
+  const bool worker = tid < kTrainThreads;
+  float* y = y_all + (worker ? tid : 0);
+  float* gy = gy_all + (worker ? tid : 0);
   const int w2off = H * d + H, w3off = w2off + L * (H * H + H), b3off = w3off + d * H, b1off = H * d;
 
-  for (int q = tid; q < Psm; q += kTrainThreads) W[q] = 0.f;
+  for (int q = tid; q < Psm; q += kTrainCta) W[q] = 0.f;
   __syncthreads();
-  for (int q = tid; q < p.P; q += kTrainThreads) W[train_perm_index<H>(q, d, netP, netPp)] = p.params[q];
+  for (int q = tid; q < p.P; q += kTrainCta) W[train_perm_index<H>(q, d, netP, netPp)] = p.params[q];
   const bool multi = gridDim.x > 1;
   float* m_ptr = multi ? p.mv_priv + (size_t)blockIdx.x * 2 * p.P : p.adam_m;
   float* v_ptr = multi ? m_ptr + p.P : p.adam_v;
   if (multi && p.do_train) {
-    for (int q = tid; q < p.P; q += kTrainThreads) {
+    for (int q = tid; q < p.P; q += kTrainCta) {
       m_ptr[q] = p.adam_m[q];
       v_ptr[q] = p.adam_v[q];
     }
@@ -251,12 +255,13 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
   for (long long mb = 0; mb < nmb; ++mb) {
     const long long cnt = (p.n_train - mb * bs) < bs ? (p.n_train - mb * bs) : bs;   // DataLoader keeps the short tail
     const float inv_bs = 1.0f / (float)cnt;
-    for (int q = tid; q < Psm; q += kTrainThreads) G[q] = 0.f;
+    for (int q = tid; q < Psm; q += kTrainCta) G[q] = 0.f;
     float loss_t = 0.f;
     for (long long s0 = (long long)blockIdx.x * kTrainThreads; s0 < cnt; s0 += (long long)gridDim.x * kTrainThreads) {
       const long long s = s0 + tid;
-      const bool valid = s < cnt;
+      const bool valid = worker && s < cnt;
       const float vscale = valid ? 1.0f : 0.0f;
+      if (worker) {
       // ---- load the sample: x[perm[pos]] + jitter * N(0, I)    (trainer.py:390) ---------------------------------
       if (valid) {
         const long long pos = mb * bs + s;
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
       const float nll = train_forward_nll<H, L, true>(W, d, B, netPp, y, acts);
       if (valid) loss_t += nll * inv_bs;
       for (int i = 0; i < d; ++i) gy[i * kTrainThreads] = y[i * kTrainThreads] * inv_bs * vscale;
+      }
       // ---- backward, blocks in reverse; y = output of block k on entry, its input on exit -----------------------------
       for (int k = B - 1; k >= 0; --k) {
         const int nin = blk_nin(d, k), i0 = blk_i0(k), nout = blk_nout(d, k), o0 = blk_o0(k);
@@ -292,18 +298,21 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
         const float* ws = W + sbase;
         const float* wt = W + tbase;
         float hs[L + 1][H], ht[L + 1][H];
+        if (worker) {
 #pragma unroll
-        for (int l = 0; l <= L; ++l)
+          for (int l = 0; l <= L; ++l)
 #pragma unroll
-          for (int j = 0; j < H; ++j) {
-            hs[l][j] = acts[k][0][l][j];
-            ht[l][j] = acts[k][1][l][j];
-          }
+            for (int j = 0; j < H; ++j) {
+              hs[l][j] = acts[k][0][l][j];
+              ht[l][j] = acts[k][1][l][j];
+            }
+        }
         float dhs[H], dht[H];
 #pragma unroll
         for (int j = 0; j < H; ++j) dhs[j] = dht[j] = 0.f;
         // output layer: z_i = x_i e^{s} + t, log-det += s   ->   ds = g (z_i - t) - 1/batch, dt = g, dx = g e^{s}
         __syncthreads();   // previous GEMM finished with the staging buffers
+        if (worker) {
         for (int o = 0; o < nout; ++o) {
           const int i = o0 + 2 * o;
           const float s = dot_row<H>(ws + w3off + i * H, hs[L]) + ws[b3off + i];
@@ -324,6 +333,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
         }
         As[H * kStageStride + tid] = 1.0f;
         At[H * kStageStride + tid] = 1.0f;
+        }
         __syncthreads();
         train_stage_gemm(G, As, Ds, nout, H, sbase + w3off + o0 * H, 2 * H, 1, sbase + b3off + o0, 2);
         train_stage_gemm(G, At, Dt, nout, H, tbase + w3off + o0 * H, 2 * H, 1, tbase + b3off + o0, 2);
@@ -331,14 +341,17 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
 #pragma unroll
         for (int l = L - 1; l >= 0; --l) {
           float dps[H], dpt[H];
+          if (worker) {
 #pragma unroll
-          for (int j = 0; j < H; ++j) {
-            dps[j] = dhs[j] * train_dact<0>(hs[l + 1][j]);
-            dpt[j] = dht[j] * train_dact<1>(ht[l + 1][j]);
-            dhs[j] = dht[j] = 0.f;
+            for (int j = 0; j < H; ++j) {
+              dps[j] = dhs[j] * train_dact<0>(hs[l + 1][j]);
+              dpt[j] = dht[j] * train_dact<1>(ht[l + 1][j]);
+              dhs[j] = dht[j] = 0.f;
+            }
           }
           const int wl = w2off + l * (H * H + H);
           __syncthreads();
+          if (worker) {
 #pragma unroll
           for (int j = 0; j < H; ++j) {
             axpy_row<H>(ws + wl + j * H, dps[j], dhs);
@@ -350,6 +363,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
           }
           As[H * kStageStride + tid] = 1.0f;
           At[H * kStageStride + tid] = 1.0f;
+          }
           __syncthreads();
           train_stage_gemm(G, As, Ds, H, H, sbase + wl, H, 1, sbase + wl + H * H, 1);
           train_stage_gemm(G, At, Dt, H, H, tbase + wl, H, 1, tbase + wl + H * H, 1);
@@ -357,12 +371,15 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
         // input layer
         {
           float dps[H], dpt[H];
+          if (worker) {
 #pragma unroll
-          for (int j = 0; j < H; ++j) {
-            dps[j] = dhs[j] * train_dact<0>(hs[0][j]);
-            dpt[j] = dht[j] * train_dact<1>(ht[0][j]);
+            for (int j = 0; j < H; ++j) {
+              dps[j] = dhs[j] * train_dact<0>(hs[0][j]);
+              dpt[j] = dht[j] * train_dact<1>(ht[0][j]);
+            }
           }
           __syncthreads();
+          if (worker) {
 #pragma unroll
           for (int j = 0; j < H; ++j) {
             Ds[j * kStageStride + tid] = dps[j];
@@ -375,6 +392,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
             gy[i * kTrainThreads] += dot_row<H>(ws + i * H, dps) + dot_row<H>(wt + i * H, dpt);
           }
           As[nin * kStageStride + tid] = 1.0f;
+          }
           __syncthreads();
           // both nets share the input: A = As for both
           train_stage_gemm(G, As, Ds, H, nin, sbase + i0 * H, 1, 2 * H, sbase + b1off, 1);
@@ -394,18 +412,18 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
     // ---- several CTAs per mini-batch: sum the partial gradients through global memory --------------------------------
     if (multi) {
       float* gb = p.gbuf + (size_t)(mb % 3) * Psm;
-      for (int q = tid; q < Psm; q += kTrainThreads)
+      for (int q = tid; q < Psm; q += kTrainCta)
         if (G[q] != 0.f) atomicAdd(gb + q, G[q]);
       train_grid_barrier(p.ctrl, phase);
-      for (int q = tid; q < Psm; q += kTrainThreads) G[q] = __ldcg(gb + q);
+      for (int q = tid; q < Psm; q += kTrainCta) G[q] = __ldcg(gb + q);
       // the buffer of mini-batch mb + 2 was last read during mb - 1: every CTA is past that point
       float* gz = p.gbuf + (size_t)((mb + 2) % 3) * Psm;
       const int chunk = (Psm + gridDim.x - 1) / gridDim.x;
-      for (int q = blockIdx.x * chunk + tid; q < Psm && q < (int)(blockIdx.x + 1) * chunk; q += kTrainThreads) gz[q] = 0.f;
+      for (int q = blockIdx.x * chunk + tid; q < Psm && q < (int)(blockIdx.x + 1) * chunk; q += kTrainCta) gz[q] = 0.f;
       __syncthreads();
     }
     if (p.grad_out && mb == nmb - 1 && blockIdx.x == 0)
-      for (int q = tid; q < p.P; q += kTrainThreads) p.grad_out[q] = G[train_perm_index<H>(q, d, netP, netPp)];
+      for (int q = tid; q < p.P; q += kTrainCta) p.grad_out[q] = G[train_perm_index<H>(q, d, netP, netPp)];
     // ---- Adam (torch.optim.Adam, weight decay added to the gradient), identical in every CTA -----------------------------
     {
       const double step = (double)(p.step0 + mb + 1);
@@ -418,12 +436,12 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
       float* __restrict__ vp = v_ptr;
       for (int net = 0; net < 2 * B; ++net) {
         const int qbase = net * netP, wbase = net * netPp;
-        for (int r0 = tid; r0 < netP; r0 += 4 * kTrainThreads) {
+        for (int r0 = tid; r0 < netP; r0 += 4 * kTrainCta) {
           int qi[4];
           float mv[4], vv[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int r = r0 + u * kTrainThreads;
+            const int r = r0 + u * kTrainCta;
             // first layer: shared memory holds W1T[i][j] (r = i H + j), the caller's vector W1[j][i] (j d + i)
             qi[u] = r < netP ? qbase + (r < H * d ? (r % H) * d + r / H : r) : -1;
             mv[u] = qi[u] >= 0 ? mp[qi[u]] : 0.f;
@@ -432,7 +450,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (qi[u] < 0) continue;
-            const int w = wbase + r0 + u * kTrainThreads;
+            const int w = wbase + r0 + u * kTrainCta;
             const float wv = W[w];
             const float g = fmaf(p.weight_decay, wv, G[w]);
             const float m = mv[u] + (g - mv[u]) * (1.0f - p.beta1);     // exp_avg.lerp_(grad, 1 - beta1)
@@ -453,11 +471,13 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
     float loss_t = 0.f;
     for (long long s0 = (long long)blockIdx.x * kTrainThreads; s0 < p.n_valid; s0 += (long long)gridDim.x * kTrainThreads) {
       const long long s = s0 + tid;
-      const bool valid = s < p.n_valid;
-      const float* xr = p.x_valid + (valid ? s : 0) * d;
-      for (int i = 0; i < d; ++i) y[i * kTrainThreads] = valid ? xr[i] : 0.f;
-      const float nll = train_forward_nll<H, L, false>(W, d, B, netPp, y, nullptr);
-      if (valid) loss_t += nll;
+      const bool valid = worker && s < p.n_valid;
+      if (worker) {
+        const float* xr = p.x_valid + (valid ? s : 0) * d;
+        for (int i = 0; i < d; ++i) y[i * kTrainThreads] = valid ? xr[i] : 0.f;
+        const float nll = train_forward_nll<H, L, false>(W, d, B, netPp, y, nullptr);
+        if (valid) loss_t += nll;
+      }
     }
     double v = (double)loss_t;
 #pragma unroll
@@ -466,7 +486,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) train_epoch_kernel(TrainPara
   }
   // ---- publish ----------------------------------------------------------------------------------------------------------------
   if (blockIdx.x == 0 && p.do_train) {
-    for (int q = tid; q < p.P; q += kTrainThreads) {
+    for (int q = tid; q < p.P; q += kTrainCta) {
       p.params[q] = W[train_perm_index<H>(q, d, netP, netPp)];
       if (multi) {
         p.adam_m[q] = m_ptr[q];

@@ -290,7 +290,7 @@ class Engine(object):
         if want_counts:
             a.n_bad_start, a.ncall = C.pointer(nbad), C.pointer(ncall)
         self._check(self.lib.nnb_mcmc_init(self.h, C.byref(a), _stream()))
-        self.gpu_launches += 1
+        self.gpu_launches += 2          # control-block reset + chain-start kernel
         return st, nbad.value, ncall.value
 
     def mcmc_run(self, st, steps, mode=L.NNB_MODE_HARD, loglstar=0.0, step_size=0.0, dynamic_step_size=False,
@@ -327,7 +327,7 @@ class Engine(object):
             a.scale_out, a.ncall_out, a.naccept_out = C.pointer(scale), C.pointer(ncall), C.pointer(nacc)
         a.launches_out, a.impl_out = C.pointer(nl), C.pointer(impl_ran)
         self._check(self.lib.nnb_mcmc_run(self.h, C.byref(a), _stream()))
-        self.gpu_launches += nl.value
+        self.gpu_launches += nl.value + 1          # + the one-thread control-block reset
         out.update(launches=nl.value, impl=impl_ran.value)
         if sync:
             out.update(scale=scale.value, ncall=ncall.value, naccept=nacc.value)
