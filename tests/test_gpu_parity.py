@@ -304,3 +304,45 @@ def test_mcmc_hard_constraint_invariants_full_size(engine, impl):
         assert torch.equal(x2.t().contiguous(), st.x) and torch.equal(ld2, st.logdet)
     else:             # tensor-core 3xTF32 path: FP32-class agreement
         assert (x2.t() - st.x).abs().max().item() < 1e-5 and (ld2 - st.logdet).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize('d,layers,blocks', [(4, 1, 1), (5, 1, 2), (7, 2, 4), (13, 1, 3), (33, 1, 3), (63, 1, 2)])
+@pytest.mark.parametrize('npart', ['1', '2'])
+def test_mcmc_generic_tensor_core_path_matches_oracle(engine, d, layers, blocks, npart):
+    """The non-specialised instantiation of the tcgen05 kernel (any 2 <= d <= 63, any num_layers / num_blocks, N3 = 32
+    when more than 16 dims are transformed per block), both thread layouts: free-running Philox noise dumped by the
+    kernel, replayed through the oracle."""
+    import os
+    from nnest_b200 import _lib as L
+    steps, n = 6, 700
+    w = oflow.NVPWeights.random(d, hidden=16, num_layers=layers, num_blocks=blocks, seed=d, gain=1.3)
+    # the thread layout is read once per process from the environment: use a fresh engine-independent switch
+    if os.environ.get('NNB_TC_NPART', '1') != npart:
+        pytest.skip('run with NNB_TC_NPART=%s to cover this layout' % npart)
+    engine.set_flow(w.flat(), d, 16, layers, blocks, 0)
+    engine.set_target(d, 0, [], t_scale=5.0, t_shift=0.0, prior_kind=1, prior_lo=-1.0, prior_hi=1.0)
+    rng = np.random.RandomState(d)
+    u0 = rng.uniform(-0.6, 0.6, size=(n, d))
+    like = olike.Rosenbrock(d)
+    logl0 = like.batch(5 * u0)
+    loglstar = float(np.percentile(logl0, 25))
+    st, _, _ = engine.mcmc_init(n, init_u=dev(np.ascontiguousarray(u0.astype(np.float32).T)), init_logl=dev(logl0),
+                                seed=11)
+    out = engine.mcmc_run(st, steps, mode=0, loglstar=loglstar, step_size=1 / d ** 0.5, dynamic_step_size=True,
+                          seed=11, trace=True, dump_noise=True, impl=L.NNB_IMPL_TCGEN05)
+    assert out['impl'] == L.NNB_IMPL_TCGEN05
+    target = omcmc.Target(like, transform=lambda x: 5 * x, prior=olike.UniformPrior(d, -1, 1), transform_prior=False)
+    ref = omcmc.mcmc_sample(w, target, steps, omcmc.ReplayNoise(out['normals'].cpu().numpy(),
+                                                                 out['uniforms'].cpu().numpy()),
+                            step_size=1 / d ** 0.5, dynamic_step_size=True, init_samples=u0, init_loglikes=logl0,
+                            loglstar=loglstar)
+    latent = out['trace_z'].permute(2, 0, 1).cpu().numpy()
+    samples = out['trace_x'].permute(2, 0, 1).cpu().numpy()
+    moved_ref = np.any(ref[1][:, 1:] != ref[1][:, :-1], axis=2)
+    moved = np.any(latent[:, 1:] != latent[:, :-1], axis=2)
+    same = np.all(moved == moved_ref, axis=1)
+    assert (~same).sum() <= 2                       # near-ties only
+    assert moved.sum() > 0.1 * moved.size           # the test moves chains
+    assert rel_err(latent[same], ref[1][same]) < TOL
+    assert rel_err(samples[same], ref[0][same]) < TOL
+    assert torch.equal(st.z, out['trace_z'][-1]) and torch.equal(st.x, out['trace_x'][-1])
