@@ -320,13 +320,22 @@ def run_gpu(args, wl):
     h_logl = torch.empty((n,), dtype=torch.float64).pin_memory()
     d2h = (h_first.numel() + h_last.numel()) * 4 + h_logl.numel() * 8
 
+    copy_stream = torch.cuda.Stream()
+
     def one_refill_e2e(it):
         if wl['mode'] == 'hard':
             kw = dict(init_u=h_u.cuda(non_blocking=True).t().contiguous(), init_logl=h_l.cuda(non_blocking=True))
         else:
             kw = dict(init_z=h_z.cuda(non_blocking=True).t().contiguous())
         st, _, _ = eng.mcmc_init(n, seed=args.seed, chain_offset=chain_offset, **kw)
-        h_first.copy_(st.x, non_blocking=True)
+        # the start points go back to the host on a side stream while the step kernel runs
+        first = st.x.clone()
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            h_first.copy_(first, non_blocking=True)
+            first.record_stream(copy_stream)
         eng.mcmc_run(st, S, mode=mode, loglstar=prob['loglstar'], step_size=step_size,
                      dynamic_step_size=wl['dynamic'], seed=args.seed, chain_offset=chain_offset, step_offset=it * S,
                      impl=kernel_impl)
