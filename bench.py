@@ -378,7 +378,7 @@ def run_gpu(args, wl):
             peak, peak_src = fp32_peak, 'FP32 FMA pipe: 148 SMs x 128 lanes x 2 x max SM clock (not in MEASURED_PEAKS.json)'
         roofline = {
             'bound': 'tensor' if used_tc else 'fp32-fma', 'achieved': achieved_tflops, 'peak': peak, 'unit': 'TFLOP/s',
-            'frac': achieved_tflops / peak, 'traffic': 9.42e6 * (n * S) / (65536.0 * 150) if used_tc else None,
+            'frac': achieved_tflops / peak, 'traffic': 9.38e6 * (n * S) / (65536.0 * 150) if used_tc else None,
             'kernel': 'mcmc_tc_kernel<MODE,NPART,D> (tcgen05 3xTF32)' if used_tc else 'mcmc_kernel<16,MODE> (FP32 FMA)',
             'launches_per_step': kernel_launches, 'launch_ms': run_ms / max(kernel_launches, 1),
             'algorithmic_flop_per_proposal': flops, 'peak_source': peak_src,
@@ -387,7 +387,7 @@ def run_gpu(args, wl):
                     'tensor pipe executes them as 3xTF32 (x3) on mask-reduced operands (x0.6).  The kernel is bound by '
                     'the per-element work around the MMAs (Philox/Box-Muller, tanh/exp, hi/lo split, likelihood: FP32, ALU '
                     'and MUFU issue slots) and by the latency of nine dependent MMA round trips per step at 16 warps per '
-                    'SM, not by the MMA rate: ncu (profiles/r1_final3_*) issue slots 47.5% busy, tensor pipe 9.4%, DRAM '
+                    'SM, not by the MMA rate: ncu (profiles/r1_final4_*) issue slots 48.5% busy, tensor pipe 9.9%, DRAM '
                     '0.04%; traffic = ncu dram bytes of one refill launch (c4) scaled to this size',
         }
         cpu = cpu_baseline_quick(wl) if world == 1 and not args.no_cpu_baseline else None
