@@ -114,10 +114,37 @@ __device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1) {
 // (NPART = 2: each gets one tanh chunk and one relu chunk).  A rolled loop keeps the code small.
 template <int NPART>
 __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float* __restrict__ bias) {
-  // one thread per chain: the tanh and relu chunks are independent work for the scheduler (unrolled by two); two threads per
-  // chain: a rolled loop keeps the code (and the 64-register budget) small
-#pragma unroll(NPART == 1 ? 2 : 1)
-  for (int c = (NPART == 1 ? 0 : t.part); c < 4; c += NPART) {
+  if (NPART == 1) {
+    // one thread per chain: all 32 pre-activations arrive with ONE tcgen05.ld (one TMEM latency instead of four); the four
+    // chunks are then independent work for the scheduler
+    uint32_t r[32];
+    tc::tmem_ld32(t.lane_tmem + 64, r);
+    tc::wait_ld();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t hi[8], lo[8];
+      const float4* b4 = reinterpret_cast<const float4*>(bias + 8 * c);
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float4 b = b4[q];
+        v[4 * q + 0] = __uint_as_float(r[8 * c + 4 * q + 0]) + b.x;
+        v[4 * q + 1] = __uint_as_float(r[8 * c + 4 * q + 1]) + b.y;
+        v[4 * q + 2] = __uint_as_float(r[8 * c + 4 * q + 2]) + b.z;
+        v[4 * q + 3] = __uint_as_float(r[8 * c + 4 * q + 3]) + b.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = c < 2 ? tc_tanh(v[j]) : fmaxf(v[j], 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tc::split_tf32(v[j], hi[j], lo[j]);
+      tc::tmem_st8(t.lane_tmem + 8 * c, hi);
+      tc::tmem_st8(t.lane_tmem + 32 + 8 * c, lo);
+    }
+    return;
+  }
+  // two threads per chain: a rolled loop keeps the code (and the 64-register budget) small
+#pragma unroll 1
+  for (int c = t.part; c < 4; c += NPART) {
     uint32_t r[8], hi[8], lo[8];
     tc::tmem_ld8(t.lane_tmem + 64 + 8 * c, r);
     tc::wait_ld();
@@ -222,6 +249,38 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
     // x = (z - t) * exp(-log_s), ld -= log_s on the dims with mask == 0   (networks.py:300-309).  The values a dim keeps
     // (its last update: blocks 1 and 0) are tested against the prior box right here (priors.py:39-43).
     const bool chk = box_check && k <= 1;
+    if (NPART == 1 && N3 == 16) {
+      // one thread per chain, at most 16 transformed dims: both output rows arrive before a single wait
+      uint32_t rs[16], rt[16];
+      tc::tmem_ld16(t.lane_tmem + 64, rs);
+      tc::tmem_ld16(t.lane_tmem + 96, rt);
+      tc::wait_ld();
+#pragma unroll
+      for (int c0 = 0; c0 < 16; c0 += 8) {
+        if (c0 < nout) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int o = c0 + j;
+            float xv = 0.f;
+            if (o < nout) {
+              const float ls = __uint_as_float(rs[o]) + b3s[o];
+              const float tt = __uint_as_float(rt[o]) + b3t[o];
+              float* yp = y + (o0 + 2 * o) * ys;
+              xv = (*yp - tt) * tc_exp(-ls);
+              *yp = xv;
+              ld -= ls;
+              if (chk) bad |= (xv < lof[o0 + 2 * o]) | (xv > hif[o0 + 2 * o]);
+            }
+            tc::split_tf32(xv, hi[j], lo[j]);
+          }
+          if (k > 0) {   // A operand of block k-1's first layer
+            tc::tmem_st8(t.lane_tmem + c0, hi);
+            tc::tmem_st8(t.lane_tmem + 32 + c0, lo);
+          }
+        }
+      }
+    } else {
     for (int c0 = (NPART == 1 ? 0 : 8 * t.part); c0 < nout; c0 += 8 * NPART) {
       uint32_t rs[8], rt[8], hi[8], lo[8];
       tc::tmem_ld8(t.lane_tmem + 64 + c0, rs);
@@ -246,6 +305,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
         tc::tmem_st8(t.lane_tmem + c0, hi);
         tc::tmem_st8(t.lane_tmem + 32 + c0, lo);
       }
+    }
     }
     if (NPART > 1 && k == 0) {
       ld_slot[0] = ld;                          // the chain's threads exchange their log-det shares and box flags through
