@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 7
+#define NNB_ABI_VERSION 8
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -239,6 +239,13 @@ int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, const float* fi
                        const double* logl_last, int64_t n_chains, int d, int64_t* nb, int64_t max_iters,
                        int64_t* worst_out, int64_t* chain_out, int64_t* prev_out, double* loglstar_out,
                        double* maxlogl_out, int* exhausted);
+
+/*
+ * Information H of nested sampling over a run of n iterations (nnest/nested.py:283), sequentially and in the reference's
+ * operation order:  h <- (a[i] + b[i] * (h + zp[i])) - zn[i]  with a = exp(logwt - logz_new) * L_worst,
+ * b = exp(logz_old - logz_new), zp = logz_old, zn = logz_new (float64, host).  Returns the final h.  Host-side, exact.
+ */
+double nnb_ns_information(double h, const double* a, const double* b, const double* zp, const double* zn, int64_t n);
 
 /*
  * Flow fitting: ONE EPOCH of the reference's Trainer._train + Trainer._validate (nnest/trainer.py:384-418) in one

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libnnb.so')
 
-NNB_ABI_VERSION = 7
+NNB_ABI_VERSION = 8
 NNB_MAX_DIM = 128
 NNB_MAX_BLOCKS = 16
 
@@ -87,6 +87,7 @@ SYMBOLS = {
                                   C.c_void_p]),
     'nnb_chain_autocorr': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, _dp, _dp, _dp, C.c_int,
                                      C.c_int, _dp, C.c_void_p]),
+    'nnb_ns_information': (C.c_double, [C.c_double, _dp, _dp, _dp, _dp, C.c_int64]),
     'nnb_write_chain_text': (C.c_int64, [C.c_char_p, C.c_char_p, _dp, C.c_int64, C.c_int, C.c_int]),
 }
 

@@ -99,10 +99,10 @@ class NSBook(object):
                 exhausted = False
         a_term = np.exp(logwt[:n_evid] - lz_new[:n_evid]) * lstar[:n_evid]
         b_term = np.exp(lz_prev[:n_evid] - lz_new[:n_evid])
-        h = self.h
-        for a, b, zp, zn in zip(a_term.tolist(), b_term.tolist(), lz_prev[:n_evid].tolist(), lz_new[:n_evid].tolist()):
-            h = (a + b * (h + zp)) - zn
-        self.h = h
+        # h <- (a + b * (h + logz_old)) - logz_new, one iteration after the other (exact host routine of the C ABI)
+        zp_c, zn_c = np.ascontiguousarray(lz_prev[:n_evid]), np.ascontiguousarray(lz_new[:n_evid])
+        self.h = lib.nnb_ns_information(float(self.h), dp(np.ascontiguousarray(a_term)), dp(np.ascontiguousarray(b_term)),
+                                        dp(zp_c), dp(zn_c), n_evid)
         self.logz = lz_new[n_evid - 1]
         # dead points: the physical point sitting in slot `worst` when its iteration started
         new_u = b_last[chain[:n_done]].astype(np.float64)

@@ -511,3 +511,20 @@ extern "C" int64_t nnb_write_chain_text(const char* path, const char* header, co
   if (fclose(f) != 0) ok = false;
   return ok ? written : (int64_t)NNB_ERR_ARG;
 }
+
+// Information recurrence of nested sampling (nnest/nested.py:283), sequential over the iterations of a run:
+//     h <- (a[i] + b[i] * (h + zp[i])) - zn[i]
+// with a = exp(logwt - logz_new) * L_worst, b = exp(logz_old - logz_new), zp = logz_old, zn = logz_new prepared by the
+// caller in float64.  Plain IEEE double arithmetic, one rounding per operation (no contraction), i.e. the reference's Python
+// expression evaluated left to right.
+extern "C" double nnb_ns_information(double h, const double* a, const double* b, const double* zp, const double* zn,
+                                     int64_t n) {
+  volatile double t;   // keeps every intermediate a rounded double (no fused multiply-add, no extended precision)
+  for (int64_t i = 0; i < n; ++i) {
+    t = h + zp[i];
+    t = b[i] * t;
+    t = a[i] + t;
+    h = t - zn[i];
+  }
+  return h;
+}

@@ -122,3 +122,23 @@ def test_bulk_respects_iteration_limit(lib):
     bk, bu, bv, bl = _bulk_run(u0, logl0, tr, batches, dlogz=1e-9, chunk=1000, max_iters=57)
     assert bk.it == st.it == 58 and bk.logz == st.logz and bk.h == st.h
     assert np.array_equal(bl, al) and np.array_equal(bu, au)
+
+
+def test_information_recurrence_is_bit_exact(lib):
+    """nnb_ns_information == the reference's Python expression (nested.py:283) evaluated iteration by iteration."""
+    import ctypes as C
+    rng = np.random.RandomState(0)
+    n = 20000
+    zn = np.sort(rng.normal(size=n) * 30) - 100
+    zp = np.concatenate(([-1e300], zn[:-1]))
+    lw = zn - np.abs(rng.normal(size=n))
+    lstar = rng.normal(size=n) * 50
+    a = np.exp(lw - zn) * lstar
+    b = np.exp(zp - zn)
+    h = 0.0
+    for i in range(n):
+        h = (a[i] + b[i] * (h + zp[i])) - zn[i]
+    dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+    got = lib.nnb_ns_information(0.0, dp(a), dp(b), dp(zp), dp(zn), n)
+    assert got == h
+    assert lib.nnb_ns_information(1.5, dp(a), dp(b), dp(zp), dp(zn), 0) == 1.5
