@@ -6,9 +6,9 @@
 //   * a tile of 128 chains = the M dimension of one tcgen05.mma is owned by NPART warpgroups (128 threads each);
 //     thread (part, t) works on chain t = TMEM lane t (warps w and w+4 address the same lane quarter), so
 //     activations never leave the chain's own threads: D row -> registers (tcgen05.ld) -> bias + tanh/relu ->
-//     hi/lo split -> A row of the next layer (tcgen05.st).  With NPART = 2 the two threads of a chain split the
-//     8-column chunks of every phase (noise, A operands, epilogues, state update) between them: at 65 536 chains a
-//     B200 has only ~14 warps per SM with one thread per chain, too few to hide the MMA round trips;
+//     hi/lo split -> A row of the next layer (tcgen05.st).  NPART = 1 (default): one thread per chain, 128 registers,
+//     the chain's current latent point resident in shared memory.  NPART = 2 (NNB_TC_NPART=2): the two threads of a
+//     chain split the 8-column chunks of every phase (noise, A operands, epilogues, state update) between them;
 //   * weights (B operands) are pre-split into tf32 hi/lo halves on the host and staged once per CTA in shared
 //     memory in the canonical K-major core-matrix layout (nnb_tc.cuh);
 //   * layer 1 of both nets shares its input, so it is ONE N=32 MMA group; the hidden and output layers are
@@ -85,10 +85,11 @@ struct TcTile {
 
 __device__ __forceinline__ void tile_sync(const TcTile& t) { tc::named_bar_sync(t.bar_id, t.bar_threads); }
 
-// Hand the freshly written A operands to the tensor core and wait for completion.  Issuing a tcgen05.mma costs
-// ~70 cycles of one lane (measured, csrc/dev/tc_latency.cu), so the MMAs of a round trip are split into two
-// independent groups (different D columns) issued concurrently by lane 0 of the tile's warps 0 and 1, each
-// committing to its own mbarrier.  Only those two warps poll; the other warps sleep on the hardware barrier.
+// Hand the freshly written A operands to the tensor core and wait for completion.  The MMAs of a round trip are split
+// into two independent groups (different D columns) issued concurrently by the elected lane of the tile's warps 0 and 1
+// (elect.sync: the operands stay in uniform registers, ~23 cycles per tcgen05.mma, csrc/dev/tc_latency.cu), each
+// committing to its own mbarrier.  Only those two warps poll; the other warps sleep on the hardware barrier (letting
+// every warp poll measured slower: the polling costs issue slots).
 template <typename F0, typename F1>
 __device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1) {
   tc::wait_st();
