@@ -235,6 +235,16 @@ class Trainer(object):
             self.total_iters += 1
             if fused:
                 train_loss, validation_loss = self._fused_epoch(flat, x_train, x_valid, training_jitter, l2_norm)
+                if not (math.isfinite(train_loss) and math.isfinite(validation_loss)):
+                    # A diverged step (inf / NaN loss) would poison the Adam moments for the rest of the run -- every later
+                    # retrain would return the old weights.  Go back to the best weights seen and restart the moments.
+                    # (The reference has no such guard; with it a rare divergence costs one epoch instead of the run.)
+                    self.logger.warning('Epoch [%i] non-finite loss: restoring the best weights, resetting Adam' % epoch)
+                    flat.copy_(best_state)
+                    self._adam_m.zero_()
+                    self._adam_v.zero_()
+                    self._adam_step = 0
+                    validation_loss = float('inf')
             else:
                 train_loss = self._train(epoch, x_train, jitter=training_jitter, l2_norm=l2_norm)
                 validation_loss = self._validate(epoch, x_valid)

@@ -232,3 +232,23 @@ def test_trainer_tiny_dataset_and_large_batch(tmp_path):
     assert np.isfinite(t.best_validation_loss)
     z, ld = t.forward(x.astype(np.float32))
     assert torch.isfinite(z).all() and torch.isfinite(ld).all()
+
+
+def test_trainer_recovers_from_a_diverged_epoch(tmp_path):
+    """A non-finite loss (here: provoked by a NaN in the training data of one call) must not poison later fits: the
+    best weights are restored and the Adam moments restarted."""
+    from nnest_b200 import Trainer
+    np.random.seed(2)
+    torch.manual_seed(2)
+    x = np.random.normal(size=(600, 3))
+    t = Trainer(3, flow='nvp', log_dir=str(tmp_path), log_level=logging.ERROR, batch_size=100)
+    t.train(x, max_iters=5, jitter=0.0)
+    good = t.best_validation_loss
+    bad = x.copy()
+    bad[5, 1] = np.nan
+    t.train(bad, max_iters=3, jitter=0.0)
+    assert float(t._adam_m.abs().max()) == 0.0 or torch.isfinite(t._adam_m).all()
+    z, ld = t.forward(x.astype(np.float32))
+    assert torch.isfinite(z).all() and torch.isfinite(ld).all()          # weights are still the last good ones
+    t.train(x, max_iters=5, jitter=0.0)
+    assert np.isfinite(t.best_validation_loss) and t.best_validation_loss <= good * 1.05 + 1e-3
