@@ -39,6 +39,8 @@ def probe_affine_transform(transform, d):
     out0 = np.asarray(transform(zero))
     promotes = out0.dtype == np.float64
     z64 = np.zeros((1, d))
+    if out0.shape != (1, d) or np.asarray(transform(z64)).shape != (1, d):
+        raise NotImplementedError('transform must map (n, x_dim) arrays to (n, x_dim) arrays (per-dimension affine map)')
     shift = np.asarray(transform(z64), dtype=np.float64).reshape(d)
     scale = np.asarray(transform(np.ones((1, d))), dtype=np.float64).reshape(d) - shift
     rng = np.random.RandomState(12345)
