@@ -86,7 +86,8 @@ class NestedSampler(Sampler):
         if not self.use_mpi:
             return batch, self.total_calls
         out = {key: dist.allgather_rows(batch[key]) for key in ('first', 'last', 'logl_last')}
-        out.update(scale=batch['scale'], ncall=batch['ncall'], trace_x=batch.get('trace_x'))
+        out.update(scale=batch['scale'], ncall=batch['ncall'], trace_x=batch.get('trace_x'),
+                   acceptance=batch.get('acceptance'))
         return out, dist.allreduce_sum_int(self.total_calls, self.device)
 
     def _bcast_array(self, a):
@@ -188,6 +189,7 @@ class NestedSampler(Sampler):
         active_logl = np.ascontiguousarray(active_logl, dtype=np.float64)
 
         lib = L.load()
+        self.refill_log = []
         first_time = True
         get_samples = True
         nb = 0
@@ -289,6 +291,11 @@ class NestedSampler(Sampler):
                     b_first = np.ascontiguousarray(batch['first'].cpu().numpy())
                     b_last = np.ascontiguousarray(batch['last'].cpu().numpy())
                     b_logl = np.ascontiguousarray(batch['logl_last'].cpu().numpy())
+                    # run diagnostics (not in the reference): one record per refill -- iteration, constraint, this rank's
+                    # acceptance, fraction of chains that moved in every coordinate and beat the constraint, final scale
+                    moved = np.all(b_first != b_last, axis=1) & (b_logl > loglstar)
+                    self.refill_log.append((it, float(loglstar), float(batch.get('acceptance', np.nan)),
+                                            float(moved.mean()), float(scale)))
 
                 c_nb = ctypes.c_int64(nb)                       # nested.py:429-439
                 fp = ctypes.POINTER(ctypes.c_float)
@@ -364,6 +371,15 @@ class NestedSampler(Sampler):
                 writer.writerow(['niter', 'ncall', 'logz', 'logzerr', 'h'])
                 writer.writerow([it + 1, total_calls, logz, np.sqrt(h / nlive), h])
             self._save_samples(self.samples, self.loglikes, weights=self.weights)
+            # run diagnostics next to the reference's result files (one row per MCMC refill / per flow fit)
+            with open(os.path.join(self.logs['results'], 'refill_log.csv'), 'w') as f:
+                writer = csv.writer(f)
+                writer.writerow(['iteration', 'loglstar', 'acceptance', 'usable_fraction', 'scale'])
+                writer.writerows(self.refill_log)
+            with open(os.path.join(self.logs['results'], 'fit_log.csv'), 'w') as f:
+                writer = csv.writer(f)
+                writer.writerow(['total_epochs', 'samples', 'jitter', 'best_epoch', 'best_validation_loss'])
+                writer.writerows(getattr(self.trainer, 'fit_log', []))
             self.logger.info("niter: {:d}\n ncall: {:d}\n nsamples: {:d}\n logz: {:6.3f} +/- {:6.3f}\n h: {:6.3f}"
                              .format(it + 1, int(total_calls), len(self.loglikes), logz, np.sqrt(h / nlive), h))
 

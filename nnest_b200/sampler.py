@@ -325,7 +325,7 @@ class Sampler(object):
         first = out['first_x'].t().contiguous()
         last = st.x.t().contiguous()
         return dict(first=first, last=last, logl_last=st.logl, scale=out['scale'], ncall=ncall,
-                    trace_x=out.get('trace_x'))
+                    trace_x=out.get('trace_x'), acceptance=out['naccept'] / float(max(1, st.n * mcmc_steps)))
 
     def _plot_trace(self, samples, latent_samples):
         pass    # plotting is outside the accelerated path

@@ -151,6 +151,7 @@ class Trainer(object):
         self.optimizer = torch.optim.Adam(self.netG.parameters(), lr=learning_rate, weight_decay=weight_decay,
                                           capturable=True)
         self._graphed = {}
+        self.fit_log = []
         # fused fitting kernel (nnb_train_epoch): flat parameter vector + Adam moments in state_dict order
         self._arch = (x_dim, hidden_dim, num_layers, num_blocks)
         self._fused = scale == '' and self.engine.train_supported(*self._arch) \
@@ -282,6 +283,9 @@ class Trainer(object):
                          % (best_validation_epoch, best_validation_loss, time.time() - start_time))
         self.best_validation_epoch = best_validation_epoch
         self.best_validation_loss = best_validation_loss
+        # run diagnostics (not in the reference): one record per fit
+        self.fit_log.append((self.total_iters, int(samples.shape[0]), float(training_jitter), int(best_validation_epoch),
+                             float(best_validation_loss)))
         _copy_into_params(params, best_state)
         self._sync_device()
 

@@ -223,3 +223,21 @@ def test_resume_from_checkpoint(tmp_path):
     assert np.all(np.diff(saved) >= 0)                       # dead points leave in order of increasing likelihood
     assert s2.samples.shape[0] == len(s2.loglikes) == len(s2.weights)
     assert abs(s2.weights.sum() - 1.0) < 1e-6
+
+
+def test_run_diagnostics_are_recorded(tmp_path):
+    """refill_log / fit_log (one record per MCMC refill / flow fit) and their CSV files in results/."""
+    from nnest_b200 import NestedSampler
+    from nnest_b200.likelihoods import Himmelblau
+    np.random.seed(5)
+    torch.manual_seed(5)
+    s = NestedSampler(2, Himmelblau(2), transform=lambda x: 5 * x, num_live_points=300, flow='nvp',
+                      log_dir=str(tmp_path), log_level=logging.WARNING)
+    s.run(mcmc_num_chains=200, train_iters=20, strategy=['mcmc'], max_iters=1500)
+    assert len(s.refill_log) >= 3 and len(s.trainer.fit_log) >= 2
+    it, lstar, acc, usable, scale = s.refill_log[-1]
+    assert 0.0 < acc < 1.0 and 0.0 < usable <= 1.0 and scale > 0
+    rows = list(csv.reader(open(os.path.join(s.logs['results'], 'refill_log.csv'))))
+    assert rows[0] == ['iteration', 'loglstar', 'acceptance', 'usable_fraction', 'scale'] and len(rows) == len(s.refill_log) + 1
+    rows = list(csv.reader(open(os.path.join(s.logs['results'], 'fit_log.csv'))))
+    assert len(rows) == len(s.trainer.fit_log) + 1
