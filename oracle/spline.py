@@ -184,3 +184,18 @@ def flow_inverse(w, z):
         z = ((z - blk['t']) * np.exp(-blk['s'])).astype(F32)
         ld = ld - blk['s'].sum()
     return z, ld.astype(F32)
+
+
+def pack_for_kernel(w, hidden):
+    """Flat float32 parameter vector in the layout of nnest_b200/csrc/nnb_spline.cuh (ActNorm s, t; assembled 1x1
+    convolution matrix, its inverse (computed in float64) and log-det; the two conditioner MLPs), block after block."""
+    parts = []
+    for blk in w.blocks:
+        Wc = w.conv_matrix(blk)
+        Wci = np.linalg.inv(Wc.astype(np.float64)).astype(F32)
+        parts += [blk['s'].ravel(), blk['t'].ravel(), Wc.ravel(), Wci.ravel(),
+                  np.array([np.log(np.abs(blk['S'])).sum()], dtype=F32)]
+        for f in ('f1', 'f2'):
+            for W, b in blk[f]:
+                parts += [W.ravel(), b.ravel()]
+    return np.concatenate([np.asarray(a, dtype=F32) for a in parts])

@@ -34,3 +34,35 @@ def test_identity_outside_the_tail_bound():
     y, ld = ospline._coupling(w, blk, x, False)
     assert y[0, 0] == x[0, 0] and y[0, 1] == x[0, 1] and ld[0] == 0.0      # both halves outside: untouched
     assert y[1, 1] == x[1, 1] and y[1, 0] != x[1, 0]
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_kernel_header_arithmetic_matches_reference(name):
+    """nnest_b200/csrc/nnb_spline.cuh (the __host__ __device__ per-sample code a CUDA kernel will wrap), compiled for the
+    CPU by oracle/build_spline_host.py, against the same goldens."""
+    import ctypes as C
+    from oracle import build_spline_host
+    lib = C.CDLL(build_spline_host.build())
+    g = load('spline_%s.npz' % name)
+    w = ospline.SplineWeights.from_golden(g)
+    d, hidden, blocks = int(g['d']), int(g['hidden']), int(g['blocks'])
+    packed = np.ascontiguousarray(ospline.pack_for_kernel(w, hidden))
+    assert packed.size == blocks * lib.spline_host_block_floats(d, hidden, w.K)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+
+    def run(inp, inverse):
+        inp = np.ascontiguousarray(inp, dtype=np.float32)
+        out, ld = np.empty_like(inp), np.empty(inp.shape[0], dtype=np.float32)
+        rc = lib.spline_host_flow(fp(packed), d, hidden, blocks, w.K, C.c_float(w.B), int(inverse), fp(inp), fp(out), fp(ld),
+                                  C.c_int64(inp.shape[0]))
+        assert rc == 0
+        return out, ld
+
+    z, ld = run(g['x'], False)
+    assert rel_err(z, g['fwd_z']) < 1e-5
+    assert np.abs(ld - g['fwd_ld']).max() < 2e-5 * max(1.0, np.abs(g['fwd_ld']).max())
+    x, ldx = run(g['zin'], True)
+    assert rel_err(x, g['inv_x']) < 1e-5
+    assert np.abs(ldx - g['inv_ld']).max() < 2e-5 * max(1.0, np.abs(g['inv_ld']).max())
+    xr, ldr = run(z, True)
+    assert np.abs(xr - g['x']).max() < 2e-5 and np.abs(ld + ldr).max() < 5e-5
