@@ -98,8 +98,12 @@ def _unconstrained_rqs(inputs, W, H, D, inverse, bound):
     ld = np.zeros_like(out)
     const = F32(np.log(np.exp(1 - MIN_DERIVATIVE) - 1))
     Dp = np.concatenate([np.full(D.shape[:-1] + (1,), const, F32), D, np.full(D.shape[:-1] + (1,), const, F32)], axis=-1)
-    if inside.any():
-        out[inside], ld[inside] = _rqs(inputs[inside], W[inside], H[inside], Dp[inside], inverse, bound)
+    if not inside.any():
+        # the reference calls RQS on the (empty) selection, which raises (networks.py:464-465); Sampler._mcmc_sample
+        # catches the ValueError and skips the proposal (sampler.py:320-324).  Only reachable when EVERY coordinate of
+        # EVERY sample of the batch lies outside the tail bound, i.e. in practice for one-sample batches
+        raise ValueError('No input values')
+    out[inside], ld[inside] = _rqs(inputs[inside], W[inside], H[inside], Dp[inside], inverse, bound)
     return out, ld
 
 

@@ -30,10 +30,14 @@ def test_identity_outside_the_tail_bound():
     g = load('spline_d2.npz')
     w = ospline.SplineWeights.from_golden(g)
     blk = w.blocks[0]
-    x = np.array([[3.5, -3.2], [0.3, 4.0]], dtype=np.float32)
+    x = np.array([[3.5, -3.2], [0.3, 4.0], [0.1, -0.4]], dtype=np.float32)
     y, ld = ospline._coupling(w, blk, x, False)
     assert y[0, 0] == x[0, 0] and y[0, 1] == x[0, 1] and ld[0] == 0.0      # both halves outside: untouched
     assert y[1, 1] == x[1, 1] and y[1, 0] != x[1, 0]
+    # a batch with NO coordinate inside the interval raises like the reference (RQS on an empty selection,
+    # networks.py:464-465); Sampler._mcmc_sample turns that into a skipped proposal (sampler.py:320-324)
+    with pytest.raises(ValueError):
+        ospline._coupling(w, blk, x[:1], False)
 
 
 @pytest.mark.parametrize('name', CASES)
