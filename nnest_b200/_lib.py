@@ -108,6 +108,14 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError('%s not found: build it with `python -m nnest_b200.build` '
                            '(the CUDA path is the only path; there is no CPU fallback)' % LIB_PATH)
+    try:      # a library older than the sources is used as is, but never silently
+        from . import build as _build
+        if os.path.isdir(_build.CSRC) and not _build.up_to_date():
+            import warnings
+            warnings.warn('libnnb.so does not match nnest_b200/csrc (content digests differ): rebuild with '
+                          '`python -m nnest_b200.build`', RuntimeWarning)
+    except Exception:
+        pass
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)      # AttributeError if the .so does not export a declared symbol

@@ -75,6 +75,7 @@ extern "C" void nnb_destroy(nnb_handle* h) {
   if (h->h_train_ctrl) cudaFreeHost(h->h_train_ctrl);
   if (h->d_train_ws) cudaFree(h->d_train_ws);
   if (h->d_stats_ws) cudaFree(h->d_stats_ws);
+  if (h->d_nn_part) cudaFree(h->d_nn_part);
   delete h;
 }
 

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "nnb_host.h"
 #include "nnb_train.cuh"
@@ -9,6 +10,16 @@
 using namespace nnb;
 
 namespace {
+
+// control block + per-CTA loss partials ([sm_count][2] doubles) in one allocation, mirrored in pinned host memory
+constexpr size_t kLossOff = 32;
+size_t train_ctrl_bytes(const nnb_handle* h) { return kLossOff + (size_t)2 * h->sm_count * sizeof(double); }
+
+int ensure_train_ctrl(nnb_handle* h) {
+  if (!h->d_train_ctrl) NNB_CUDA(h, cudaMalloc(&h->d_train_ctrl, train_ctrl_bytes(h)));
+  if (!h->h_train_ctrl) NNB_CUDA(h, cudaMallocHost(&h->h_train_ctrl, train_ctrl_bytes(h)));
+  return NNB_OK;
+}
 
 template <int H, int L>
 int launch_train(nnb_handle* h, TrainParams& p, int grid, size_t smem, cudaStream_t st) {
@@ -62,18 +73,17 @@ extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* str
   const int grid = (int)g;
   const int Psm = train_psm(d, H, L, B);
 
-  if (!h->d_train_ctrl) NNB_CUDA(h, cudaMalloc(&h->d_train_ctrl, sizeof(TrainCtrl)));
-  if (!h->h_train_ctrl) NNB_CUDA(h, cudaMallocHost(&h->h_train_ctrl, sizeof(TrainCtrl)));
-  NNB_CUDA(h, cudaMemsetAsync(h->d_train_ctrl, 0, sizeof(TrainCtrl), st));
+  { int rc0 = ensure_train_ctrl(h); if (rc0) return rc0; }
+  NNB_CUDA(h, cudaMemsetAsync(h->d_train_ctrl, 0, train_ctrl_bytes(h), st));
   if (grid > 1) {
-    const size_t need = (size_t)3 * Psm + (size_t)grid * 2 * P;
+    // [grid][Psm] partial gradients | [Psm] their fixed-order sum | [grid][2][P] private Adam moments
+    const size_t need = (size_t)(grid + 1) * Psm + (size_t)grid * 2 * P;
     if (h->train_ws_floats < need) {
       if (h->d_train_ws) cudaFree(h->d_train_ws);
       h->d_train_ws = nullptr;
       NNB_CUDA(h, cudaMalloc(&h->d_train_ws, need * sizeof(float)));
       h->train_ws_floats = need;
     }
-    NNB_CUDA(h, cudaMemsetAsync(h->d_train_ws, 0, (size_t)3 * Psm * sizeof(float), st));
   }
 
   TrainParams p{};
@@ -87,9 +97,11 @@ extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* str
   p.weight_decay = (float)a->weight_decay;
   p.step0 = a->step0;
   p.params = a->params; p.adam_m = a->adam_m; p.adam_v = a->adam_v;
-  p.gbuf = grid > 1 ? h->d_train_ws : nullptr;
-  p.mv_priv = grid > 1 ? h->d_train_ws + (size_t)3 * Psm : nullptr;
+  p.gpart = grid > 1 ? h->d_train_ws : nullptr;
+  p.gsum = grid > 1 ? h->d_train_ws + (size_t)grid * Psm : nullptr;
+  p.mv_priv = grid > 1 ? h->d_train_ws + (size_t)(grid + 1) * Psm : nullptr;
   p.ctrl = (TrainCtrl*)h->d_train_ctrl;
+  p.loss_part = reinterpret_cast<double*>(reinterpret_cast<char*>(h->d_train_ctrl) + kLossOff);
   p.grad_out = a->grad_out;
   p.do_train = a->do_train ? 1 : 0;
 
@@ -100,11 +112,14 @@ extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* str
   else if (H == 32 && L == 1) rc = launch_train<32, 1>(h, p, grid, smem, st);
   else rc = launch_train<32, 2>(h, p, grid, smem, st);
   if (rc) return rc;
-  NNB_CUDA(h, cudaMemcpyAsync(h->h_train_ctrl, h->d_train_ctrl, sizeof(TrainCtrl), cudaMemcpyDeviceToHost, st));
+  NNB_CUDA(h, cudaMemcpyAsync(h->h_train_ctrl, h->d_train_ctrl, train_ctrl_bytes(h), cudaMemcpyDeviceToHost, st));
   NNB_CUDA(h, cudaStreamSynchronize(st));
-  const TrainCtrl* c = (const TrainCtrl*)h->h_train_ctrl;
-  if (a->train_loss_sum_out) *a->train_loss_sum_out = c->train_loss;
-  if (a->val_nll_sum_out) *a->val_nll_sum_out = c->val_loss;
+  // losses: per-CTA partials added in CTA order (deterministic, unlike floating-point atomics)
+  const double* lp = reinterpret_cast<const double*>(reinterpret_cast<const char*>(h->h_train_ctrl) + kLossOff);
+  double tl = 0.0, vl = 0.0;
+  for (int c = 0; c < grid; ++c) { tl += lp[2 * c]; vl += lp[2 * c + 1]; }
+  if (a->train_loss_sum_out) *a->train_loss_sum_out = tl;
+  if (a->val_nll_sum_out) *a->val_nll_sum_out = vl;
   if (a->grid_out) *a->grid_out = grid;
   return NNB_OK;
 }
@@ -115,11 +130,14 @@ extern "C" int nnb_mean_nn_distance(nnb_handle* h, const double* x, int64_t n, i
   NNB_CUDA(h, cudaSetDevice(h->device));
   *out = 0.0;
   if (n < 2) return NNB_OK;
-  if (!h->d_train_ctrl) NNB_CUDA(h, cudaMalloc(&h->d_train_ctrl, sizeof(TrainCtrl)));
-  if (!h->h_train_ctrl) NNB_CUDA(h, cudaMallocHost(&h->h_train_ctrl, sizeof(TrainCtrl)));
-  NNB_CUDA(h, cudaMemsetAsync(h->d_train_ctrl, 0, sizeof(TrainCtrl), st));
   const int grid = (int)((n + 127) / 128);
-  double* acc = &((TrainCtrl*)h->d_train_ctrl)->train_loss;
+  if (h->nn_part_cap < grid) {
+    if (h->d_nn_part) cudaFree(h->d_nn_part);
+    h->d_nn_part = nullptr;
+    NNB_CUDA(h, cudaMalloc(&h->d_nn_part, sizeof(double) * grid));
+    h->nn_part_cap = grid;
+  }
+  double* acc = h->d_nn_part;
   if (d <= 16) {
     nn_min_dist_kernel<16><<<grid, 128, 128 * 16 * sizeof(double), st>>>(x, n, d, acc);
   } else if (d <= 32) {
@@ -130,8 +148,11 @@ extern "C" int nnb_mean_nn_distance(nnb_handle* h, const double* x, int64_t n, i
     nn_min_dist_kernel<0><<<grid, 128, smem, st>>>(x, n, d, acc);
   }
   NNB_CUDA(h, cudaGetLastError());
-  NNB_CUDA(h, cudaMemcpyAsync(h->h_train_ctrl, h->d_train_ctrl, sizeof(TrainCtrl), cudaMemcpyDeviceToHost, st));
+  std::vector<double> part((size_t)grid);
+  NNB_CUDA(h, cudaMemcpyAsync(part.data(), acc, sizeof(double) * grid, cudaMemcpyDeviceToHost, st));
   NNB_CUDA(h, cudaStreamSynchronize(st));
-  *out = ((const TrainCtrl*)h->h_train_ctrl)->train_loss / (double)n;
+  double sum = 0.0;
+  for (int b = 0; b < grid; ++b) sum += part[(size_t)b];   // block order: deterministic
+  *out = sum / (double)n;
   return NNB_OK;
 }

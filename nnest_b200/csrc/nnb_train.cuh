@@ -16,9 +16,12 @@
 //     sample's `in` / `dpre` vectors as columns of two shared-memory matrices ([feature][sample], rows 16-byte
 //     aligned), then each (o, i) pair is owned by one thread, which runs down the sample axis with float4 loads.
 //     No atomics inside a CTA.
-//   * several CTAs per mini-batch: partial gradients are added into a global buffer (red.global.add.f32), a grid
-//     barrier (cooperative launch) follows, and every CTA applies the identical Adam update to its own
-//     shared-memory copy of the weights (optimizer moments: one private global copy per CTA, L2 resident).
+//   * several CTAs per mini-batch (cooperative launch): every CTA stores its partial gradient in its own global slot;
+//     after a grid barrier CTA c sums slice c of all slots IN CTA ORDER (a fixed-order reduce-scatter: the result does
+//     not depend on which CTA arrives first, so a seed reproduces bit for bit), a second grid barrier publishes the
+//     summed slices, and every CTA applies the identical Adam update to its own shared-memory copy of the weights
+//     (optimizer moments: one private global copy per CTA, L2 resident).  Losses are summed the same way: per-CTA
+//     partials in a fixed warp order, added up by the host in CTA order.
 // Parameter layout: the caller's flat vector is netG.state_dict() order ("natural", as nnb_set_flow); in shared
 // memory each net starts at a multiple of 4 floats and the first layer is stored transposed (W1T[i][j]) so that
 // every inner loop reads float4 rows.  Adam is element-wise, so only the copy in / copy out permutes.
@@ -33,8 +36,8 @@ constexpr int kStageStride = 132;   // floats per staged row: 128 samples + 4 (r
 enum { kTagTrain = 3 };
 
 struct TrainCtrl {
-  double train_loss;     // sum over mini-batches of mean(-log p)          (trainer.py:396)
-  double val_loss;       // sum over validation samples of -log p          (trainer.py:414)
+  double train_loss;     // (nnb_mean_nn_distance accumulator)
+  double val_loss;
   unsigned int ticket;   // grid-barrier arrivals (monotonic)
   unsigned int pad;
 };
@@ -56,7 +59,10 @@ struct TrainParams {
   float* adam_m;                // [P] in / out
   float* adam_v;                // [P] in / out
   float* mv_priv;               // [grid][2][P] workspace when grid > 1
-  float* gbuf;                  // [3][Psm] workspace when grid > 1 (zeroed by the host)
+  float* gpart;                 // [grid][Psm] workspace when grid > 1: every CTA's partial gradient of the mini-batch
+  float* gsum;                  // [Psm] workspace when grid > 1: the partials summed in CTA order
+  double* loss_part;            // [grid][2]: per-CTA sums of the mini-batch mean losses (trainer.py:396) and of the
+                                // validation -log p (trainer.py:414), zeroed by the host
   TrainCtrl* ctrl;
   float* grad_out;              // optional [P]: data gradient of the LAST mini-batch (natural layout)
   int do_train;
@@ -226,6 +232,8 @@ __global__ void __launch_bounds__(kTrainCta, 1) train_epoch_kernel(TrainParams p
   float* At = As + IM * kStageStride;
   float* Ds = At + IM * kStageStride;
   float* Dt = Ds + OM * kStageStride;
+  double* red_d = reinterpret_cast<double*>(Dt + OM * kStageStride);   // 8 doubles behind the staging matrices
+  float* red_s = reinterpret_cast<float*>(red_d);
   const int tid = threadIdx.x;
   // warps 0-3 own one sample each ("workers"); warps 4-7 only join the CTA-wide phases (weight-gradient contractions,
   // Adam, copies), which are latency bound with four warps
@@ -406,20 +414,32 @@ __global__ void __launch_bounds__(kTrainCta, 1) train_epoch_kernel(TrainParams p
       float v = loss_t;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((tid & 31) == 0 && v != 0.f) atomicAdd(&p.ctrl->train_loss, (double)v);
+      if ((tid & 31) == 0) red_s[tid >> 5] = v;
+      __syncthreads();
+      if (tid == 0) {   // fixed warp order; the slot belongs to this CTA alone
+        double t = 0.0;
+        for (int w = 0; w < kTrainThreads / 32; ++w) t += (double)red_s[w];
+        p.loss_part[2 * blockIdx.x] += t;
+      }
     }
     __syncthreads();
     // ---- several CTAs per mini-batch: sum the partial gradients through global memory --------------------------------
     if (multi) {
-      float* gb = p.gbuf + (size_t)(mb % 3) * Psm;
-      for (int q = tid; q < Psm; q += kTrainCta)
-        if (G[q] != 0.f) atomicAdd(gb + q, G[q]);
+      float* gp = p.gpart + (size_t)blockIdx.x * Psm;
+      for (int q = tid; q < Psm; q += kTrainCta) gp[q] = G[q];
       train_grid_barrier(p.ctrl, phase);
-      for (int q = tid; q < Psm; q += kTrainCta) G[q] = __ldcg(gb + q);
-      // the buffer of mini-batch mb + 2 was last read during mb - 1: every CTA is past that point
-      float* gz = p.gbuf + (size_t)((mb + 2) % 3) * Psm;
+      // fixed-order reduce-scatter: this CTA owns one slice of the parameters and adds the partials in CTA order
       const int chunk = (Psm + gridDim.x - 1) / gridDim.x;
-      for (int q = blockIdx.x * chunk + tid; q < Psm && q < (int)(blockIdx.x + 1) * chunk; q += kTrainCta) gz[q] = 0.f;
+      const int q_hi = min(Psm, (int)(blockIdx.x + 1) * chunk);
+      for (int q = blockIdx.x * chunk + tid; q < q_hi; q += kTrainCta) {
+        float acc = 0.f;
+#pragma unroll 8
+        for (unsigned int c = 0; c < gridDim.x; ++c) acc += __ldcg(p.gpart + (size_t)c * Psm + q);
+        p.gsum[q] = acc;
+      }
+      // the slots are rewritten only after the next mini-batch's compute, i.e. after every CTA has passed this barrier
+      train_grid_barrier(p.ctrl, phase);
+      for (int q = tid; q < Psm; q += kTrainCta) G[q] = __ldcg(p.gsum + q);
       __syncthreads();
     }
     if (p.grad_out && mb == nmb - 1 && blockIdx.x == 0)
@@ -482,7 +502,14 @@ __global__ void __launch_bounds__(kTrainCta, 1) train_epoch_kernel(TrainParams p
     double v = (double)loss_t;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((tid & 31) == 0 && p.n_valid > 0) atomicAdd(&p.ctrl->val_loss, v);
+    __syncthreads();
+    if ((tid & 31) == 0) red_d[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0 && p.n_valid > 0) {
+      double t = 0.0;
+      for (int w = 0; w < kTrainThreads / 32; ++w) t += red_d[w];
+      p.loss_part[2 * blockIdx.x + 1] = t;
+    }
   }
   // ---- publish ----------------------------------------------------------------------------------------------------------------
   if (blockIdx.x == 0 && p.do_train) {
@@ -555,10 +582,14 @@ __global__ void __launch_bounds__(128, 2) nn_min_dist_kernel(const double* __res
       }
     }
   }
+  // per-block partial in a fixed order (the host adds the blocks in order): the jitter of a seeded run is reproducible
   double v = valid && n > 1 ? sqrt(best) : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((tid & 31) == 0) atomicAdd(sum_out, v);
+  __shared__ double wsum[4];
+  if ((tid & 31) == 0) wsum[tid >> 5] = v;
+  __syncthreads();
+  if (tid == 0) sum_out[blockIdx.x] = ((wsum[0] + wsum[1]) + wsum[2]) + wsum[3];
 }
 
 }  // namespace nnb

@@ -1,8 +1,10 @@
 """One-process-per-GPU plumbing (torch.distributed; NCCL over NVLink on the GPU box, gloo in CPU tests).
 
 Replaces the reference's mpi4py pickle collectives (nnest/sampler.py:165-177; nnest/nested.py:199-226,416-427):
-  * chains are sharded by rank -- rank r owns global chain ids [r*n, (r+1)*n), which key the Philox streams, so a
-    chain's trajectory does not depend on how many GPUs the batch is split over;
+  * chains are sharded by rank -- rank r owns global chain ids [r*n, (r+1)*n), which key the Philox streams, so with a
+    FIXED step size a chain's trajectory does not depend on how many GPUs the batch is split over (with
+    mcmc_dynamic_step_size=True the scale adapts on each rank's own accept counts, as under the reference's MPI mode,
+    so trajectories then depend on the split);
   * after a refill only the end states (start point, end point, end loglike: all that nested.py:432-437 reads)
     are all-gathered, in rank order = the reference's np.concatenate order;
   * flow weights are broadcast from rank 0 as one flat buffer after every (re)training.
@@ -35,6 +37,30 @@ def allgather_rows(t):
     parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
     dist.all_gather(parts, t)
     return torch.cat(parts, dim=0)
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous share [lo, hi) of n items for `rank`: the first n % world ranks get one extra."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def allgather_ragged(a, n_total, device):
+    """Rank-order concatenation of 1-D float64 numpy shares cut with shard_bounds (lengths differ by at most one)."""
+    if not is_distributed():
+        return a
+    world = dist.get_world_size()
+    width = (int(n_total) + world - 1) // world
+    buf = torch.zeros((width,), dtype=torch.float64, device=device)
+    buf[:len(a)] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    out = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, r, world)
+        out.append(parts[r][:hi - lo].cpu().numpy())
+    return np.concatenate(out)
 
 
 def broadcast_array(a, device, src=0):

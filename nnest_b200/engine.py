@@ -30,6 +30,12 @@ def flatten_state_dict(sd, scale=''):
     Key layout: flow.flows.<i>.{scale_net,translate_net}.<2j>.{weight,bias} (+ flow.flows.<i>.scale for
     ScaleLayer), reference nnest/networks.py:262-282,312-347."""
     get = lambda k: np.asarray(sd[k].detach().cpu().numpy() if hasattr(sd[k], 'detach') else sd[k], dtype=np.float32)
+    if scale is None:
+        # infer the `scale` kwarg of SingleSpeedNVP from the keys: no scale_net -> translate only; ScaleLayer parameters
+        # (flow.flows.<odd>.scale) -> 'constant'
+        has_s = any('.scale_net.' in k for k in sd)
+        has_c = any(k.startswith('flow.flows.') and k.endswith('.scale') for k in sd)
+        scale = '' if has_s else ('constant' if has_c else 'translate')
     translate_only = scale in ('translate', 'constant')
     stride = 2 if scale == 'constant' else 1
     idx = sorted({int(k.split('.')[2]) for k in sd if k.startswith('flow.flows.')})

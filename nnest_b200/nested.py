@@ -116,8 +116,8 @@ class NestedSampler(Sampler):
         if strategy is None or len(strategy) == 0:
             strategy = ['rejection_prior', 'mcmc']
         for method in strategy:
-            if method not in ('rejection_prior', 'mcmc'):
-                raise NotImplementedError("strategy %r is not implemented on the accelerated path" % method)
+            if method not in ('rejection_prior', 'rejection_flow', 'density_flow', 'mcmc'):
+                raise ValueError("unknown sampling strategy %r" % method)
         expired_strategies = []
         current_method = ''
 
@@ -168,18 +168,28 @@ class NestedSampler(Sampler):
             active_v = self.transform(active_u)
             active_logl = np.load(os.path.join(ckpt, 'active_logl_%s.npy' % it))
             active_derived = np.load(os.path.join(ckpt, 'active_derived_%s.npy' % it))
-            bk.saved_v = [np.load(os.path.join(ckpt, 'saved_v.npy')).reshape(it, -1)]
-            bk.saved_logl = [np.load(os.path.join(ckpt, 'saved_logl.npy'))]
-            bk.saved_logwt = [np.load(os.path.join(ckpt, 'saved_logwt.npy'))]
+            if it > 0:     # checkpoint_0 holds empty arrays (the reference loads them as empty lists, nested.py:193-195)
+                bk.saved_v = [np.load(os.path.join(ckpt, 'saved_v.npy')).reshape(it, self.x_dim)]
+                bk.saved_logl = [np.load(os.path.join(ckpt, 'saved_logl.npy'))]
+                bk.saved_logwt = [np.load(os.path.join(ckpt, 'saved_logwt.npy'))]
             assert it == bk.num_dead()
             total_calls = data['ncall']
         else:
             active_u = self.sample_prior(nlive) if primary else np.empty((nlive, self.x_dim), dtype=np.float64)
             active_u = self._bcast_array(active_u)
             active_v = self.transform(active_u)
-            # float64 live points -> float64 likelihood (nested.py:228 with priors.py:46)
-            active_logl, active_derived = self.loglike(active_u)
-            total_calls = self.total_calls
+            # float64 live points -> float64 likelihood (nested.py:228 with priors.py:46).  Multi-GPU: every rank evaluates
+            # its contiguous share and the values are all-gathered in rank order (the reference scatters / gathers,
+            # nested.py:212-226), so the call counter sums to nlive over the ranks.
+            if self.use_mpi:
+                lo, hi = dist.shard_bounds(nlive, self.mpi_rank, self.mpi_size)
+                part, _ = self.loglike(active_u[lo:hi])
+                active_logl = dist.allgather_ragged(np.asarray(part, dtype=np.float64), nlive, self.device)
+                active_derived = np.empty((nlive, 0))
+                total_calls = dist.allreduce_sum_int(self.total_calls, self.device)
+            else:
+                active_logl, active_derived = self.loglike(active_u)
+                total_calls = self.total_calls
             if primary:
                 self.logger.info('Step [0] max logl [%5.4e] vol [1.0] ncalls [%d]' % (np.max(active_logl), total_calls))
                 self._write_checkpoint(bk, active_u, active_v, active_logl, active_derived, total_calls, strategy,
@@ -244,25 +254,50 @@ class NestedSampler(Sampler):
             if current_method != old_method:
                 get_samples = True
 
-            if not current_method == 'rejection_prior' and (first_time or it % update_interval == 0):
+            if not current_method == 'rejection_prior' and (first_time or it % update_interval == 0):   # nested.py:311
                 self.trainer.train(active_u, max_iters=train_iters, jitter=jitter)     # nested.py:311-314
                 first_time = False
 
-            if current_method == 'rejection_prior':
+            if current_method in ('rejection_prior', 'rejection_flow', 'density_flow'):
 
-                if get_samples:
+                if get_samples:                                 # nested.py:316-377
                     nb = 0
-                    samples, loglikes, _, nc = self._rejection_prior_sample(loglstar, num_trials=rejection_trials)
+                    if current_method == 'rejection_prior':
+                        samples, loglikes, _, nc = self._rejection_prior_sample(loglstar, num_trials=rejection_trials)
+                        label = 'Rejection prior'
+                    elif current_method == 'rejection_flow':
+                        samples, loglikes, _, nc = self._rejection_flow_sample(
+                            active_u, loglstar, enlargement_factor=rejection_enlargement_factor,
+                            cache=it % rejection_cache_interval == 0 or it % update_interval == 0)
+                        label = 'Rejection flow'
+                    else:
+                        samples, loglikes, _, nc = self._density_sample(loglstar)
+                        label = 'Density flow'
                     ncs.append(nc)
                     mean_calls = np.mean(ncs[-20:]) if len(ncs) > 20 else 0
-                    if expected_vol < volume_switch >= 0 or \
-                            (volume_switch < 0 and mean_calls > mcmc_steps and 'mcmc' in strategy
-                             and 'mcmc' not in expired_strategies):
-                        self.logger.info('Rejection prior no longer efficient, switching sampling method')
-                        expired_strategies.append('rejection_prior')
+                    can_switch = 'mcmc' in strategy and 'mcmc' not in expired_strategies
+                    expire = False
+                    if current_method == 'rejection_prior':
+                        expire = expected_vol < volume_switch >= 0 or \
+                            (volume_switch < 0 and mean_calls > mcmc_steps and can_switch)
+                    else:
+                        expire = mean_calls > mcmc_steps and can_switch
+                    if self.use_mpi:
+                        # nested.py:295-298,366-377: every rank contributes its draw(s), all ranks consume the rank-ordered
+                        # concatenation; a strategy expired on any rank is expired on all of them (every rank reaches
+                        # this point in the same iteration, so the union is taken where the flag can change)
+                        samples = dist.allgather_rows(torch.from_numpy(np.ascontiguousarray(
+                            samples, dtype=np.float64)).to(self.device)).cpu().numpy()
+                        loglikes = dist.allgather_rows(torch.from_numpy(np.ascontiguousarray(
+                            loglikes, dtype=np.float64)).to(self.device)).cpu().numpy()
+                        expire = bool(dist.allreduce_sum_int(int(expire), self.device))
+                        total_calls = dist.allreduce_sum_int(self.total_calls, self.device)
+                    if expire:
+                        self.logger.info('%s no longer efficient, switching sampling method' % label)
+                        expired_strategies.append(current_method)
                         ncs = []
 
-                for ib in range(nb, samples.shape[0]):          # nested.py:375-385
+                for ib in range(nb, samples.shape[0]):          # nested.py:379-389
                     nb += 1
                     get_samples = nb == samples.shape[0]
                     if loglikes[ib] > loglstar:
@@ -272,7 +307,8 @@ class NestedSampler(Sampler):
                         accept_point = True
                         break
 
-                total_calls = self.total_calls
+                if not self.use_mpi:
+                    total_calls = self.total_calls
                 if accept_point and it > 0 and (it + 1) % log_interval == 0 and primary:
                     self.logger.info(
                         'Step [%d] loglstar [%5.4e] max logl [%5.4e] logz [%5.4e] vol [%6.5e] ncalls [%d] mean '

@@ -140,7 +140,16 @@ class Sampler(object):
                 log_level=log_level)
         else:
             self.trainer = trainer
-        self.engine = self.trainer.engine
+        # b1: an injected trainer only has to honour the reference's contract (netG + forward / inverse / train,
+        # nnest/sampler.py:196-212).  A nnest_b200.Trainer brings its own Engine; for any other object (e.g. the
+        # reference's own Trainer) the kernels get their own Engine and the weights of trainer.netG.state_dict() are
+        # re-exported to it before every batch of chains (_sync_foreign_trainer).
+        self.engine = getattr(self.trainer, 'engine', None)
+        self._foreign_trainer = self.engine is None
+        if self._foreign_trainer:
+            from .engine import Engine
+            self.engine = Engine()
+            self._sync_foreign_trainer()
         self.device = self.engine.device
 
         if self.single_or_primary_process:
@@ -236,6 +245,12 @@ class Sampler(object):
         with open(os.path.join(self.logs['info'], 'params.txt'), 'w') as f:
             json.dump(my_dict, f, indent=4)
 
+    def _sync_foreign_trainer(self):
+        """Weights of an injected trainer that is not a nnest_b200.Trainer: netG.state_dict() in the reference's key
+        layout (nnest/networks.py:262-282,328-347) -> nnb_set_flow.  Cheap (<= 47 KB) and done before every batch
+        because such a trainer's train() cannot tell the kernels that the weights changed."""
+        self.engine.set_flow_from_state_dict(self.trainer.netG.state_dict(), scale=None)
+
     # ---- the hot path -----------------------------------------------------------------------------
     def _start_chains(self, num_chains, init_samples, init_loglikes, max_start_tries):
         """Chain start (nnest/sampler.py:262-284) on the device.  Returns (ChainState, ncall)."""
@@ -264,6 +279,8 @@ class Sampler(object):
         """Runs the fused kernels; returns (state, result dict, ncall)."""
         if step_size <= 0.0:
             step_size = 2 / self.x_dim ** 0.5
+        if self._foreign_trainer:
+            self._sync_foreign_trainer()
         st, ncall = self._start_chains(num_chains, init_samples, init_loglikes, max_start_tries)
         self.total_calls += ncall
         mode = L.NNB_MODE_MH if loglstar is None else L.NNB_MODE_HARD
@@ -383,18 +400,111 @@ class Sampler(object):
                 write(os.path.join(self.logs['chains'], outfile + '_%s.txt' % (ib + 1)), samples[ib], loglikes[ib],
                       weights[ib], None if derived_samples is None else derived_samples[ib])
 
-    # ---- rejection samplers used before the switch to MCMC (nnest/sampler.py:529-543) -------------------
+    # ---- rejection samplers used before / instead of MCMC (nnest/sampler.py:529-630), batched on the device -----------
+    # The reference draws ONE candidate per loop turn.  Here a block of k candidates goes through the kernels in one
+    # launch and the first acceptable one (in draw order) is returned -- the sequential algorithm exactly, since the
+    # candidates are independent; the ones drawn after it are discarded and only the loop turns the reference would have
+    # made are counted (ncall, total_calls).
+    def _loglike_rows(self, x):
+        """likelihood of host rows WITHOUT touching the call counter (the batched samplers count what they consume)"""
+        x, xd = self._to_device_rows(x)
+        logl = self.engine.loglike(xd).cpu().numpy()
+        if self._like.follows_input_dtype and x.dtype == np.float32 and not self._t_f64:
+            logl = logl.astype(np.float32)
+        return logl
+
     def _rejection_prior_sample(self, loglstar, num_trials=None):
+        """nnest/sampler.py:529-543.  num_trials=None: k prior draws per launch; np.random is then rewound and advanced
+        by exactly the draws the one-at-a-time loop would have consumed, so a seeded run sees the same stream."""
+        derived = np.empty((1, 0))
         if num_trials is None:
             ncall = 0
+            k = int(min(max(8, 2 * getattr(self, '_rej_prior_mean', 4)), 1 << 16))
+            rewindable = isinstance(self._prior_obj, UniformPrior) and self.sample_prior == self._prior_obj.sample
             while True:
-                x = self.sample_prior(1)
-                logl, derived = self.loglike(x)
-                ncall += 1
-                if logl > loglstar:
-                    break
-        else:
-            x = self.sample_prior(num_trials)
-            logl, derived = self.loglike(x)
-            ncall = num_trials / np.sum(logl > loglstar)
+                state = np.random.get_state() if rewindable else None
+                x = self.sample_prior(k if rewindable else 1)
+                logl = self._loglike_rows(x)
+                ok = np.nonzero(logl > loglstar)[0]
+                if len(ok):
+                    j = int(ok[0])
+                    if rewindable and j + 1 < k:
+                        np.random.set_state(state)
+                        self.sample_prior(j + 1)
+                    ncall += j + 1
+                    self.total_calls += j + 1
+                    self._rej_prior_mean = 0.8 * getattr(self, '_rej_prior_mean', 4) + 0.2 * ncall
+                    return x[j:j + 1], logl[j:j + 1], derived, ncall
+                ncall += x.shape[0]
+                self.total_calls += x.shape[0]
+                k = min(2 * k, 1 << 16)
+        x = self.sample_prior(num_trials)
+        logl, derived = self.loglike(x)
+        ncall = num_trials / np.sum(logl > loglstar)
         return x, logl, derived, ncall
+
+    def _rejection_flow_sample(self, init_samples, loglstar, enlargement_factor=1.1, constant_efficiency_factor=None,
+                               cache=False):
+        """nnest/sampler.py:545-607: uniform draws in the latent ball of radius enlargement * max |z(live)|, mapped
+        through the flow, thinned by the Jacobian envelope exp(log|J| - max log|J|) and by the likelihood constraint."""
+        def get_cache():
+            z, log_det_J = self.trainer.forward(np.asarray(init_samples, dtype=np.float32))
+            self.max_log_det_J = float(enlargement_factor * torch.max(-log_det_J))
+            self.max_r = float(torch.linalg.norm(z, dim=1).max())
+
+        if not cache or not hasattr(self, 'max_log_det_J'):
+            get_cache()
+        if constant_efficiency_factor is not None:
+            enlargement_factor = (1 / constant_efficiency_factor) ** (1 / self.x_dim)
+        d, ncall = self.x_dim, 0
+        k = int(min(max(64, 4 * getattr(self, '_rej_flow_mean', 16)), 1 << 16))
+        while True:
+            g = torch.randn((k, d), device=self.device)
+            r = torch.rand((k, 1), device=self.device) ** (1. / d)
+            z = enlargement_factor * self.max_r * g * r / torch.linalg.norm(g, dim=1, keepdim=True)
+            x, log_det_J = self.trainer.inverse(z)
+            logl, logp = self.engine.loglike(x, want_prior=True)
+            rnd_u = torch.rand((k,), device=self.device)
+            ratio = (log_det_J.double() - self.max_log_det_J).exp().clamp(max=1)
+            inside = logp > -1e30
+            evaluated = inside & ~(rnd_u > ratio)                    # the turns that reach self.loglike
+            good = evaluated & ~(torch.isfinite(logl) & (logl < loglstar)) & (rnd_u < ratio)
+            idx = torch.nonzero(good)
+            if idx.numel():
+                j = int(idx[0])
+                n_eval = int(evaluated[:j + 1].sum())
+                ncall += n_eval
+                self.total_calls += n_eval
+                self._rej_flow_mean = 0.8 * getattr(self, '_rej_flow_mean', 16) + 0.2 * (j + 1)
+                lj = logl[j:j + 1].cpu().numpy()
+                if self._like.follows_input_dtype and not self._t_f64:
+                    lj = lj.astype(np.float32)
+                return x[j:j + 1].cpu().numpy(), lj, np.empty((1, 0)), ncall
+            n_eval = int(evaluated.sum())
+            ncall += n_eval
+            self.total_calls += n_eval
+            k = min(2 * k, 1 << 16)
+
+    def _density_sample(self, loglstar):
+        """nnest/sampler.py:609-630: draws from the flow's own density until one beats the constraint."""
+        ncall = 0
+        k = int(min(max(64, 4 * getattr(self, '_dens_mean', 16)), 1 << 16))
+        while True:
+            x = self.trainer.get_samples(self.trainer.get_prior_samples(k))
+            logl, logp = self.engine.loglike(x, want_prior=True)
+            inside = logp > -1e30
+            idx = torch.nonzero(inside & (logl > loglstar))
+            if idx.numel():
+                j = int(idx[0])
+                n_eval = int(inside[:j + 1].sum())
+                ncall += n_eval
+                self.total_calls += n_eval
+                self._dens_mean = 0.8 * getattr(self, '_dens_mean', 16) + 0.2 * (j + 1)
+                lj = logl[j:j + 1].cpu().numpy()
+                if self._like.follows_input_dtype and not self._t_f64:
+                    lj = lj.astype(np.float32)
+                return x[j:j + 1].cpu().numpy(), lj, np.empty((1, 0)), ncall
+            n_eval = int(inside.sum())
+            ncall += n_eval
+            self.total_calls += n_eval
+            k = min(2 * k, 1 << 16)

@@ -241,3 +241,130 @@ def test_run_diagnostics_are_recorded(tmp_path):
     assert rows[0] == ['iteration', 'loglstar', 'acceptance', 'usable_fraction', 'scale'] and len(rows) == len(s.refill_log) + 1
     rows = list(csv.reader(open(os.path.join(s.logs['results'], 'fit_log.csv'))))
     assert len(rows) == len(s.trainer.fit_log) + 1
+
+
+def test_trainer_injection_b1(tmp_path):
+    """Sampler(trainer=obj).  (i) a separately built nnest_b200.Trainer; (ii) a foreign object that only
+    honours the reference's contract (netG with the reference's state_dict keys + forward / inverse / train) -- it has
+    no `.engine`; the sampler exports netG's weights to its own kernels before every batch."""
+    from nnest_b200 import NestedSampler, Trainer
+    from nnest_b200.likelihoods import Rosenbrock
+    from nnest_b200.networks import SingleSpeedNVP
+    g = load('flow_d2.npz')
+    sd = {k: torch.from_numpy(v) for k, v in state_dict_of(g).items()}
+    # (i)
+    tr = Trainer(2, flow='nvp', log_dir=str(tmp_path / 't'), log_level=logging.WARNING)
+    tr.load_state_dict(sd)
+    s = NestedSampler(2, Rosenbrock(2), transform=lambda x: 5 * x, flow='nvp', num_live_points=50,
+                      log_dir=str(tmp_path / 'a'), log_level=logging.WARNING, trainer=tr)
+    assert s.trainer is tr and s.engine is tr.engine
+    u = s.sample_prior(32)
+    logl, _ = s.loglike(u)
+    a = s._mcmc_sample(5, init_samples=u, init_loglikes=logl, loglstar=float(np.median(logl)), step_size=0.3)
+
+    # (ii) duck-typed trainer on the CPU, no engine attribute
+    class Foreign(object):
+        def __init__(self):
+            self.netG = SingleSpeedNVP(2, 16, 3, 1)          # CPU module, reference key names
+            self.netG.load_state_dict(sd)
+            self.device = torch.device('cpu')
+            self.writer = None
+            self.trained = 0
+
+        def forward(self, x, to_numpy=False):
+            z, ld = self.netG.forward(torch.as_tensor(np.asarray(x), dtype=torch.float32))
+            return (z.detach().numpy(), ld.detach().numpy()) if to_numpy else (z.detach(), ld.detach())
+
+        def inverse(self, z, to_numpy=False):
+            x, ld = self.netG.inverse(torch.as_tensor(np.asarray(z), dtype=torch.float32))
+            return (x.detach().numpy(), ld.detach().numpy()) if to_numpy else (x.detach(), ld.detach())
+
+        def train(self, samples, max_iters=0, jitter=0.0, **kw):
+            self.trained += 1
+            with torch.no_grad():                              # "training" changes the weights behind the sampler's back
+                for p in self.netG.parameters():
+                    p.mul_(0.5)
+
+    f = Foreign()
+    s2 = NestedSampler(2, Rosenbrock(2), transform=lambda x: 5 * x, flow='nvp', num_live_points=50,
+                       log_dir=str(tmp_path / 'b'), log_level=logging.WARNING, trainer=f, seed=0)
+    assert s2.trainer is f and not hasattr(f, 'engine')
+    b = s2._mcmc_sample(5, init_samples=u, init_loglikes=logl, loglstar=float(np.median(logl)), step_size=0.3)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])      # same weights, same seed -> same chains
+    # the kernels follow the foreign trainer's weights
+    f.train(None)
+    c = s2._mcmc_sample(5, init_samples=u, init_loglikes=logl, loglstar=float(np.median(logl)), step_size=0.3)
+    z = c[1][:, -1]
+    x_ref, _ = f.inverse(z, to_numpy=True)
+    assert rel_err(c[0][:, -1], x_ref) < 1e-5
+
+
+def test_resume_from_checkpoint_0(tmp_path):
+    """a run interrupted before its first log_interval checkpoint restarts from checkpoint_0 (empty dead-point
+    arrays)."""
+    from nnest_b200 import NestedSampler
+    from nnest_b200.likelihoods import Rosenbrock
+    np.random.seed(4)
+    kw = dict(transform=lambda x: 5 * x, num_live_points=200, flow='nvp', log_dir=str(tmp_path), log_level=logging.WARNING)
+    s1 = NestedSampler(2, Rosenbrock(2), **kw)
+    s1.run(mcmc_num_chains=50, train_iters=10, max_iters=20, log_interval=100000, strategy=['mcmc'])
+    run_dir = s1.logs['run_dir']
+    cks = [f for f in os.listdir(os.path.join(run_dir, 'checkpoint')) if f.startswith('checkpoint_')]
+    assert cks == ['checkpoint_0.txt']
+    s2 = NestedSampler(2, Rosenbrock(2), **dict(kw, log_dir=run_dir))
+    s2.run(mcmc_num_chains=200, train_iters=30, strategy=['mcmc'])
+    assert np.abs(s2.logz + 5.80) <= 0.3 + 3 * s2.logzerr
+    assert np.array_equal(np.load(os.path.join(run_dir, 'checkpoint', 'active_u_0.npy')).shape, (200, 2))
+
+
+def test_batched_rejection_prior_equals_one_at_a_time(tmp_path):
+    """_rejection_prior_sample draws k candidates per launch; result, call counters and the np.random stream must equal
+    the reference's one-draw-per-turn loop (nnest/sampler.py:529-538)."""
+    from nnest_b200 import NestedSampler
+    from nnest_b200.likelihoods import Himmelblau
+    s = NestedSampler(2, Himmelblau(2), transform=lambda x: 5 * x, flow='nvp', num_live_points=50,
+                      log_dir=str(tmp_path), log_level=logging.WARNING)
+    loglstar = -20.0          # ~10 % of the prior volume
+    for seed in range(5):
+        np.random.seed(seed)
+        calls0 = s.total_calls
+        x, logl, der, ncall = s._rejection_prior_sample(loglstar)
+        after = np.random.uniform()
+        np.random.seed(seed)                                   # sequential restatement
+        n = 0
+        while True:
+            xs = s.sample_prior(1)
+            ls = s._loglike_rows(xs)
+            n += 1
+            if ls > loglstar:
+                break
+        assert n == ncall and s.total_calls - calls0 == ncall
+        assert np.array_equal(xs, x) and np.array_equal(ls, logl) and x.shape == (1, 2) and der.shape == (1, 0)
+        assert np.random.uniform() == after                    # same position in the np.random stream
+
+
+@pytest.mark.parametrize('first', ['rejection_flow', 'density_flow'])
+def test_flow_rejection_strategies(tmp_path, first):
+    """The reference's other refill strategies (nnest/sampler.py:545-630, nnest/nested.py:337-362) on the device: every
+    returned point lies in the prior box and beats the constraint; a full run with the strategy reaches the Rosenbrock
+    evidence."""
+    from nnest_b200 import NestedSampler
+    from nnest_b200.likelihoods import Rosenbrock
+    np.random.seed(2)
+    torch.manual_seed(2)
+    s = NestedSampler(2, Rosenbrock(2), transform=lambda x: 5 * x, flow='nvp', num_live_points=400,
+                      log_dir=str(tmp_path), log_level=logging.WARNING)
+    u = s.sample_prior(400)
+    logl, _ = s.loglike(u)
+    s.trainer.train(u[logl > np.median(logl)], max_iters=30, jitter=-1.0)
+    lstar = float(np.median(logl))
+    for _ in range(5):
+        if first == 'rejection_flow':
+            x, l, der, nc = s._rejection_flow_sample(u[logl > lstar], lstar)
+        else:
+            x, l, der, nc = s._density_sample(lstar)
+        assert x.shape == (1, 2) and l.shape == (1,) and nc >= 1
+        assert np.all(np.abs(x) <= 1) and l[0] > lstar
+        assert np.allclose(s._loglike_rows(x), l, rtol=1e-6)
+    s.run(strategy=['rejection_prior', first, 'mcmc'], mcmc_num_chains=200, train_iters=30)
+    assert np.abs(s.logz + 5.80) <= 0.25 + 3 * s.logzerr
