@@ -59,7 +59,8 @@ class MCMCSampler(Sampler):
             initial_jitter=0.01,
             final_jitter=0.01,
             init_samples=None,
-            train_iters=10000):
+            train_iters=10000,
+            thin=1):
         mean = np.mean(training_samples, axis=0)
         std = np.std(training_samples, axis=0)
         training_samples = (training_samples - mean) / std          # mcmc.py:107-110
@@ -67,11 +68,11 @@ class MCMCSampler(Sampler):
         self.trainer.train(training_samples, max_iters=train_iters, jitter=initial_jitter)
 
         # as the reference (mcmc.py:114-116) the step size stays fixed at 2/sqrt(d): dynamic_step_size is not passed
+        # `samples * std + mean` (mcmc.py:117, float64) is evaluated on the device while the trace is staged to the host;
+        # thin=k (extension, default 1 = the reference's full trace) keeps every k-th state
         samples, latent_samples, derived_samples, loglikes, scale, ncall = self._mcmc_sample(
             mcmc_steps, num_chains=mcmc_num_chains, stats_interval=stats_interval, output_interval=output_interval,
-            init_samples=init_samples)
-
-        samples = samples * std + mean                               # transform on (chain, step, dim)
+            init_samples=init_samples, thin=thin, sample_affine=(std, mean))
         if mcmc_steps > 1:
             # mcmc.py:119-120; the statistics of the transformed trace are taken on the device copy
             self._chain_stats(None, trace=self._device_trace, t_scale=std, t_shift=mean)

@@ -81,15 +81,6 @@ class NestedSampler(Sampler):
                                  'max_ess', 'jump_distance', 'scale', 'loglstar', 'logz', 'fraction_remain', 'ncall'])
 
     # ---- multi-GPU helpers -----------------------------------------------------------------------
-    def _allgather_batch(self, batch):
-        """Rank-order concatenation of every rank's end states (NCCL all_gather over NVLink)."""
-        if not self.use_mpi:
-            return batch, self.total_calls
-        out = {key: dist.allgather_rows(batch[key]) for key in ('first', 'last', 'logl_last')}
-        out.update(scale=batch['scale'], ncall=batch['ncall'], trace_x=batch.get('trace_x'),
-                   acceptance=batch.get('acceptance'))
-        return out, dist.allreduce_sum_int(self.total_calls, self.device)
-
     def _bcast_array(self, a):
         return dist.broadcast_array(a, self.device)
 
@@ -322,11 +313,10 @@ class NestedSampler(Sampler):
                     idx = np.random.randint(low=0, high=nlive, size=mcmc_num_chains)
                     batch = self._mcmc_refill(mcmc_steps, active_u[idx, :], active_logl[idx], loglstar, step_size,
                                               mcmc_dynamic_step_size, keep_trace=chain_stats)
-                    batch, total_calls = self._allgather_batch(batch)
+                    b_first, b_last, b_logl = self._refill_to_host(batch)     # all ranks' chains, rank order
+                    total_calls = dist.allreduce_sum_int(self.total_calls, self.device) if self.use_mpi \
+                        else self.total_calls
                     scale = batch['scale']
-                    b_first = np.ascontiguousarray(batch['first'].cpu().numpy())
-                    b_last = np.ascontiguousarray(batch['last'].cpu().numpy())
-                    b_logl = np.ascontiguousarray(batch['logl_last'].cpu().numpy())
                     # run diagnostics (not in the reference): one record per refill -- iteration, constraint, this rank's
                     # acceptance, fraction of chains that moved in every coordinate and beat the constraint, final scale
                     moved = np.all(b_first != b_last, axis=1) & (b_logl > loglstar)

@@ -256,11 +256,15 @@ class Sampler(object):
         """Chain start (nnest/sampler.py:262-284) on the device.  Returns (ChainState, ncall)."""
         offset = self.mpi_rank * num_chains
         if init_samples is not None:
-            u = torch.from_numpy(np.ascontiguousarray(np.asarray(init_samples, dtype=np.float32))).to(self.device)
+            init_samples = np.asarray(init_samples)
+            hu = self._pinned('init_u', init_samples.shape, torch.float32)
+            hu.numpy()[...] = init_samples                      # float64 -> float32 (trainer.py:249) into pinned memory
+            u = hu.to(self.device, non_blocking=True)
             logl = None
             if init_loglikes is not None:
-                logl = torch.from_numpy(np.ascontiguousarray(np.asarray(init_loglikes, dtype=np.float64))
-                                        ).to(self.device)
+                hl = self._pinned('init_logl', (init_samples.shape[0],), torch.float64)
+                hl.numpy()[...] = init_loglikes
+                logl = hl.to(self.device, non_blocking=True)
             st, nbad, ncall = self.engine.mcmc_init(u.shape[0], init_u=u.t().contiguous(), init_logl=logl,
                                                     seed=self.seed, chain_offset=offset)
             return st, ncall
@@ -311,38 +315,113 @@ class Sampler(object):
             output_interval=None,
             stats_interval=None,
             plot_trace=True,
-            prior_volume_steps=1):
+            prior_volume_steps=1,
+            thin=1,
+            sample_affine=None):
         """Same contract as the reference (nnest/sampler.py:229-463): returns
         (samples (N,S+1,d) f32, latent_samples (N,S+1,d) f32, derived (N,S+1,0), loglikes (N,S+1) f64, scale, ncall).
-        The arrays are host views of the chain-minor device trace (no extra transposition pass)."""
+        The arrays are host views of the chain-minor device trace (no extra transposition pass).
+        Extensions (both default to the reference's behaviour): thin=k returns every k-th state of the trace (rows 0, k,
+        2k, ...: arrays shaped (N, S//k+1, .)); sample_affine=(scale, shift) returns samples * scale + shift in float64,
+        evaluated on the device (what MCMCSampler.run applies to the whole trace on the host, mcmc.py:117)."""
         if prior_volume_steps != 1:
             raise NotImplementedError('prior_volume_steps != 1')
         st, out, ncall = self._mcmc_device(mcmc_steps, step_size, dynamic_step_size, num_chains, init_samples,
                                            init_loglikes, loglstar, max_start_tries, trace=True)
-        samples = out['trace_x'].cpu().numpy().transpose(2, 0, 1)        # (S+1, d, N) -> (N, S+1, d) view
-        latent_samples = out['trace_z'].cpu().numpy().transpose(2, 0, 1)
-        loglikes = out['trace_logl'].cpu().numpy().transpose(1, 0)
-        derived_samples = np.empty((st.n, mcmc_steps + 1, 0))
+        rows = list(range(0, mcmc_steps + 1, max(1, int(thin))))
+        samples = self._trace_to_host(out['trace_x'], rows, sample_affine).transpose(2, 0, 1)   # (T,d,N) -> (N,T,d) view
+        latent_samples = self._trace_to_host(out['trace_z'], rows, None).transpose(2, 0, 1)
+        loglikes = self._trace_to_host(out['trace_logl'], rows, None).transpose(1, 0)
+        derived_samples = np.empty((st.n, len(rows), 0))
         self._device_trace = out['trace_x']          # (S+1, d, N) on the device, for the chain statistics
         ts, tb = self._affine()
         for it in range(1, mcmc_steps + 1):
             if output_interval is not None and it % output_interval == 0:
-                self._save_samples(self.transform(samples[:, :it + 1].reshape(-1, self.x_dim)).reshape(
-                    st.n, it + 1, self.x_dim), loglikes[:, :it + 1])
+                full = out['trace_x'][:it + 1].cpu().numpy().transpose(2, 0, 1)
+                self._save_samples(self.transform(full.reshape(-1, self.x_dim)).reshape(st.n, it + 1, self.x_dim),
+                                   out['trace_logl'][:it + 1].cpu().numpy().transpose(1, 0))
             if stats_interval is not None and it % stats_interval == 0:
                 self._chain_stats(None, step=it, trace=self._device_trace, t_scale=ts, t_shift=tb)
         return samples, latent_samples, derived_samples, loglikes, out['scale'], ncall
 
+    _STAGE_BYTES = 128 << 20
+
+    def _trace_to_host(self, trace, rows, affine):
+        """Rows `rows` of a device trace (T, d, N) / (T, N) -> pageable host array (len(rows), ...), through two pinned
+        staging buffers: the device->host copy of chunk k+1 runs while chunk k is moved into the result by a few host
+        threads (a single pageable .cpu() of a multi-GB trace is bound by first-touch page faults on one core).
+        affine=(scale, shift): float64 rows * scale[:, None] + shift[:, None], computed on the device."""
+        from concurrent.futures import ThreadPoolExecutor
+        inner = tuple(trace.shape[1:])
+        dtype = torch.float64 if affine is not None else trace.dtype
+        out = np.empty((len(rows),) + inner, dtype=np.float64 if dtype == torch.float64 else np.float32)
+        if not rows:
+            return out
+        row_bytes = int(np.prod(inner)) * out.itemsize
+        per = max(1, min(len(rows), self._STAGE_BYTES // max(1, row_bytes)))
+        stage = [self._pinned('stage%d' % i, (per,) + inner, dtype) for i in range(2)]
+        events = [torch.cuda.Event(), torch.cuda.Event()]
+        if affine is not None:
+            sc = torch.as_tensor(np.broadcast_to(affine[0], (inner[0],)).copy(), dtype=torch.float64, device=self.device)
+            sh = torch.as_tensor(np.broadcast_to(affine[1], (inner[0],)).copy(), dtype=torch.float64, device=self.device)
+        step = rows[1] - rows[0] if len(rows) > 1 else 1
+        chunks = [(i, min(i + per, len(rows))) for i in range(0, len(rows), per)]
+
+        def launch(ci):
+            a, b = chunks[ci]
+            src = trace[rows[a]:rows[b - 1] + 1:step]
+            if affine is not None:
+                src = src.double() * sc[:, None] + sh[:, None]
+            stage[ci % 2][:b - a].copy_(src, non_blocking=True)
+            events[ci % 2].record()
+
+        nthreads = 8
+        with ThreadPoolExecutor(nthreads) as pool:
+            launch(0)
+            for ci, (a, b) in enumerate(chunks):
+                events[ci % 2].synchronize()
+                if ci + 1 < len(chunks):
+                    launch(ci + 1)
+                src = stage[ci % 2].numpy()[:b - a].reshape(b - a, -1)
+                dst = out[a:b].reshape(b - a, -1)
+                cols = dst.shape[1]
+                cuts = [cols * t // nthreads for t in range(nthreads + 1)]
+                list(pool.map(lambda t: np.copyto(dst[:, cuts[t]:cuts[t + 1]], src[:, cuts[t]:cuts[t + 1]]),
+                              range(nthreads)))
+        return out
+
     def _mcmc_refill(self, mcmc_steps, init_samples, init_loglikes, loglstar, step_size, dynamic_step_size,
                      keep_trace=False):
         """What NestedSampler.run needs from a batch (nested.py:429-439): start point, end point and end
-        loglike of every chain, on the host; the trace stays on the device (optional, for chain statistics)."""
+        loglike of every chain (device tensors, chain-major); the trace stays on the device (optional, for chain
+        statistics).  `_refill_to_host` gathers them over the ranks and brings them to the host."""
         st, out, ncall = self._mcmc_device(mcmc_steps, step_size, dynamic_step_size, init_samples.shape[0],
                                            init_samples, init_loglikes, loglstar, 0, trace=keep_trace)
         first = out['first_x'].t().contiguous()
         last = st.x.t().contiguous()
         return dict(first=first, last=last, logl_last=st.logl, scale=out['scale'], ncall=ncall,
                     trace_x=out.get('trace_x'), acceptance=out['naccept'] / float(max(1, st.n * mcmc_steps)))
+
+    def _pinned(self, name, shape, dtype):
+        """Page-locked host staging buffers, allocated once per shape and reused by every refill."""
+        cache = self.__dict__.setdefault('_pin_cache', {})
+        key = (name, tuple(shape), dtype)
+        if key not in cache:
+            cache[key] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+        return cache[key]
+
+    def _refill_to_host(self, batch):
+        """End states of a refill -> host arrays (first (N,d) f32, last (N,d) f32, logl_last (N,) f64), N = chains of all
+        ranks in rank order (one NCCL all_gather per array over NVLink = the reference's gather + bcast + concatenate,
+        nested.py:416-427).  Copies go through pinned buffers, asynchronously, with ONE synchronisation."""
+        out = {}
+        for key in ('first', 'last', 'logl_last'):
+            t = dist.allgather_rows(batch[key]) if self.use_mpi else batch[key]
+            host = self._pinned(key, t.shape, t.dtype)
+            host.copy_(t, non_blocking=True)
+            out[key] = host
+        torch.cuda.current_stream().synchronize()
+        return out['first'].numpy(), out['last'].numpy(), out['logl_last'].numpy()
 
     def _plot_trace(self, samples, latent_samples):
         pass    # plotting is outside the accelerated path

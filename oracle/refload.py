@@ -12,6 +12,9 @@ import os
 import sys
 
 REFERENCE_ROOT = os.environ.get("NNEST_REFERENCE_ROOT", "/root/reference")
+# the reference installed by oracle/build_ref.py (pip --target; git-ignored, travels to the GPU box): used by bench.py's
+# cpu_baseline / --impl reference legs when the source tree is absent
+INSTALLED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_shims")
 
 
@@ -19,10 +22,16 @@ def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "nnest"))
 
 
-def load_reference():
-    """Returns the imported reference `nnest` module (never the product package)."""
-    if not reference_available():
-        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+def installed_reference_available():
+    return os.path.isfile(os.path.join(INSTALLED_ROOT, "nnest", "sampler.py"))
+
+
+def load_reference(installed=False):
+    """Returns the imported reference `nnest` module (never the product package).  installed=True imports the copy
+    installed under oracle/_ref instead of the source tree."""
+    root = INSTALLED_ROOT if installed else REFERENCE_ROOT
+    if not (installed_reference_available() if installed else reference_available()):
+        raise RuntimeError("reference not present at %s" % root)
     try:
         import matplotlib  # noqa: F401
     except ImportError:
@@ -40,10 +49,10 @@ def load_reference():
                 mod = importlib.util.module_from_spec(spec)
                 sys.modules[name] = mod
                 spec.loader.exec_module(mod)
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     from torch.utils.tensorboard import SummaryWriter
     SummaryWriter.add_figure = lambda *a, **k: None
     import nnest
-    assert os.path.abspath(nnest.__file__).startswith(os.path.abspath(REFERENCE_ROOT)), nnest.__file__
+    assert os.path.abspath(nnest.__file__).startswith(os.path.abspath(root)), nnest.__file__
     return nnest

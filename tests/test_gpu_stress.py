@@ -16,8 +16,8 @@ def test_mcmc_refill_is_bit_reproducible():
     wl = dict(bench.WORKLOADS['c4'])
     d, n, S = wl['d'], wl['chains'], 40
     eng.set_target(d, 0, [], t_scale=5.0, t_shift=0.0, prior_kind=L.NNB_PRIOR_BOX_U, prior_lo=-1.0, prior_hi=1.0)
-    prob = bench.make_problem(wl, lambda u: eng.loglike(torch.from_numpy(u).cuda()).cpu().numpy())
-    eng.set_flow(bench.flat_weights(prob['layers']), d, 16, 1, 3, 0)
+    prob = bench.make_problem('c4', wl, n)
+    eng.set_flow_from_state_dict(prob['sd'])
     u = torch.from_numpy(np.ascontiguousarray(prob['init_u'].astype(np.float32).T)).cuda()
     logl = torch.from_numpy(prob['init_logl']).cuda()
     ref = None
