@@ -20,9 +20,10 @@ weights (a retrain precedes every refill at this size: update_interval = nlive /
 GPU fixed (N independent shards, same collectives).
 
 `value`  = device-timed (CUDA events, max over ranks) steps with the inputs resident in HBM.
-`e2e`    = the same refill through the repo's Python API from HOST arrays to the live-point replacement on the host:
-           Sampler._mcmc_refill -> Sampler._refill_to_host (gather + pinned D2H) -> NSBook.bulk (nnb_ns_consume replay
-           of nested.py:429-439 over the whole gathered batch); c5: MCMCSampler._mcmc_sample with a thinned host trace.
+`e2e`    = the same refill through the repo's Python API, HOST arrays in, HOST arrays out: Sampler._mcmc_refill ->
+           Sampler._refill_to_host (all_gather + pinned D2H); c5: MCMCSampler._mcmc_sample with a thinned host trace.
+`ns_loop`= (extra) the refill as NestedSampler.run drives it, including the host replay of the live-point replacement
+           over the whole gathered batch (NSBook.bulk -> nnb_ns_consume, nested.py:429-439), replicated on every rank.
 `--impl reference` times the reference's own Sampler._mcmc_sample (UNMODIFIED, installed under oracle/_ref by
 oracle/build_ref.py; the oracle port if that is absent) on the host cores, on a bounded sample of the same workload.
 Prints ONE JSON line.
@@ -324,7 +325,8 @@ def run_gpu(args, name, wl):
     gat_first = torch.empty((n_total, d), dtype=torch.float32, device='cuda')
     gat_last = torch.empty((n_total, d), dtype=torch.float32, device='cuda')
     gat_logl = torch.empty((n_total,), dtype=torch.float64, device='cuda')
-    kernel_impl = {'auto': L.NNB_IMPL_AUTO, 'ffma': L.NNB_IMPL_FFMA, 'tcgen05': L.NNB_IMPL_TCGEN05}[args.kernel]
+    kernel_impl = {'auto': L.NNB_IMPL_AUTO, 'ffma': L.NNB_IMPL_FFMA, 'tcgen05': L.NNB_IMPL_TCGEN05,
+                   'warp': L.NNB_IMPL_WARP}[args.kernel]
     run_ev = []
     coll = {'bcast': 0, 'all_gather': 0}
 
@@ -416,26 +418,44 @@ def run_gpu(args, name, wl):
         smp = NestedSampler(d, like, transform=lambda x: ts * x, flow='nvp', num_live_points=n_total, log_dir=log_dir,
                             log_level=logging.WARNING, seed=args.seed)
         smp.trainer.load_state_dict(sd_t)
-        my_u, my_l = prob['init_u'][sl], prob['init_logl'][sl]
+        my_u = np.ascontiguousarray(prob['init_u'][sl], dtype=np.float32)     # float32(active_u[idx]) (trainer.py:249)
+        my_l = np.ascontiguousarray(prob['init_logl'][sl])
         h2d = my_u.size * 4 + my_l.size * 8
         d2h = n_total * (2 * d * 4 + 8)
-        live_u0, live_l0 = prob['init_u'], np.ascontiguousarray(prob['init_logl'])
 
         def one_e2e(it):
+            """host start points in -> host end states of ALL ranks' chains out (what nested.py:429-439 consumes)"""
             t0 = time.perf_counter()
             batch = smp._mcmc_refill(S, my_u, my_l, prob['loglstar'], step_size, wl['dynamic'])
             t1 = time.perf_counter()
-            b_first, b_last, b_logl = smp._refill_to_host(batch)
+            smp._refill_to_host(batch)
             t2 = time.perf_counter()
-            # live-point replacement over the whole gathered batch (every rank replays it, nested.py:429-439)
+            for k, v in (('mcmc_refill_ms', t1 - t0), ('gather_d2h_ms', t2 - t1)):
+                e2e_parts[k] = e2e_parts.get(k, 0.0) + 1e3 * v
+            return 0
+
+        # the refill as NestedSampler.run drives it: chain starts by INDEX into the device-resident live set, gather + D2H,
+        # then the live-point replacement over the whole gathered batch on the host (every rank replays it,
+        # nested.py:429-439; NSBook.bulk -> nnb_ns_consume) and the scatter of the replacements into the device live set
+        live_u0, live_l0 = prob['init_u'], np.ascontiguousarray(prob['init_logl'])
+        live_dev = (torch.from_numpy(np.ascontiguousarray(live_u0)).cuda(), torch.from_numpy(live_l0).cuda())
+        my_idx = np.arange(chain_offset, chain_offset + n, dtype=np.int64)
+        ns_parts = {}
+
+        def one_ns_refill(it):
+            t0 = time.perf_counter()
+            batch = smp._mcmc_refill(S, None, None, prob['loglstar'], step_size, wl['dynamic'],
+                                     live=(live_dev[0], live_dev[1], my_idx))
+            b_first, b_last, b_logl = smp._refill_to_host(batch)
+            t1 = time.perf_counter()
             bk = NSBook(n_total)
             au, al = live_u0.copy(), live_l0.copy()
             av = ts * au
-            t3 = time.perf_counter()
+            t2 = time.perf_counter()
             bk.bulk(au, av, al, smp.transform, b_first, b_last, b_logl, 0, n_total, 0.0, 1 << 60)
-            t4 = time.perf_counter()
-            for k, v in (('mcmc_refill_ms', t1 - t0), ('gather_d2h_ms', t2 - t1), ('consume_replay_ms', t4 - t3)):
-                e2e_parts[k] = e2e_parts.get(k, 0.0) + 1e3 * v
+            t3 = time.perf_counter()
+            for k, v in (('refill_gather_d2h_ms', t1 - t0), ('consume_replay_ms', t3 - t2)):
+                ns_parts[k] = ns_parts.get(k, 0.0) + 1e3 * v
             return bk.it
     else:
         thin = args.thin
@@ -455,21 +475,34 @@ def run_gpu(args, name, wl):
             e2e_parts['mcmc_sample_ms'] = e2e_parts.get('mcmc_sample_ms', 0.0) + 1e3 * (time.perf_counter() - t0)
             return out[0].shape[1]
 
-    one_e2e(0)
-    e2e_parts.clear()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    e0.record()
-    for it in range(e2e_steps):
-        consumed = one_e2e(it)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n_total * S * e2e_steps / (t.item() * 1e-3)
-    e2e_parts = {k: v / e2e_steps for k, v in e2e_parts.items()}
+
+    def time_loop(fn, parts):
+        fn(0)
+        parts.clear()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(e2e_steps):
+            last_ret = fn(it)
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        for k in list(parts):
+            parts[k] /= e2e_steps
+        return n_total * S * e2e_steps / (tt.item() * 1e-3), tt.item() / e2e_steps, last_ret
+
+    e2e_value, e2e_ms, consumed = time_loop(one_e2e, e2e_parts)
+    ns_loop = None
+    if wl['mode'] == 'hard':
+        v, ms_, consumed = time_loop(one_ns_refill, ns_parts)
+        ns_loop = {'value': v, 'unit': 'proposals/s', 'ms_per_refill': ms_, 'ms_per_refill_parts': ns_parts,
+                   'iterations_consumed_per_refill': int(consumed),
+                   'what': 'refill as NestedSampler.run drives it: start indices into the device-resident live set -> '
+                           'Sampler._mcmc_refill -> _refill_to_host (all_gather + pinned D2H) -> NSBook.bulk (host replay of '
+                           'nested.py:429-439 over the whole gathered batch, replicated on every rank)'}
 
     if rank == 0:
         peaks = {}
@@ -518,9 +551,12 @@ def run_gpu(args, name, wl):
                                        'last logl) of one fixed-step-size refill of all %d chains; identical for every '
                                        '--gpus N' % n_total}},
             'e2e': {'value': e2e_value, 'unit': 'proposals/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'steps': e2e_steps, 'api': 'Sampler._mcmc_refill + _refill_to_host + NSBook.bulk (nnb_ns_consume)'
-                    if wl['mode'] == 'hard' else 'MCMCSampler._mcmc_sample(thin=%d)' % args.thin,
-                    'ms_per_step_parts': e2e_parts, 'iterations_consumed_last_step': int(consumed)},
+                    'steps': e2e_steps, 'ms_per_step': e2e_ms,
+                    'api': 'Sampler._mcmc_refill(host float32 start points, host loglikes) + Sampler._refill_to_host '
+                           '(all_gather over ranks + pinned D2H of first x, last x, last logl)'
+                    if wl['mode'] == 'hard' else 'MCMCSampler._mcmc_sample(thin=%d): host start points -> host trace' % args.thin,
+                    'ms_per_step_parts': e2e_parts},
+            'ns_loop': ns_loop,
             'gpu_launches': launches,
             'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
         }))
@@ -537,7 +573,7 @@ def main():
     ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--seed', type=int, default=0)
-    ap.add_argument('--kernel', default='auto', choices=['auto', 'ffma', 'tcgen05'])
+    ap.add_argument('--kernel', default='auto', choices=['auto', 'ffma', 'tcgen05', 'warp'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=10, help='timed steps of the end-to-end arm (<= --steps)')
     ap.add_argument('--thin', type=int, default=10, help='c5 end-to-end arm: keep every thin-th state of the trace')

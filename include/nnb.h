@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 8
+#define NNB_ABI_VERSION 9
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -58,9 +58,11 @@ enum {
 
 enum { NNB_PRIOR_NONE = 0, NNB_PRIOR_BOX_U = 1, NNB_PRIOR_BOX_V = 2 };
 enum { NNB_MODE_HARD = 0, NNB_MODE_MH = 1 };
-/* kernel variant of nnb_mcmc_run: AUTO picks the tcgen05 (tensor-core, 3xTF32) kernel when the flow shape allows
- * it (hidden_dim == 16, 2 <= x_dim <= 63, scale == ''), else the FP32-FMA kernel */
-enum { NNB_IMPL_AUTO = 0, NNB_IMPL_FFMA = 1, NNB_IMPL_TCGEN05 = 2 };
+/* kernel variant of nnb_mcmc_run.  AUTO: batches small enough to be held co-resident by the 16-lanes-per-chain kernel
+ * (<= 2 x 32 chains per SM; hidden_dim == 16, scale == '') run there -- a step's latency is ~10x shorter than with one
+ * thread per chain, which is what bounds small / sharded batches; larger batches run the tcgen05 (tensor-core, 3xTF32)
+ * kernel when the flow shape allows it (hidden_dim == 16, 2 <= x_dim <= 63, scale == ''), else the FP32-FMA kernel */
+enum { NNB_IMPL_AUTO = 0, NNB_IMPL_FFMA = 1, NNB_IMPL_TCGEN05 = 2, NNB_IMPL_WARP = 3 };
 
 typedef struct nnb_handle nnb_handle;
 
@@ -198,7 +200,7 @@ typedef struct {
   int64_t* naccept_out;  /* accepted proposals (total_accepted, sampler.py:418-420) */
   int impl;              /* NNB_IMPL_* */
   int64_t* launches_out; /* [host] kernels launched by this call (1 when the persistent cooperative kernel ran) */
-  int* impl_out;         /* [host] NNB_IMPL_FFMA or NNB_IMPL_TCGEN05: the variant that ran */
+  int* impl_out;         /* [host] NNB_IMPL_FFMA, NNB_IMPL_TCGEN05 or NNB_IMPL_WARP: the variant that ran */
 } nnb_mcmc_args;
 
 int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream);

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libnnb.so')
 
-NNB_ABI_VERSION = 8
+NNB_ABI_VERSION = 9
 NNB_MAX_DIM = 128
 NNB_MAX_BLOCKS = 16
 
@@ -19,7 +19,7 @@ NNB_FLOW_TRANSLATE_ONLY, NNB_FLOW_CONST_SCALE = 1, 2
  NNB_LIKE_GAUSSIAN_SHELL) = range(6)
 NNB_PRIOR_NONE, NNB_PRIOR_BOX_U, NNB_PRIOR_BOX_V = 0, 1, 2
 NNB_MODE_HARD, NNB_MODE_MH = 0, 1
-NNB_IMPL_AUTO, NNB_IMPL_FFMA, NNB_IMPL_TCGEN05 = 0, 1, 2
+NNB_IMPL_AUTO, NNB_IMPL_FFMA, NNB_IMPL_TCGEN05, NNB_IMPL_WARP = 0, 1, 2, 3
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)

@@ -114,6 +114,8 @@ class NSBook(object):
         self.saved_v.append(dead)
         self.saved_logwt.append(np.array(logwt[:n_evid], copy=True))
         self.saved_logl.append(np.array(lstar[:n_evid], copy=True))
+        self.last_slots = np.array(worst[:n_done], copy=True)       # (slot, chain) pairs of this call, in order: lets the
+        self.last_chains = np.array(chain[:n_done], copy=True)      # caller mirror the replacements elsewhere (device)
         if n_done:
             # live set: last write to a slot wins
             wd = worst[:n_done]

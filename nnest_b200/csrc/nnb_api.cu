@@ -53,6 +53,7 @@ extern "C" int nnb_create(int device, nnb_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   h->coop_supported = prop.cooperativeLaunch;
   h->max_smem = (int)prop.sharedMemPerBlockOptin;
+  h->max_smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
   if ((e = cudaMalloc(&h->d_ctrl, sizeof(Ctrl))) != cudaSuccess ||
       (e = cudaMallocHost(&h->h_ctrl, sizeof(Ctrl))) != cudaSuccess) {
     delete h;
@@ -67,6 +68,7 @@ extern "C" void nnb_destroy(nnb_handle* h) {
   cudaSetDevice(h->device);
   if (h->d_weights) cudaFree(h->d_weights);
   if (h->d_weights_tc) cudaFree(h->d_weights_tc);
+  if (h->d_weights_warp) cudaFree(h->d_weights_warp);
   if (h->d_step_counts) cudaFree(h->d_step_counts);
   if (h->d_target) cudaFree(h->d_target);
   if (h->d_ctrl) cudaFree(h->d_ctrl);
@@ -159,7 +161,9 @@ extern "C" int nnb_set_flow(nnb_handle* h, int d, int hidden, int num_layers, in
   NNB_CUDA(h, cudaMemcpy(h->d_weights, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
   h->flow = f;
   h->has_flow = true;
-  return nnb_tc_pack(h, weights);
+  int rc = nnb_tc_pack(h, weights);
+  if (rc) return rc;
+  return nnb_warp_pack(h, weights);
 }
 
 extern "C" int nnb_set_target(nnb_handle* h, int d, const nnb_target* t) {
@@ -345,11 +349,22 @@ extern "C" int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream)
   p.replay_normals = a->replay_normals; p.replay_uniforms = a->replay_uniforms;
   p.dump_normals = a->dump_normals; p.dump_uniforms = a->dump_uniforms;
   p.ctrl = h->d_ctrl;
-  if (a->impl < NNB_IMPL_AUTO || a->impl > NNB_IMPL_TCGEN05) return fail(h, NNB_ERR_ARG, "impl");
+  if (a->impl < NNB_IMPL_AUTO || a->impl > NNB_IMPL_WARP) return fail(h, NNB_ERR_ARG, "impl");
   if (a->impl == NNB_IMPL_TCGEN05 && !h->tc_ok)
     return fail(h, NNB_ERR_UNSUPPORTED, "tcgen05 path needs hidden_dim == 16, 2 <= x_dim <= 63 and scale == ''");
-  const bool use_tc = h->tc_ok && a->impl != NNB_IMPL_FFMA;
-  if (a->steps > 0 && use_tc) {
+  if (a->impl == NNB_IMPL_WARP && !h->warp_ok)
+    return fail(h, NNB_ERR_UNSUPPORTED, "the 16-lanes-per-chain kernel needs hidden_dim == 16 and scale == ''");
+  bool use_warp = false;
+  if (a->steps > 0 && h->warp_ok && (a->impl == NNB_IMPL_WARP || (a->impl == NNB_IMPL_AUTO && n <= nnb_warp_capacity(h)))) {
+    rc = nnb_launch_mcmc_warp(h, p, a->steps, st, &use_warp);
+    if (rc) return rc;
+    if (!use_warp && a->impl == NNB_IMPL_WARP)
+      return fail(h, NNB_ERR_UNSUPPORTED,
+                  "the 16-lanes-per-chain kernel holds every chain co-resident: too many chains (or a single dynamic step)");
+  }
+  const bool use_tc = !use_warp && h->tc_ok && a->impl != NNB_IMPL_FFMA;
+  if (use_warp) {
+  } else if (a->steps > 0 && use_tc) {
     rc = nnb_launch_mcmc_tc(h, p, a->steps, st);
     if (rc) return rc;
   } else if (a->steps > 0) {
@@ -362,7 +377,7 @@ extern "C" int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream)
     if (rc) return rc;
   }
   if (a->launches_out) *a->launches_out = a->steps > 0 ? h->last_launches : 0;
-  if (a->impl_out) *a->impl_out = use_tc ? NNB_IMPL_TCGEN05 : NNB_IMPL_FFMA;
+  if (a->impl_out) *a->impl_out = use_warp ? NNB_IMPL_WARP : (use_tc ? NNB_IMPL_TCGEN05 : NNB_IMPL_FFMA);
   NNB_CUDA(h, cudaGetLastError());
   // no result requested: the call stays asynchronous (results of the last run: nnb_mcmc_result)
   if (!a->scale_out && !a->ncall_out && !a->naccept_out) return NNB_OK;

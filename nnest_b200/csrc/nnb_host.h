@@ -5,11 +5,13 @@
 #include <string>
 
 #include "nnb_kernels.cuh"
+#include "nnb_warp_desc.h"
 
 struct nnb_handle {
   int device = 0;
   int sm_count = 0;
   int max_smem = 0;
+  int max_smem_per_sm = 0;
   bool has_flow = false, has_target = false;
   nnb::FlowDesc flow{};
   float* d_weights = nullptr;
@@ -19,7 +21,11 @@ struct nnb_handle {
   bool tc_ok = false;
   nnb::TcFlowDesc tcflow{};
   float* d_weights_tc = nullptr;
-  unsigned int* d_step_counts = nullptr;   // workspace of the cooperative kernel
+  // 16-lanes-per-chain variant (small batches): (s, t) weight pairs interleaved
+  bool warp_ok = false;
+  nnb::WarpFlowDesc warpflow{};
+  float* d_weights_warp = nullptr;
+  unsigned int* d_step_counts = nullptr;   // workspace of the cooperative kernels
   int step_counts_cap = 0;
   int coop_supported = 0;
   long long last_launches = 0;             // kernels launched by the last nnb_mcmc_run
@@ -39,6 +45,9 @@ struct nnb_handle {
 int nnb_fail(nnb_handle* h, int code, const std::string& msg);
 int nnb_tc_pack(nnb_handle* h, const float* weights_natural);                         // nnb_tc.cu
 int nnb_launch_mcmc_tc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st);      // nnb_tc.cu
+int nnb_warp_pack(nnb_handle* h, const float* weights_natural);                       // nnb_warp.cu
+int nnb_launch_mcmc_warp(nnb_handle* h, McmcParams p, int steps, cudaStream_t st, bool* ran);   // nnb_warp.cu
+long long nnb_warp_capacity(const nnb_handle* h);                                     // nnb_warp.cu
 
 #define NNB_CUDA(h, call)                                                                        \
   do {                                                                                           \

@@ -68,8 +68,8 @@ int nnb_launch_mcmc_tc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st) 
   // tile barriers) measured faster than two threads per chain at every batch size tried on the B200 (1 k - 131 k chains),
   // so it is the default; NNB_TC_NPART=2 selects the two-thread layout (the chain's threads split every per-column
   // phase and the second one draws the next step's noise during the accept test).
-  static const int npart_env = [] { const char* e = getenv("NNB_TC_NPART"); return e ? atoi(e) : 0; }();
-  const int npart = npart_env == 2 ? 2 : 1;
+  const char* npart_env = getenv("NNB_TC_NPART");     // read at every launch (the tests switch layouts in-process)
+  const int npart = npart_env && atoi(npart_env) == 2 ? 2 : 1;
   // the reference's default architecture at the dimensions of the named workloads: fully unrolled kernels
   static const bool generic_only = getenv("NNB_TC_GENERIC") != nullptr;
   if (!generic_only && h->tcflow.L == 1 && h->tcflow.B == 3) {

@@ -190,6 +190,27 @@ class NestedSampler(Sampler):
         active_logl = np.ascontiguousarray(active_logl, dtype=np.float64)
 
         lib = L.load()
+        # Device-resident live set (float64, like the host arrays): chain starts are gathered from it on the device, and the
+        # replacements of a batch are applied to it by a scatter from the gathered end states -- only indices cross PCIe.
+        # Built at the first MCMC refill (the rejection phase replaces live points on the host only).
+        live_dev = None
+        pend_slots, pend_chains = [], []
+
+        def flush_live():
+            """apply the pending (slot <- chain of the last gathered batch) replacements to the device live set"""
+            if not pend_slots:
+                return
+            slots = np.concatenate(pend_slots)
+            chains_ = np.concatenate(pend_chains)
+            _, first_rev = np.unique(slots[::-1], return_index=True)          # last write to a slot wins
+            keep = len(slots) - 1 - first_rev
+            sl = torch.from_numpy(np.ascontiguousarray(slots[keep])).to(self.device)
+            ch = torch.from_numpy(np.ascontiguousarray(chains_[keep])).to(self.device)
+            g = self._gathered_dev
+            live_dev[0].index_copy_(0, sl, g['last'].index_select(0, ch).double())
+            live_dev[1].index_copy_(0, sl, g['logl_last'].index_select(0, ch))
+            del pend_slots[:], pend_chains[:]
+
         self.refill_log = []
         first_time = True
         get_samples = True
@@ -219,6 +240,8 @@ class NestedSampler(Sampler):
                                                               b_last, b_logl, nb, kmax, dlogz, max_iters)
                     if n_done:
                         max_logl = np.max(active_logl)
+                        pend_slots.append(bk.last_slots)
+                        pend_chains.append(bk.last_chains)
                     if exhausted:
                         accept_point = False
                     get_samples = nb == b_first.shape[0]
@@ -311,8 +334,13 @@ class NestedSampler(Sampler):
                 if get_samples:                                 # nested.py:402-427
                     nb = 0
                     idx = np.random.randint(low=0, high=nlive, size=mcmc_num_chains)
-                    batch = self._mcmc_refill(mcmc_steps, active_u[idx, :], active_logl[idx], loglstar, step_size,
-                                              mcmc_dynamic_step_size, keep_trace=chain_stats)
+                    if live_dev is None:
+                        live_dev = (torch.from_numpy(active_u).to(self.device), torch.from_numpy(active_logl).to(self.device))
+                        del pend_slots[:], pend_chains[:]
+                    else:
+                        flush_live()
+                    batch = self._mcmc_refill(mcmc_steps, None, None, loglstar, step_size, mcmc_dynamic_step_size,
+                                              keep_trace=chain_stats, live=(live_dev[0], live_dev[1], idx))
                     b_first, b_last, b_logl = self._refill_to_host(batch)     # all ranks' chains, rank order
                     total_calls = dist.allreduce_sum_int(self.total_calls, self.device) if self.use_mpi \
                         else self.total_calls
@@ -335,6 +363,8 @@ class NestedSampler(Sampler):
                     active_v[worst] = self.transform(active_u[worst])
                     active_logl[worst] = b_logl[ib]
                     accept_point = True
+                    pend_slots.append(np.array([worst], dtype=np.int64))
+                    pend_chains.append(np.array([ib], dtype=np.int64))
 
                 if accept_point and it > 0 and it % log_interval == 0 and primary:
                     if chain_stats and batch.get('trace_x') is not None:

@@ -252,9 +252,21 @@ class Sampler(object):
         self.engine.set_flow_from_state_dict(self.trainer.netG.state_dict(), scale=None)
 
     # ---- the hot path -----------------------------------------------------------------------------
-    def _start_chains(self, num_chains, init_samples, init_loglikes, max_start_tries):
-        """Chain start (nnest/sampler.py:262-284) on the device.  Returns (ChainState, ncall)."""
+    def _start_chains(self, num_chains, init_samples, init_loglikes, max_start_tries, live=None):
+        """Chain start (nnest/sampler.py:262-284) on the device.  Returns (ChainState, ncall).
+        live=(live_u_dev (nlive,d) f64, live_logl_dev (nlive,) f64, idx (n,) int64 host): the start points are gathered from
+        the device-resident live set (only the indices cross PCIe); values equal float32(init_samples) bit for bit."""
         offset = self.mpi_rank * num_chains
+        if live is not None:
+            live_u, live_logl, idx = live
+            hi = self._pinned('init_idx', (len(idx),), torch.int64)
+            hi.numpy()[...] = idx
+            di = hi.to(self.device, non_blocking=True)
+            u = live_u.index_select(0, di).float()              # float64 -> float32 (trainer.py:249)
+            logl = live_logl.index_select(0, di)
+            st, nbad, ncall = self.engine.mcmc_init(u.shape[0], init_u=u.t().contiguous(), init_logl=logl,
+                                                    seed=self.seed, chain_offset=offset)
+            return st, ncall
         if init_samples is not None:
             init_samples = np.asarray(init_samples)
             hu = self._pinned('init_u', init_samples.shape, torch.float32)
@@ -279,13 +291,13 @@ class Sampler(object):
         raise Exception('Could not find starting value')
 
     def _mcmc_device(self, mcmc_steps, step_size, dynamic_step_size, num_chains, init_samples, init_loglikes,
-                     loglstar, max_start_tries, trace):
+                     loglstar, max_start_tries, trace, live=None):
         """Runs the fused kernels; returns (state, result dict, ncall)."""
         if step_size <= 0.0:
             step_size = 2 / self.x_dim ** 0.5
         if self._foreign_trainer:
             self._sync_foreign_trainer()
-        st, ncall = self._start_chains(num_chains, init_samples, init_loglikes, max_start_tries)
+        st, ncall = self._start_chains(num_chains, init_samples, init_loglikes, max_start_tries, live=live)
         self.total_calls += ncall
         mode = L.NNB_MODE_MH if loglstar is None else L.NNB_MODE_HARD
         first_x = st.x.clone()
@@ -391,12 +403,15 @@ class Sampler(object):
         return out
 
     def _mcmc_refill(self, mcmc_steps, init_samples, init_loglikes, loglstar, step_size, dynamic_step_size,
-                     keep_trace=False):
+                     keep_trace=False, live=None):
         """What NestedSampler.run needs from a batch (nested.py:429-439): start point, end point and end
         loglike of every chain (device tensors, chain-major); the trace stays on the device (optional, for chain
-        statistics).  `_refill_to_host` gathers them over the ranks and brings them to the host."""
-        st, out, ncall = self._mcmc_device(mcmc_steps, step_size, dynamic_step_size, init_samples.shape[0],
-                                           init_samples, init_loglikes, loglstar, 0, trace=keep_trace)
+        statistics).  `_refill_to_host` gathers them over the ranks and brings them to the host.
+        live=(live_u_dev, live_logl_dev, idx): start from rows `idx` of the device-resident live set instead of the host
+        arrays init_samples / init_loglikes (which may then be None)."""
+        n = len(live[2]) if live is not None else init_samples.shape[0]
+        st, out, ncall = self._mcmc_device(mcmc_steps, step_size, dynamic_step_size, n,
+                                           init_samples, init_loglikes, loglstar, 0, trace=keep_trace, live=live)
         first = out['first_x'].t().contiguous()
         last = st.x.t().contiguous()
         return dict(first=first, last=last, logl_last=st.logl, scale=out['scale'], ncall=ncall,
@@ -415,11 +430,14 @@ class Sampler(object):
         ranks in rank order (one NCCL all_gather per array over NVLink = the reference's gather + bcast + concatenate,
         nested.py:416-427).  Copies go through pinned buffers, asynchronously, with ONE synchronisation."""
         out = {}
+        dev = {}
         for key in ('first', 'last', 'logl_last'):
             t = dist.allgather_rows(batch[key]) if self.use_mpi else batch[key]
+            dev[key] = t
             host = self._pinned(key, t.shape, t.dtype)
             host.copy_(t, non_blocking=True)
             out[key] = host
+        self._gathered_dev = dev          # device copies of the gathered batch: source of the live-set updates
         torch.cuda.current_stream().synchronize()
         return out['first'].numpy(), out['last'].numpy(), out['logl_last'].numpy()
 

@@ -153,7 +153,7 @@ HARD = {
 }
 
 
-IMPLS = [pytest.param(1, id='ffma'), pytest.param(2, id='tcgen05')]
+IMPLS = [pytest.param(1, id='ffma'), pytest.param(2, id='tcgen05'), pytest.param(3, id='warp16')]
 
 
 def _run_replay(engine, g, mode, init_u=None, init_z=None, init_logl=None, loglstar=None, step_size=0.0, dynamic=False,
@@ -278,7 +278,7 @@ def test_mcmc_sharding_invariance(engine, impl):
 def test_mcmc_hard_constraint_invariants_full_size(engine, impl):
     """Config-4 shape (65536 chains, d=30): every chain's end point obeys the constraint and the box."""
     g = load('mcmc_hard_rosen30.npz')
-    d, n, steps = 30, 65536, 10
+    d, n, steps = 30, (65536 if impl != 3 else 8192), 10      # the 16-lane kernel's range: the N = 8 shard of config 4
     engine.set_flow_from_state_dict(state_dict_of(g))
     engine.set_target(d, 0, [], t_scale=5.0, t_shift=0.0, prior_kind=1, prior_lo=-1.0, prior_hi=1.0)
     rng = np.random.RandomState(2)
@@ -302,8 +302,9 @@ def test_mcmc_hard_constraint_invariants_full_size(engine, impl):
     x2, ld2 = engine.flow_inverse(st.z.t())
     if impl == 1:     # same FFMA arithmetic as the batch flow kernel: bit for bit
         assert torch.equal(x2.t().contiguous(), st.x) and torch.equal(ld2, st.logdet)
-    else:             # tensor-core 3xTF32 path: FP32-class agreement
+    else:             # tensor-core 3xTF32 path / 16-lane summation order: FP32-class agreement
         assert (x2.t() - st.x).abs().max().item() < 1e-5 and (ld2 - st.logdet).abs().max().item() < 1e-5
+    assert out['impl'] == (impl if impl else out['impl'])
 
 
 @pytest.mark.parametrize('d,layers,blocks', [(4, 1, 1), (5, 1, 2), (7, 2, 4), (13, 1, 3), (33, 1, 3), (63, 1, 2)])
@@ -316,9 +317,29 @@ def test_mcmc_generic_tensor_core_path_matches_oracle(engine, d, layers, blocks,
     from nnest_b200 import _lib as L
     steps, n = 6, 700
     w = oflow.NVPWeights.random(d, hidden=16, num_layers=layers, num_blocks=blocks, seed=d, gain=1.3)
-    # the thread layout is read once per process from the environment: use a fresh engine-independent switch
-    if os.environ.get('NNB_TC_NPART', '1') != npart:
-        pytest.skip('run with NNB_TC_NPART=%s to cover this layout' % npart)
+    old = os.environ.get('NNB_TC_NPART')
+    os.environ['NNB_TC_NPART'] = npart           # read by the library at every launch
+    try:
+        _generic_case(engine, L.NNB_IMPL_TCGEN05, w, d, layers, blocks, steps, n)
+    finally:
+        if old is None:
+            del os.environ['NNB_TC_NPART']
+        else:
+            os.environ['NNB_TC_NPART'] = old
+
+
+@pytest.mark.parametrize('d,layers,blocks', [(2, 1, 3), (4, 0, 1), (5, 1, 2), (7, 2, 4), (13, 1, 3), (33, 1, 3),
+                                             (63, 1, 2), (100, 1, 3)])
+def test_mcmc_generic_16_lane_path_matches_oracle(engine, d, layers, blocks):
+    """The 16-lanes-per-chain kernel on shapes off the beaten track: odd dims, no / two hidden layers, one block (odd dims
+    never transformed), more than 16 outputs per block (two per lane), more than 64 dims (two Philox blocks per lane)."""
+    from nnest_b200 import _lib as L
+    w = oflow.NVPWeights.random(d, hidden=16, num_layers=layers, num_blocks=blocks, seed=d, gain=1.3)
+    _generic_case(engine, L.NNB_IMPL_WARP, w, d, layers, blocks, 6, 700)
+
+
+def _generic_case(engine, impl, w, d, layers, blocks, steps, n):
+    from nnest_b200 import _lib as L
     engine.set_flow(w.flat(), d, 16, layers, blocks, 0)
     engine.set_target(d, 0, [], t_scale=5.0, t_shift=0.0, prior_kind=1, prior_lo=-1.0, prior_hi=1.0)
     rng = np.random.RandomState(d)
@@ -329,8 +350,8 @@ def test_mcmc_generic_tensor_core_path_matches_oracle(engine, d, layers, blocks,
     st, _, _ = engine.mcmc_init(n, init_u=dev(np.ascontiguousarray(u0.astype(np.float32).T)), init_logl=dev(logl0),
                                 seed=11)
     out = engine.mcmc_run(st, steps, mode=0, loglstar=loglstar, step_size=1 / d ** 0.5, dynamic_step_size=True,
-                          seed=11, trace=True, dump_noise=True, impl=L.NNB_IMPL_TCGEN05)
-    assert out['impl'] == L.NNB_IMPL_TCGEN05
+                          seed=11, trace=True, dump_noise=True, impl=impl)
+    assert out['impl'] == impl
     target = omcmc.Target(like, transform=lambda x: 5 * x, prior=olike.UniformPrior(d, -1, 1), transform_prior=False)
     ref = omcmc.mcmc_sample(w, target, steps, omcmc.ReplayNoise(out['normals'].cpu().numpy(),
                                                                  out['uniforms'].cpu().numpy()),
