@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 9
+#define NNB_ABI_VERSION 10
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -58,9 +58,9 @@ enum {
 
 enum { NNB_PRIOR_NONE = 0, NNB_PRIOR_BOX_U = 1, NNB_PRIOR_BOX_V = 2 };
 enum { NNB_MODE_HARD = 0, NNB_MODE_MH = 1 };
-/* kernel variant of nnb_mcmc_run.  AUTO: batches small enough to be held co-resident by the 16-lanes-per-chain kernel
- * (<= 2 x 32 chains per SM; hidden_dim == 16, scale == '') run there -- a step's latency is ~10x shorter than with one
- * thread per chain, which is what bounds small / sharded batches; larger batches run the tcgen05 (tensor-core, 3xTF32)
+/* kernel variant of nnb_mcmc_run.  AUTO: batches of up to ~6 k chains (3/4 of what the 16-lanes-per-chain kernel holds
+ * co-resident: 2 x 28 chains per SM; hidden_dim == 16, scale == '') run there -- a step's latency is 2-3x shorter than with
+ * one thread per chain, which is what bounds small / sharded batches; larger batches run the tcgen05 (tensor-core, 3xTF32)
  * kernel when the flow shape allows it (hidden_dim == 16, 2 <= x_dim <= 63, scale == ''), else the FP32-FMA kernel */
 enum { NNB_IMPL_AUTO = 0, NNB_IMPL_FFMA = 1, NNB_IMPL_TCGEN05 = 2, NNB_IMPL_WARP = 3 };
 
@@ -85,6 +85,29 @@ const char* nnb_last_error(nnb_handle* h);
  */
 int nnb_set_flow(nnb_handle* h, int d, int hidden, int num_layers, int num_blocks, int flags,
                  const float* weights, size_t n_floats);
+
+/*
+ * Install a neural-spline flow, the reference's DEFAULT flow='spline' (SingleSpeedSpline = [ActNorm, Invertible1x1Conv,
+ * NSF_CL] x num_blocks with num_bins = 8, tail_bound = 3: nnest/networks.py:393-705, built at nnest/trainer.py:92-98).
+ * It replaces whatever flow the handle held; nnb_flow_forward / nnb_flow_inverse / nnb_mcmc_init / nnb_mcmc_run then use
+ * it.  packed [host], per block (d = x_dim, H = hidden, nlow = d/2 (+1 if d is odd), nup = d - nlow, P = 3 num_bins - 1):
+ *     s[d] t[d]                              ActNorm: y = x exp(s) + t                       (networks.py:656-695)
+ *     W[d*d] Winv[d*d] logdet[1]             1x1 convolution y = x W, W = P L (U + diag S) assembled by the caller
+ *                                            (row-major), its inverse, sum(log|S|)           (networks.py:622-653)
+ *     f1: W0[H*nlow] b0[H] W1[H*H] b1[H] W2[H*H] b2[H] W3[(P*nup)*H] b3[P*nup]               conditioner of the upper half
+ *     f2: W0[H*nup]  b0[H] W1[H*H] b1[H] W2[H*H] b2[H] W3[(P*nlow)*H] b3[P*nlow]             conditioner of the lower half
+ * (nn.Linear weights row-major (out, in); MLP = Linear, LeakyReLU(0.2) x 3, Linear, networks.py:401-417).  Synchronous.
+ */
+int nnb_set_flow_spline(nnb_handle* h, int d, int hidden, int num_blocks, int num_bins, double tail_bound,
+                        const float* packed, size_t n_floats);
+/*
+ * flags[r] = 1 when, for sample r, some coupling transform of the map (inverse != 0: the inverse map) finds NONE of its
+ * coordinates inside the tail bound: evaluated on a one-sample batch the reference's RQS raises ValueError('No input
+ * values') there (networks.py:464-465; caught as "skip this proposal" at nnest/sampler.py:320-324).  Always 0 for the
+ * affine-coupling flow.  z [dev] n x d with strides, flags [dev] int32 n.
+ */
+int nnb_flow_empty_halves(nnb_handle* h, const float* z, int64_t z_rs, int64_t z_cs, int inverse, int* flags, int64_t n,
+                          void* stream);
 
 /*
  * Flow maps (replace Trainer.inverse / Trainer.forward, nnest/trainer.py:247-269 ->

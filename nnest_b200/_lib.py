@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libnnb.so')
 
-NNB_ABI_VERSION = 9
+NNB_ABI_VERSION = 10
 NNB_MAX_DIM = 128
 NNB_MAX_BLOCKS = 16
 
@@ -67,6 +67,9 @@ SYMBOLS = {
     'nnb_destroy': (None, [C.c_void_p]),
     'nnb_last_error': (C.c_char_p, [C.c_void_p]),
     'nnb_set_flow': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_size_t]),
+    'nnb_set_flow_spline': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _fp, C.c_size_t]),
+    'nnb_flow_empty_halves': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
+                                        C.c_void_p]),
     'nnb_flow_inverse': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                    C.c_void_p, C.c_int64, C.c_void_p]),
     'nnb_flow_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,

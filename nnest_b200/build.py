@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 OBJDIR = os.path.join(LIBDIR, 'obj')
 LIB = os.path.join(LIBDIR, 'libnnb.so')
-UNITS = ['nnb_api.cu', 'nnb_tc.cu', 'nnb_tc_d2.cu', 'nnb_tc_d10.cu', 'nnb_tc_d30.cu', 'nnb_tc_d50.cu', 'nnb_warp.cu', 'nnb_train.cu', 'nnb_stats.cu', 'nnb_h16.cu', 'nnb_h32.cu', 'nnb_h64.cu']
+UNITS = ['nnb_api.cu', 'nnb_tc.cu', 'nnb_tc_d2.cu', 'nnb_tc_d10.cu', 'nnb_tc_d30.cu', 'nnb_tc_d50.cu', 'nnb_warp.cu', 'nnb_spline.cu', 'nnb_train.cu', 'nnb_stats.cu', 'nnb_h16.cu', 'nnb_h32.cu', 'nnb_h64.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 NVCC_FLAGS = ARCH + ['-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC', '-Xptxas', '-v'] + \
     os.environ.get('NNB_EXTRA_NVCC_FLAGS', '').split()

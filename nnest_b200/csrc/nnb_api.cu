@@ -69,6 +69,7 @@ extern "C" void nnb_destroy(nnb_handle* h) {
   if (h->d_weights) cudaFree(h->d_weights);
   if (h->d_weights_tc) cudaFree(h->d_weights_tc);
   if (h->d_weights_warp) cudaFree(h->d_weights_warp);
+  if (h->d_weights_spline) cudaFree(h->d_weights_spline);
   if (h->d_step_counts) cudaFree(h->d_step_counts);
   if (h->d_target) cudaFree(h->d_target);
   if (h->d_ctrl) cudaFree(h->d_ctrl);
@@ -161,6 +162,7 @@ extern "C" int nnb_set_flow(nnb_handle* h, int d, int hidden, int num_layers, in
   NNB_CUDA(h, cudaMemcpy(h->d_weights, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
   h->flow = f;
   h->has_flow = true;
+  h->flow_is_spline = false;
   int rc = nnb_tc_pack(h, weights);
   if (rc) return rc;
   return nnb_warp_pack(h, weights);
@@ -235,6 +237,7 @@ static int flow_dispatch(nnb_handle* h, const float* in, int64_t irs, int64_t ic
   if (n == 0) return NNB_OK;
   NNB_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->flow_is_spline) return nnb_spline_flow(h, INV, in, irs, ics, out, ors, ocs, logdet, nullptr, n, st);
   switch (h->flow.H) {
     case 16: return LaunchH<16>::flow(h, INV, in, irs, ics, out, ors, ocs, logdet, n, st);
     case 32: return LaunchH<32>::flow(h, INV, in, irs, ics, out, ors, ocs, logdet, n, st);
@@ -302,6 +305,9 @@ extern "C" int nnb_mcmc_init(nnb_handle* h, const nnb_mcmc_init_args* a, void* s
   p.init_u = a->init_u; p.init_z = a->init_z; p.init_logl = a->init_logl;
   p.seed_lo = (unsigned int)(a->seed & 0xffffffffu); p.seed_hi = (unsigned int)(a->seed >> 32);
   p.chain_offset = a->chain_offset; p.start_try = a->start_try; p.ctrl = h->d_ctrl;
+  if (h->flow_is_spline) {
+    rc = nnb_spline_init(h, p, st);
+  } else
   switch (h->flow.H) {
     case 16: rc = LaunchH<16>::init(h, p, st); break;
     case 32: rc = LaunchH<32>::init(h, p, st); break;
@@ -355,7 +361,20 @@ extern "C" int nnb_mcmc_run(nnb_handle* h, const nnb_mcmc_args* a, void* stream)
   if (a->impl == NNB_IMPL_WARP && !h->warp_ok)
     return fail(h, NNB_ERR_UNSUPPORTED, "the 16-lanes-per-chain kernel needs hidden_dim == 16 and scale == ''");
   bool use_warp = false;
-  if (a->steps > 0 && h->warp_ok && (a->impl == NNB_IMPL_WARP || (a->impl == NNB_IMPL_AUTO && n <= nnb_warp_capacity(h)))) {
+  if (h->flow_is_spline) {
+    if (a->impl != NNB_IMPL_AUTO && a->impl != NNB_IMPL_FFMA)
+      return fail(h, NNB_ERR_UNSUPPORTED, "flow='spline' runs the FP32 one-thread-per-chain kernel only");
+    if (a->steps > 0) {
+      rc = nnb_spline_mcmc(h, p, a->steps, st);
+      if (rc) return rc;
+    }
+    if (a->launches_out) *a->launches_out = a->steps > 0 ? h->last_launches : 0;
+    if (a->impl_out) *a->impl_out = NNB_IMPL_FFMA;
+    NNB_CUDA(h, cudaGetLastError());
+    if (!a->scale_out && !a->ncall_out && !a->naccept_out) return NNB_OK;
+    return nnb_mcmc_result(h, a->scale_out, a->ncall_out, a->naccept_out, stream);
+  }
+  if (a->steps > 0 && h->warp_ok && (a->impl == NNB_IMPL_WARP || (a->impl == NNB_IMPL_AUTO && n <= nnb_warp_capacity(h) * 3 / 4))) {
     rc = nnb_launch_mcmc_warp(h, p, a->steps, st, &use_warp);
     if (rc) return rc;
     if (!use_warp && a->impl == NNB_IMPL_WARP)

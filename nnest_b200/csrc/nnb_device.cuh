@@ -464,6 +464,24 @@ __device__ __forceinline__ double prior_any(const TargetSmem& tg, const XG& xg, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per-step grid barrier of the persistent (cooperative) MCMC kernels.  The only thing the CTAs exchange is the step's
+// accept count, so arrival and payload travel in ONE 64-bit reduction (arrivals << 32 | accepted): no fence, no second
+// word to read back -- two L2 round trips (the RED and one successful poll) instead of five.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_arrive(unsigned long long* word, unsigned int accepted) {
+  atomicAdd(word, (1ull << 32) | (unsigned long long)accepted);
+}
+__device__ __forceinline__ unsigned int grid_wait(const unsigned long long* word, unsigned int n_ctas) {
+  unsigned long long w;
+  for (;;) {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(word) : "memory");
+    if ((unsigned int)(w >> 32) >= n_ctas) break;
+    __nanosleep(20);
+  }
+  return (unsigned int)(w & 0xffffffffull);
+}
+
+// ---------------------------------------------------------------------------------------------
 // CTA-wide helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int block_count(bool pred) { return (unsigned int)__syncthreads_count(pred); }

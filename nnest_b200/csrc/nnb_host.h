@@ -21,11 +21,16 @@ struct nnb_handle {
   bool tc_ok = false;
   nnb::TcFlowDesc tcflow{};
   float* d_weights_tc = nullptr;
+  // neural-spline flow (flow='spline', nnb_spline.cu): parameters stay in global memory
+  bool flow_is_spline = false;
+  int spline_d = 0, spline_hidden = 0, spline_blocks = 0, spline_bins = 0;
+  float spline_bound = 0.f;
+  float* d_weights_spline = nullptr;
   // 16-lanes-per-chain variant (small batches): (s, t) weight pairs interleaved
   bool warp_ok = false;
   nnb::WarpFlowDesc warpflow{};
   float* d_weights_warp = nullptr;
-  unsigned int* d_step_counts = nullptr;   // workspace of the cooperative kernels
+  unsigned long long* d_step_counts = nullptr;   // workspace of the cooperative kernels (per-step barrier words)
   int step_counts_cap = 0;
   int coop_supported = 0;
   long long last_launches = 0;             // kernels launched by the last nnb_mcmc_run
@@ -48,6 +53,10 @@ int nnb_launch_mcmc_tc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st);
 int nnb_warp_pack(nnb_handle* h, const float* weights_natural);                       // nnb_warp.cu
 int nnb_launch_mcmc_warp(nnb_handle* h, McmcParams p, int steps, cudaStream_t st, bool* ran);   // nnb_warp.cu
 long long nnb_warp_capacity(const nnb_handle* h);                                     // nnb_warp.cu
+int nnb_spline_flow(nnb_handle* h, bool inverse, const float* in, int64_t irs, int64_t ics, float* out, int64_t ors,
+                    int64_t ocs, float* logdet, int* empty_out, int64_t n, cudaStream_t st);      // nnb_spline.cu
+int nnb_spline_init(nnb_handle* h, const InitParams& p, cudaStream_t st);              // nnb_spline.cu
+int nnb_spline_mcmc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st);          // nnb_spline.cu
 
 #define NNB_CUDA(h, call)                                                                        \
   do {                                                                                           \

@@ -54,7 +54,8 @@ struct McmcParams {
   Ctrl* ctrl;
   int cpc;                     // chains per CTA (tensor-core kernel)
   int coop;                    // persistent cooperative launch: grid barrier per step (tensor-core kernel)
-  unsigned int* step_counts;   // [nsteps] accepted proposals per step, zeroed by the host (coop mode)
+  unsigned long long* step_counts;   // [nsteps] per-step grid-barrier words, zeroed by the host (coop mode): CTAs that
+                                     // arrived << 32 | accepted proposals -- ONE atomic per CTA carries both
   int total_tiles;             // tensor-core kernel, coop mode: tiles that arrive at the per-step grid barrier
   int tc_jc;                   // tensor-core kernel: Philox blocks of the next step drawn during the accept phase (-1 = default)
 };

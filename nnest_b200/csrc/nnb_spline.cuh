@@ -1,9 +1,12 @@
 // nnb_spline.cuh -- neural-spline flow of the reference (its default flow='spline'), per-sample arithmetic.
 //
-// STATUS: groundwork for SURVEY section 8(f) #3.  This header is NOT yet part of libnnb.so (no kernel includes it and
-// flow='spline' still raises in the Python layer).  The functions are __host__ __device__ so that the arithmetic can be
-// checked on the CPU against goldens recorded from the real reference before any kernel is wrapped around it
-// (oracle/spline_host.cpp compiles this header with g++; tests/test_oracle_spline.py).
+// Used by the kernels of nnb_spline.cu (batched flow maps, chain start, fused MCMC step for flow='spline').  The
+// functions are __host__ __device__ so that the same arithmetic is also checked on the CPU against goldens recorded
+// from the real reference (oracle/spline_host.cpp compiles this header with g++; tests/test_oracle_spline.py).
+// Vectors are addressed with a stride (x[i * xs]): 1 on the host, the CTA width in the kernels (column layout, conflict
+// free).  `empty` (optional) is set when a coupling call finds NONE of its coordinates inside the tail bound: evaluated
+// on a one-sample batch the reference's RQS raises ValueError('No input values') there (networks.py:464-465), which
+// Sampler._mcmc_sample turns into a skipped proposal (sampler.py:320-324).
 //
 // Reference (nnest/networks.py): MLP :401-417, unconstrained_RQS / RQS :425-553, NSF_CL :556-619, Invertible1x1Conv
 // :622-653, ActNorm :656-695, SingleSpeedSpline :698-705 = [ActNorm, 1x1 conv, NSF_CL] x num_blocks, 8 bins, tail bound 3.
@@ -118,12 +121,12 @@ NNB_HD float rqs(float v, const float* raw, int K, float bound, bool inverse, fl
 
 // hidden part of the conditioner MLP: Linear(nin, H) LeakyReLU [Linear(H, H) LeakyReLU] x 2 -> h[H]; returns the pointer
 // to the output layer's weights W3 (o x H) followed by b3
-NNB_HD const float* mlp_hidden(const float* w, int nin, int H, const float* x, float* h) {
+NNB_HD const float* mlp_hidden(const float* w, int nin, int H, const float* x, int xs, float* h) {
   float g[kMaxHidden];
   const float* b = w + H * nin;
   for (int j = 0; j < H; ++j) {
     float a = b[j];
-    for (int i = 0; i < nin; ++i) a += w[j * nin + i] * x[i];
+    for (int i = 0; i < nin; ++i) a += w[j * nin + i] * x[i * xs];
     h[j] = leaky(a);
   }
   w = b + H;
@@ -142,46 +145,50 @@ NNB_HD const float* mlp_hidden(const float* w, int nin, int H, const float* x, f
 
 // transform the `m` coordinates tgt[] conditioned on cond[] (ncond values) with the MLP at `w`
 NNB_HD void couple(const float* w, int ncond, int m, int H, int K, float bound, bool inverse, const float* cond, float* tgt,
-                   float& ld) {
+                   int xs, float& ld, int* empty) {
   float h[kMaxHidden], raw[3 * kMaxBins];
   const int P = 3 * K - 1;
-  const float* w3 = mlp_hidden(w, ncond, H, cond, h);
+  const float* w3 = mlp_hidden(w, ncond, H, cond, xs, h);
   const float* b3 = w3 + m * P * H;
+  int inside = 0;
   for (int j = 0; j < m; ++j) {
-    if (!(tgt[j] >= -bound && tgt[j] <= bound)) continue;   // identity: skip the output layer rows as well
+    const float v = tgt[j * xs];
+    if (!(v >= -bound && v <= bound)) continue;   // identity: skip the output layer rows as well
+    ++inside;
     for (int q = 0; q < P; ++q) {
       const float* row = w3 + (j * P + q) * H;
       float a = b3[j * P + q];
       for (int i = 0; i < H; ++i) a += row[i] * h[i];
       raw[q] = a;
     }
-    tgt[j] = rqs(tgt[j], raw, K, bound, inverse, ld);
+    tgt[j * xs] = rqs(v, raw, K, bound, inverse, ld);
   }
+  if (empty && inside == 0) *empty = 1;
 }
 
 // whole flow on one sample, in place on x[d]; tmp[d] scratch.  Returns log|det|.
-NNB_HD float flow_forward(const Shape& sh, const float* packed, float* x, float* tmp) {
+NNB_HD float flow_forward(const Shape& sh, const float* packed, float* x, float* tmp, int xs = 1, int* empty = nullptr) {
   const int d = sh.d, nlow = sh.nlow(), nup = sh.nup();
   float ld = 0.f;
   for (int k = 0; k < sh.blocks; ++k) {
     const float* p = packed + k * sh.block_floats();
     const float *s = p, *t = p + d, *Wc = p + 2 * d, *ldc = Wc + 2 * d * d;
-    for (int i = 0; i < d; ++i) { tmp[i] = x[i] * expf(s[i]) + t[i]; ld += s[i]; }          // ActNorm
+    for (int i = 0; i < d; ++i) { tmp[i * xs] = x[i * xs] * expf(s[i]) + t[i]; ld += s[i]; }   // ActNorm
     for (int j = 0; j < d; ++j) {                                                            // 1x1 convolution
       float a = 0.f;
-      for (int i = 0; i < d; ++i) a += tmp[i] * Wc[i * d + j];
-      x[j] = a;
+      for (int i = 0; i < d; ++i) a += tmp[i * xs] * Wc[i * d + j];
+      x[j * xs] = a;
     }
     ld += ldc[0];
     const float* f1 = ldc + 1;
     const float* f2 = f1 + sh.mlp_floats(nlow, (3 * sh.K - 1) * nup);
-    couple(f1, nlow, nup, sh.H, sh.K, sh.bound, false, x, x + nlow, ld);                    // upper | lower
-    couple(f2, nup, nlow, sh.H, sh.K, sh.bound, false, x + nlow, x, ld);                    // lower | new upper
+    couple(f1, nlow, nup, sh.H, sh.K, sh.bound, false, x, x + nlow * xs, xs, ld, empty);    // upper | lower
+    couple(f2, nup, nlow, sh.H, sh.K, sh.bound, false, x + nlow * xs, x, xs, ld, empty);    // lower | new upper
   }
   return ld;
 }
 
-NNB_HD float flow_inverse(const Shape& sh, const float* packed, float* z, float* tmp) {
+NNB_HD float flow_inverse(const Shape& sh, const float* packed, float* z, float* tmp, int xs = 1, int* empty = nullptr) {
   const int d = sh.d, nlow = sh.nlow(), nup = sh.nup();
   float ld = 0.f;
   for (int k = sh.blocks - 1; k >= 0; --k) {
@@ -189,15 +196,15 @@ NNB_HD float flow_inverse(const Shape& sh, const float* packed, float* z, float*
     const float *s = p, *t = p + d, *Wci = p + 2 * d + d * d, *ldc = p + 2 * d + 2 * d * d;
     const float* f1 = ldc + 1;
     const float* f2 = f1 + sh.mlp_floats(nlow, (3 * sh.K - 1) * nup);
-    couple(f2, nup, nlow, sh.H, sh.K, sh.bound, true, z + nlow, z, ld);
-    couple(f1, nlow, nup, sh.H, sh.K, sh.bound, true, z, z + nlow, ld);
+    couple(f2, nup, nlow, sh.H, sh.K, sh.bound, true, z + nlow * xs, z, xs, ld, empty);
+    couple(f1, nlow, nup, sh.H, sh.K, sh.bound, true, z, z + nlow * xs, xs, ld, empty);
     for (int j = 0; j < d; ++j) {
       float a = 0.f;
-      for (int i = 0; i < d; ++i) a += z[i] * Wci[i * d + j];
-      tmp[j] = a;
+      for (int i = 0; i < d; ++i) a += z[i * xs] * Wci[i * d + j];
+      tmp[j * xs] = a;
     }
     ld -= ldc[0];
-    for (int i = 0; i < d; ++i) { z[i] = (tmp[i] - t[i]) * expf(-s[i]); ld -= s[i]; }
+    for (int i = 0; i < d; ++i) { z[i * xs] = (tmp[i * xs] - t[i]) * expf(-s[i]); ld -= s[i]; }
   }
   return ld;
 }

@@ -336,7 +336,8 @@ static __device__ __noinline__ double tc_prior(TargetDesc td, const double* td_s
 }
 
 // shared-memory carve-up (bytes): [tc weights][target doubles][y: ntiles*d*128 f][zp: ntiles*d*128 f]
-//   [nz: ntiles*d*128 f][ldp: ntiles*(NPART + 1)*128 f][flag: ntiles*128 i][mbar: 4 x 8][tmem base 8][red 32 x 4]
+//   [nz: ntiles*d*128 f][ldp: ntiles*(NPART + 1)*128 f][flag: ntiles*128 i][mbar: 8 x 8][tmem base 8][red 32 x 4]
+//   [weight mbarriers: NNB_MAX_BLOCKS x 8]
 template <int MODE, int NPART, int DD>
 __global__ void __launch_bounds__(kTcMaxTiles * 128 * NPART, 1)
 mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, const double* __restrict__ tgt_g,
@@ -358,13 +359,24 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   int* flag_all = reinterpret_cast<int*>(ldp_all + (size_t)ntiles * (NPART + 1) * 128);
   uint64_t* mbars = reinterpret_cast<uint64_t*>(flag_all + (size_t)ntiles * 128);
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(mbars + 2 * kTcMaxTiles);
+  uint64_t* wbars = reinterpret_cast<uint64_t*>(tmem_base_s + 2 + 32);   // one mbarrier per coupling block's weights
 
-  {
-    const float4* s4 = reinterpret_cast<const float4*>(wglob);
-    float4* d4 = reinterpret_cast<float4*>(wsm);
-    for (int i = threadIdx.x; i < f.total_floats / 4; i += blockDim.x) d4[i] = s4[i];
-    for (int i = threadIdx.x; i < nd; i += blockDim.x) td_s[i] = tgt_g[i];
+  // Weights: TMA bulk copies (cp.async.bulk -> UBLKCP), one per coupling block in the order the flow inverse needs them
+  // (last block first), each completing on its own mbarrier.  They land while the CTA allocates TMEM, loads the chains'
+  // state and draws the first step's noise; the wait sits in front of the step loop.
+  const int nblk_w = DD > 0 ? 3 : f.B;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < nblk_w; ++k) tc::mbar_init(&wbars[k], 1);
+    tc::mbar_fence_init();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int k = nblk_w - 1; k >= 0; --k) {
+      const int off = f.off[k];
+      const uint32_t bytes = 4u * (uint32_t)((k + 1 < nblk_w ? f.off[k + 1] : f.total_floats) - off);
+      tc::mbar_expect_tx(&wbars[k], bytes);
+      tc::tma_bulk_g2s(wsm + off, wglob + off, bytes, &wbars[k]);
+    }
   }
+  for (int i = threadIdx.x; i < nd; i += blockDim.x) td_s[i] = tgt_g[i];
   TargetSmem tg;
   target_bind(tg, td, td_s);
 
@@ -382,7 +394,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
     for (int i = 0; i < 2 * kTcMaxTiles; ++i) tc::mbar_init(&mbars[i], 1);
     tc::mbar_fence_init();
   }
-  // weights were written through the generic proxy; the tensor core reads them through the async proxy
+  // (the TMA writes the weights through the async proxy, which is also how the tensor core reads them)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc::fence_before_sync();
   __syncthreads();
@@ -480,6 +492,8 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   const bool philox_u = p.replay_uniforms == nullptr;
   if (tile_active && active && philox) gen_normals(part, nj, NPART, p.step_offset + (unsigned int)(p.s0 + 1), p.s0);
   if (tile_active && active && philox_u && part == NPART - 1) gen_uniform(p.step_offset + (unsigned int)(p.s0 + 1), p.s0);
+  // weights have landed (each thread observes every block's mbarrier: phase 0 completes when its bytes are in)
+  for (int k = nblk_w - 1; k >= 0; --k) tc::mbar_wait(&wbars[k], 0u);
   // prior box on the flow's own coordinates (nested sampling): tested inside the output epilogues of the flow
   const bool fast_box = MODE == NNB_MODE_HARD && tg.desc.prior_kind == NNB_PRIOR_BOX_U && (DD > 0 || f.B >= 2);
 
@@ -639,16 +653,14 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       // Tiles rendezvous inside the CTA through shared-memory atomics (no CTA-wide barrier: the tiles of an SM drift apart
       // freely inside a step); the LAST tile of the CTA to finish the step carries the CTA's count to the grid barrier
       // (all CTAs are co-resident: cooperative launch) and becomes the CTA's poller for this step.  step_counts[si] was
-      // zeroed by the host; `ticket` counts CTA arrivals monotonically.
+      // zeroed by the host: CTA arrivals and the accept count travel in one 64-bit reduction (grid_arrive / grid_wait).
       if (tile_active && tit == 0) {
         if (tile_cnt) atomicAdd(&co_words[2], tile_cnt);
         __threadfence_block();
         if (atomicAdd(&co_words[1], 1u) == (unsigned int)(my_tiles - 1)) {
           co_words[1] = 0u;
           const unsigned int blk = atomicExch(&co_words[2], 0u);
-          if (blk) atomicAdd(&p.step_counts[si], blk);
-          __threadfence();
-          atomicAdd(&p.ctrl->ticket, 1u);
+          grid_arrive(&p.step_counts[si], blk);
           cta_poller = true;
         }
       }
@@ -682,10 +694,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       // next step publishes the new scale to the tile's threads.
       volatile unsigned int* vw = co_words;
       if (cta_poller) {
-        const unsigned int target = (unsigned int)(si + 1) * gridDim.x;
-        while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < target) __nanosleep(64);
-        __threadfence();
-        const unsigned int na = *reinterpret_cast<volatile unsigned int*>(&p.step_counts[si]);
+        const unsigned int na = grid_wait(&p.step_counts[si], gridDim.x);
         if (p.dynamic) {
           int a = (int)vw[4], r = (int)vw[5];
           double sc = *reinterpret_cast<volatile double*>(co_words + 6);
@@ -700,7 +709,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
         __threadfence_block();
         vw[3] = (unsigned int)(si + 1);
       } else {
-        while (vw[3] < (unsigned int)(si + 1)) __nanosleep(128);   // polling costs issue slots the other tiles need
+        while (vw[3] < (unsigned int)(si + 1)) __nanosleep(32);   // polling costs issue slots the other tiles need
       }
     }
   }
@@ -731,7 +740,8 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
 
 __host__ inline size_t tc_smem_bytes(const TcFlowDesc& f, int tdoubles, int ntiles, int npart) {
   return (size_t)f.total_floats * 4 + (size_t)tdoubles * 8 + 3 * (size_t)ntiles * f.d * 128 * 4 +
-         (size_t)ntiles * (npart + 1) * 128 * 4 + (size_t)ntiles * 128 * 4 + 2 * kTcMaxTiles * 8 + 8 + 32 * 4;
+         (size_t)ntiles * (npart + 1) * 128 * 4 + (size_t)ntiles * 128 * 4 + 2 * kTcMaxTiles * 8 + 8 + 32 * 4 +
+         NNB_MAX_BLOCKS * 8;
 }
 
 }  // namespace nnb

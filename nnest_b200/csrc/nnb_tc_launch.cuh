@@ -36,10 +36,10 @@ static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t s
     if (h->step_counts_cap < steps) {
       if (h->d_step_counts) cudaFree(h->d_step_counts);
       h->d_step_counts = nullptr;
-      NNB_CUDA(h, cudaMalloc(&h->d_step_counts, sizeof(unsigned int) * steps));
+      NNB_CUDA(h, cudaMalloc(&h->d_step_counts, sizeof(unsigned long long) * steps));
       h->step_counts_cap = steps;
     }
-    NNB_CUDA(h, cudaMemsetAsync(h->d_step_counts, 0, sizeof(unsigned int) * steps, st));
+    NNB_CUDA(h, cudaMemsetAsync(h->d_step_counts, 0, sizeof(unsigned long long) * steps, st));
     p.s0 = 0; p.nsteps = steps; p.coop = 1; p.step_counts = h->d_step_counts;
     long long tiles = 0;   // tiles holding at least one chain
     for (int b = 0; b < grid; ++b) {

@@ -66,7 +66,7 @@ namespace {
 
 // chains per CTA and grid such that every CTA is resident (needed by the per-step grid barrier): spread the batch over
 // all SMs, two CTAs per SM at most (launch bounds); returns false when the batch does not fit
-template <int MODE>
+template <int MODE, int DD>
 bool warp_plan(nnb_handle* h, long long n, int tdoubles, int* cpc_out, int* grid_out, size_t* smem_out) {
   for (int per_sm = 1; per_sm <= 2; ++per_sm) {
     long long cpc = (n + (long long)h->sm_count * per_sm - 1) / ((long long)h->sm_count * per_sm);
@@ -76,8 +76,8 @@ bool warp_plan(nnb_handle* h, long long n, int tdoubles, int* cpc_out, int* grid
     const size_t sm = warp_smem_bytes(h->warpflow, tdoubles, (int)cpc);
     if (sm * per_sm > (size_t)h->max_smem_per_sm || sm > (size_t)h->max_smem) continue;
     int occ = 0;
-    if (nnb_set_smem(mcmc_warp_kernel<MODE>, sm) != cudaSuccess) continue;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mcmc_warp_kernel<MODE>, (int)cpc * kWarpLanes, sm) !=
+    if (nnb_set_smem(mcmc_warp_kernel<MODE, DD>, sm) != cudaSuccess) continue;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mcmc_warp_kernel<MODE, DD>, (int)cpc * kWarpLanes, sm) !=
         cudaSuccess)
       continue;
     const long long grid = (n + cpc - 1) / cpc;
@@ -88,13 +88,13 @@ bool warp_plan(nnb_handle* h, long long n, int tdoubles, int* cpc_out, int* grid
   return false;
 }
 
-template <int MODE>
+template <int MODE, int DD>
 int launch_warp_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t st, bool* ran) {
   const int tdoubles = target_doubles(h->tdesc.d, h->tdesc.n_params);
   int cpc = 0, grid = 0;
   size_t sm = 0;
   *ran = false;
-  if (!warp_plan<MODE>(h, p.n, tdoubles, &cpc, &grid, &sm)) return NNB_OK;
+  if (!warp_plan<MODE, DD>(h, p.n, tdoubles, &cpc, &grid, &sm)) return NNB_OK;
   if (p.dynamic && steps > 1 && !h->coop_supported) return NNB_OK;
   p.cpc = cpc;
   p.s0 = 0; p.nsteps = steps;
@@ -102,13 +102,13 @@ int launch_warp_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t st, bo
     if (h->step_counts_cap < steps) {
       if (h->d_step_counts) cudaFree(h->d_step_counts);
       h->d_step_counts = nullptr;
-      NNB_CUDA(h, cudaMalloc(&h->d_step_counts, sizeof(unsigned int) * steps));
+      NNB_CUDA(h, cudaMalloc(&h->d_step_counts, sizeof(unsigned long long) * steps));
       h->step_counts_cap = steps;
     }
-    NNB_CUDA(h, cudaMemsetAsync(h->d_step_counts, 0, sizeof(unsigned int) * steps, st));
+    NNB_CUDA(h, cudaMemsetAsync(h->d_step_counts, 0, sizeof(unsigned long long) * steps, st));
     p.coop = 1; p.step_counts = h->d_step_counts;
     void* args[] = {(void*)&h->warpflow, (void*)&h->d_weights_warp, (void*)&h->tdesc, (void*)&h->d_target, (void*)&p};
-    NNB_CUDA(h, cudaLaunchCooperativeKernel((const void*)mcmc_warp_kernel<MODE>, dim3(grid), dim3(cpc * kWarpLanes), args,
+    NNB_CUDA(h, cudaLaunchCooperativeKernel((const void*)mcmc_warp_kernel<MODE, DD>, dim3(grid), dim3(cpc * kWarpLanes), args,
                                             sm, st));
   } else if (p.dynamic) {
     // a single step: the scale update after it is the only one; run it through the cooperative path too when possible,
@@ -116,7 +116,7 @@ int launch_warp_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t st, bo
     return NNB_OK;
   } else {
     p.coop = 0; p.step_counts = nullptr;
-    mcmc_warp_kernel<MODE><<<grid, cpc * kWarpLanes, sm, st>>>(h->warpflow, h->d_weights_warp, h->tdesc, h->d_target, p);
+    mcmc_warp_kernel<MODE, DD><<<grid, cpc * kWarpLanes, sm, st>>>(h->warpflow, h->d_weights_warp, h->tdesc, h->d_target, p);
     NNB_CUDA(h, cudaGetLastError());
   }
   h->last_launches = 1;
@@ -127,9 +127,25 @@ int launch_warp_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t st, bo
 }  // namespace
 
 // *ran = false: the batch is outside this kernel's range (too many chains to be co-resident, ...): caller falls back
+template <int DD>
+static int launch_warp_dim(nnb_handle* h, McmcParams p, int steps, cudaStream_t st, bool* ran) {
+  return p.mode == NNB_MODE_MH ? launch_warp_mode<NNB_MODE_MH, DD>(h, p, steps, st, ran)
+                               : launch_warp_mode<NNB_MODE_HARD, DD>(h, p, steps, st, ran);
+}
+
 int nnb_launch_mcmc_warp(nnb_handle* h, McmcParams p, int steps, cudaStream_t st, bool* ran) {
-  return p.mode == NNB_MODE_MH ? launch_warp_mode<NNB_MODE_MH>(h, p, steps, st, ran)
-                               : launch_warp_mode<NNB_MODE_HARD>(h, p, steps, st, ran);
+  // the reference's default architecture at the dimensions of the named workloads: fully unrolled kernels
+  static const bool generic_only = getenv("NNB_WARP_GENERIC") != nullptr;
+  if (!generic_only && h->warpflow.L == 1 && h->warpflow.B == 3) {
+    switch (h->warpflow.d) {
+      case 2: return launch_warp_dim<2>(h, p, steps, st, ran);
+      case 10: return launch_warp_dim<10>(h, p, steps, st, ran);
+      case 30: return launch_warp_dim<30>(h, p, steps, st, ran);
+      case 50: return launch_warp_dim<50>(h, p, steps, st, ran);
+      default: break;
+    }
+  }
+  return launch_warp_dim<0>(h, p, steps, st, ran);
 }
 
 // largest batch the kernel holds co-resident (two CTAs of kWarpMaxCpc chains per SM)

@@ -26,7 +26,7 @@
 namespace nnb {
 
 constexpr int kWarpLanes = 16;          // lanes per chain
-constexpr int kWarpMaxCpc = 32;         // chains per CTA (512 threads)
+constexpr int kWarpMaxCpc = 28;         // chains per CTA (448 threads: two CTAs per SM at 72 registers per thread)
 
 __host__ __device__ inline int warp_round16(int v) { return (v + 15) & ~15; }
 __host__ __device__ inline int warp_block_floats(int d, int L, int k) {
@@ -37,7 +37,12 @@ __host__ __device__ inline bool warp_supported(const FlowDesc& f) {
   return f.H == 16 && f.d >= 2 && !(f.flags & (NNB_FLOW_TRANSLATE_ONLY | NNB_FLOW_CONST_SCALE));
 }
 // per-chain shared-memory slot (floats): zc[d] xc[d] zp[d] y[d] tv[d] tm[d] h[2][32]
-__host__ __device__ inline int warp_chain_floats(int d) { return 6 * round4(d) + 64; }
+// The stride is an odd multiple of 16 floats: the two chains of a warp then sit 16 banks apart, so neither their
+// broadcast reads (same index, two addresses) nor their lane-indexed accesses (16 consecutive words each) collide.
+__host__ __device__ inline int warp_chain_floats(int d) {
+  const int c = 6 * round4(d) + 64;
+  return (c & 31) == 16 ? c : ((c + 31) & ~31) + 16;
+}
 __host__ inline size_t warp_smem_bytes(const WarpFlowDesc& f, int tdoubles, int cpc) {
   return (size_t)f.total_floats * 4 + (size_t)((tdoubles + 1) & ~1) * 8 + (size_t)cpc * warp_chain_floats(f.d) * 4 + 64;
 }
@@ -90,12 +95,15 @@ static __device__ __noinline__ double warp_prior(TargetDesc td, const double* td
   return prior_any(tg, row, false);
 }
 
-template <int MODE>
+// DD > 0: x_dim = DD, num_layers = 1 and num_blocks = 3 (the reference's defaults) are compile-time constants: every
+// loop unrolls and every shared-memory offset becomes an immediate (the generic instantiation spends most of its
+// instructions on loop control and address arithmetic: profiles/r2_warp1_*)
+template <int MODE, int DD>
 __global__ void __launch_bounds__(kWarpMaxCpc * kWarpLanes, 2)
 mcmc_warp_kernel(WarpFlowDesc f, const float* __restrict__ wglob, TargetDesc td, const double* __restrict__ tgt_g,
                  McmcParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int d = f.d, L = f.L, nB = f.B;
+  const int d = DD > 0 ? DD : f.d, L = DD > 0 ? 1 : f.L, nB = DD > 0 ? 3 : f.B;
   const int cpc = p.cpc;
   float* wsm = reinterpret_cast<float*>(smem_raw);
   double* td_s = reinterpret_cast<double*>(smem_raw + (size_t)f.total_floats * 4);
@@ -220,14 +228,18 @@ mcmc_warp_kernel(WarpFlowDesc f, const float* __restrict__ wglob, TargetDesc td,
       float ld = 0.f;
       bool bad = false;
       int hb = 0;
+#pragma unroll
       for (int k = nB - 1; k >= 0; --k) {
         const int nin = blk_nin(d, k), i0 = blk_i0(k), nout = blk_nout(d, k), o0 = blk_o0(k);
         const int NO = warp_round16(nout);
-        const float* wb = wsm + f.off[k];
+        const int boff = DD > 0 ? (k > 0 ? warp_block_floats(d, L, 0) : 0) + (k > 1 ? warp_block_floats(d, L, 1) : 0)
+                                : f.off[k];
+        const float* wb = wsm + boff;
         const float2* W1 = reinterpret_cast<const float2*>(wb);
         const float2* b1 = W1 + nin * 16;
         float2 bb = b1[lane];
         float as = bb.x, at = bb.y;
+#pragma unroll
         for (int a = 0; a < nin; ++a) {
           const float v = y[i0 + 2 * a];
           const float2 w = W1[a * 16 + lane];
@@ -239,6 +251,7 @@ mcmc_warp_kernel(WarpFlowDesc f, const float* __restrict__ wglob, TargetDesc td,
         h[16 + lane] = fmaxf(at, 0.f);
         __syncwarp(gmask);
         const float2* Wl = b1 + 16;
+#pragma unroll
         for (int l = 0; l < L; ++l) {
           bb = Wl[256 + lane];
           as = bb.x; at = bb.y;
@@ -252,6 +265,7 @@ mcmc_warp_kernel(WarpFlowDesc f, const float* __restrict__ wglob, TargetDesc td,
         }
         const float2* W3 = Wl;
         const float2* b3 = W3 + 16 * NO;
+#pragma unroll
         for (int o = lane; o < nout; o += kWarpLanes) {
           bb = b3[o];
           as = bb.x; at = bb.y;
@@ -290,8 +304,10 @@ mcmc_warp_kernel(WarpFlowDesc f, const float* __restrict__ wglob, TargetDesc td,
           }
           __syncwarp(gmask);
           float acc = 0.f;
-          if (lane == 0)
+          if (lane == 0) {
+#pragma unroll
             for (int i = 0; i < d - 1; ++i) acc = __fadd_rn(acc, tm[i]);      // left to right, as likelihoods.py:50-51
+          }
           acc = __shfl_sync(gmask, acc, 0, kWarpLanes);
           v = -(double)acc;
           if (!isfinite(v)) v = -INFINITY;
@@ -362,16 +378,11 @@ mcmc_warp_kernel(WarpFlowDesc f, const float* __restrict__ wglob, TargetDesc td,
       if (threadIdx.x == 0) {
         const unsigned int blk = cta_words[0];
         cta_words[0] = 0u;
-        if (blk) atomicAdd(&p.step_counts[si], blk);
-        __threadfence();
-        atomicAdd(&p.ctrl->ticket, 1u);
+        grid_arrive(&p.step_counts[si], blk);
       }
       if (more) draw(step_abs + 1u, s);                   // overlaps the grid barrier
       if (threadIdx.x == 0) {
-        const unsigned int target = (unsigned int)(si + 1) * gridDim.x;
-        while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < target) __nanosleep(32);
-        __threadfence();
-        const unsigned int na = *reinterpret_cast<volatile unsigned int*>(&p.step_counts[si]);
+        const unsigned int na = grid_wait(&p.step_counts[si], gridDim.x);
         if (p.dynamic) {
           if (2ull * na > (unsigned long long)n) co_accept += 1; else co_reject += 1;
           if (co_accept > co_reject) co_scale *= exp(1.0 / (1 + co_accept));

@@ -123,6 +123,25 @@ class Engine(object):
         flat, d, hidden, nl, nb, flags = flatten_state_dict(sd, scale)
         self.set_flow(flat, d, hidden, nl, nb, flags)
 
+    def set_flow_spline(self, packed, d, hidden, num_blocks, num_bins=8, tail_bound=3.0):
+        """Install a neural-spline flow (flow='spline'); `packed` in the layout of include/nnb.h: nnb_set_flow_spline."""
+        packed = np.ascontiguousarray(packed, dtype=np.float32)
+        self._check(self.lib.nnb_set_flow_spline(self.h, d, hidden, num_blocks, num_bins, float(tail_bound),
+                                                 packed.ctypes.data_as(C.POINTER(C.c_float)), packed.size))
+        self.d = d
+        self.flow_shape = (d, hidden, 'spline', num_blocks, num_bins)
+
+    def flow_empty_halves(self, z, inverse=True):
+        """int32 flags (n,): 1 where the reference's RQS would raise ValueError('No input values') on the one-sample batch
+        z[r] (a coupling transform with no coordinate inside the tail bound); always 0 for the affine-coupling flow."""
+        assert z.is_cuda and z.dtype == torch.float32 and z.dim() == 2 and z.shape[1] == self.d
+        flags = torch.zeros((z.shape[0],), dtype=torch.int32, device=z.device)
+        if z.shape[0]:
+            self._check(self.lib.nnb_flow_empty_halves(self.h, _ptr(z), z.stride(0), z.stride(1), 1 if inverse else 0,
+                                                       _ptr(flags), z.shape[0], _stream()))
+            self.gpu_launches += 1
+        return flags
+
     def _flow(self, fn, a):
         assert a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[1] == self.d
         n = a.shape[0]

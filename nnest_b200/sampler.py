@@ -564,6 +564,9 @@ class Sampler(object):
             rnd_u = torch.rand((k,), device=self.device)
             ratio = (log_det_J.double() - self.max_log_det_J).exp().clamp(max=1)
             inside = logp > -1e30
+            if getattr(self.trainer, 'flow_kind', 'nvp') == 'spline':
+                # drawn one at a time, such a candidate makes the reference's inverse raise ValueError -> `continue`
+                inside = inside & (self.engine.flow_empty_halves(z) == 0)
             evaluated = inside & ~(rnd_u > ratio)                    # the turns that reach self.loglike
             good = evaluated & ~(torch.isfinite(logl) & (logl < loglstar)) & (rnd_u < ratio)
             idx = torch.nonzero(good)
@@ -587,9 +590,12 @@ class Sampler(object):
         ncall = 0
         k = int(min(max(64, 4 * getattr(self, '_dens_mean', 16)), 1 << 16))
         while True:
-            x = self.trainer.get_samples(self.trainer.get_prior_samples(k))
+            z = self.trainer.get_prior_samples(k)
+            x = self.trainer.get_samples(z)
             logl, logp = self.engine.loglike(x, want_prior=True)
             inside = logp > -1e30
+            if getattr(self.trainer, 'flow_kind', 'nvp') == 'spline':
+                inside = inside & (self.engine.flow_empty_halves(z) == 0)
             idx = torch.nonzero(inside & (logl > loglstar))
             if idx.numel():
                 j = int(idx[0])

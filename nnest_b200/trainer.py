@@ -25,7 +25,7 @@ import torch
 
 from . import dist
 from .engine import Engine
-from .networks import SingleSpeedNVP
+from .networks import SingleSpeedNVP, SingleSpeedSpline
 from .utils.logger import create_logger
 
 
@@ -116,8 +116,10 @@ class Trainer(object):
                  weight_decay=1e-6,
                  log_level=logging.INFO,
                  engine=None):
-        if flow.lower() != 'nvp':
-            raise NotImplementedError("nnest_b200 accelerates flow='nvp' (RealNVP); got flow=%r" % flow)
+        if flow.lower() not in ('nvp', 'spline'):
+            raise NotImplementedError("nnest_b200 implements flow='nvp' (RealNVP) and flow='spline' (neural spline "
+                                      "flow, the reference's default); got flow=%r" % flow)
+        self.flow_kind = flow.lower()
         if num_slow != 0:
             raise NotImplementedError('fast/slow flows (num_slow > 0) are not on the accelerated path')
         if base_dist is not None:
@@ -134,7 +136,10 @@ class Trainer(object):
         self.num_slow = 0
         self.scale = scale
 
-        self.netG = SingleSpeedNVP(x_dim, hidden_dim, num_blocks, num_layers, scale=scale, device=self.device)
+        if self.flow_kind == 'spline':      # trainer.py:92-98: 8 bins, tail bound 3; num_layers / scale do not apply
+            self.netG = SingleSpeedSpline(x_dim, hidden_dim, num_blocks, num_bins=8, tail_bound=3, device=self.device)
+        else:
+            self.netG = SingleSpeedNVP(x_dim, hidden_dim, num_blocks, num_layers, scale=scale, device=self.device)
 
         if load_model:
             self.path = os.path.join(log_dir, load_model)
@@ -154,7 +159,7 @@ class Trainer(object):
         self.fit_log = []
         # fused fitting kernel (nnb_train_epoch): flat parameter vector + Adam moments in state_dict order
         self._arch = (x_dim, hidden_dim, num_layers, num_blocks)
-        self._fused = scale == '' and self.engine.train_supported(*self._arch) \
+        self._fused = self.flow_kind == 'nvp' and scale == '' and self.engine.train_supported(*self._arch) \
             and os.environ.get('NNB_TRAIN_AUTOGRAD', '0') != '1'
         self._lr, self._wd = learning_rate, weight_decay
         self._adam_m = self._adam_v = None
@@ -176,10 +181,26 @@ class Trainer(object):
         """Export the current weights to the CUDA kernels (and to every rank, rank 0's weights win)."""
         if broadcast:
             dist.broadcast_parameters(self.netG, src=0)       # NCCL over NVLink, one flat buffer
+        if self.flow_kind == 'spline':
+            if broadcast and dist.is_distributed():
+                for m in self.netG.flow.flows:               # the fixed permutations are not parameters
+                    if hasattr(m, 'P'):
+                        torch.distributed.broadcast(m.P, src=0)
+            g = self.netG
+            self.engine.set_flow_spline(g.packed_for_kernel(), self.x_dim, g.num_hidden, g.num_blocks, g.num_bins,
+                                        g.tail_bound)
+            return
         self.engine.set_flow_from_state_dict(self.netG.state_dict(), scale=self.scale)
 
-    def load_state_dict(self, sd):
+    def load_state_dict(self, sd, permutations=None):
+        """netG.load_state_dict + export to the kernels.  flow='spline': `permutations` = the fixed P matrices of the 1x1
+        convolutions (the reference does not keep them in the state_dict, networks.py:631); loaded weights count as
+        initialised (no data-dependent ActNorm initialisation afterwards)."""
         self.netG.load_state_dict(sd)
+        if self.flow_kind == 'spline':
+            if permutations is not None:
+                self.netG.set_permutations(permutations)
+            self.netG.mark_initialised()
         self._sync_device()
 
     # ------------------------------------------------------------------------------------------
@@ -316,6 +337,12 @@ class Trainer(object):
         n = x_train.shape[0]
         order = torch.randperm(n, device=x_train.device)
         bs = self.batch_size
+        if n and getattr(self.netG, 'needs_data_init', lambda: False)():
+            # ActNorm's data-dependent initialisation (networks.py:687-693) happens on the first batch the flow sees; done
+            # eagerly here because the training step below is replayed from a CUDA graph
+            with torch.no_grad():
+                first = x_train[order[:bs]]
+                self.netG.forward(first + jitter * torch.randn_like(first))
         total = torch.zeros((), device=x_train.device)
         nfull = n // bs
         if nfull and not l2_norm:
@@ -360,7 +387,12 @@ class Trainer(object):
         return z, log_det_J
 
     def inverse(self, z, to_numpy=False):
-        x, log_det_J = self.engine.flow_inverse(self._as_device(z))
+        z = self._as_device(z)
+        if self.flow_kind == 'spline' and z.shape[0] == 1 and bool(self.engine.flow_empty_halves(z).all()):
+            # RQS on an empty selection (networks.py:464-465): a coupling transform finds no coordinate of the batch inside
+            # the tail bound.  Checked for one-sample batches, the only case in which it happens in practice.
+            raise ValueError('No input values')
+        x, log_det_J = self.engine.flow_inverse(z)
         if to_numpy:
             return x.cpu().numpy(), log_det_J.cpu().numpy()
         return x, log_det_J

@@ -89,7 +89,7 @@ class Target(object):
 
 def mcmc_sample(weights, target, mcmc_steps, noise, step_size=0.0, dynamic_step_size=False,
                 init_samples=None, init_loglikes=None, loglstar=None, init_z=None,
-                record_internals=False):
+                record_internals=False, flow=None):
     """Restatement of Sampler._mcmc_sample.  Returns the reference's 6-tuple
     (samples (N,S+1,d) f32, latent (N,S+1,d) f32, derived (N,S+1,0), loglikes (N,S+1) f64, scale, ncall)
     plus, when record_internals, a dict of per-step arrays (accept masks, log-ratios, ...).
@@ -97,6 +97,19 @@ def mcmc_sample(weights, target, mcmc_steps, noise, step_size=0.0, dynamic_step_
     init_z: start latents for the `init_samples is None` case (the reference draws them from
             netG.prior, sampler.py:276; injected here so every path can share them).
     """
+    global oflow
+    _saved_flow = oflow
+    if flow is not None:                              # e.g. oracle.spline: same flow_forward / flow_inverse signatures
+        oflow = flow
+    try:
+        return _mcmc_sample(weights, target, mcmc_steps, noise, step_size, dynamic_step_size, init_samples,
+                            init_loglikes, loglstar, init_z, record_internals)
+    finally:
+        oflow = _saved_flow
+
+
+def _mcmc_sample(weights, target, mcmc_steps, noise, step_size, dynamic_step_size, init_samples, init_loglikes, loglstar,
+                 init_z, record_internals):
     d = weights.d
     if step_size <= 0.0:
         step_size = 2 / d ** 0.5                       # sampler.py:248-249

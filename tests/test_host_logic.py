@@ -74,4 +74,6 @@ def test_samplers_and_trainer_refuse_to_run_without_a_gpu(tmp_path):
     with pytest.raises(Exception):
         NestedSampler(2, Rosenbrock(2), flow='nvp', log_dir=str(tmp_path), log_level=logging.ERROR)
     with pytest.raises(NotImplementedError):
-        Trainer(2, flow='spline', log_dir=None)
+        Trainer(2, flow='choleksy', log_dir=None)          # only 'nvp' and 'spline' are implemented on the device
+    with pytest.raises(NotImplementedError):
+        Trainer(2, flow='spline', num_slow=1, log_dir=None)
