@@ -61,9 +61,25 @@ def main():
     parts = [torch.empty_like(digest) for _ in range(world)]
     dist.all_gather(parts, digest)
     same = all(torch.equal(p, parts[0]) for p in parts)
+
+    # ---- 3. the DEFAULT strategy (rejection_prior first), every rank with its OWN numpy stream ---------------------
+    # (the rejection phase must gather the ranks' draws and agree on the switch to MCMC, as the reference
+    # does at nested.py:295-298,366-378; otherwise the live sets diverge and the collectives dead-lock)
+    np.random.seed(100 + rank)
+    torch.manual_seed(100 + rank)
+    s3 = NestedSampler(2, Rosenbrock(2), transform=lambda x: 5 * x, flow='nvp', num_live_points=300,
+                       log_dir=os.path.join(os.path.dirname(out_path), 'logs3'), log_level=logging.WARNING, seed=4)
+    s3.run(mcmc_num_chains=128, train_iters=30)
+    digest3 = torch.tensor([s3.logz, s3.h, float(s3.niter), float(s3.samples.sum()), float(s3.total_calls >= 0)],
+                           dtype=torch.float64, device='cuda')
+    parts3 = [torch.empty_like(digest3) for _ in range(world)]
+    dist.all_gather(parts3, digest3)
+    same3 = all(torch.equal(p, parts3[0]) for p in parts3)
     if rank == 0:
         json.dump({'world': world, 'shard_ok': ok_shard, 'ranks_identical': bool(same), 'logz': float(s.logz),
-                   'logzerr': float(s.logzerr), 'niter': int(s.niter)}, open(out_path, 'w'))
+                   'logzerr': float(s.logzerr), 'niter': int(s.niter), 'default_strategy_ranks_identical': bool(same3),
+                   'default_strategy_logz': float(s3.logz), 'default_strategy_logzerr': float(s3.logzerr)},
+                  open(out_path, 'w'))
     dist.destroy_process_group()
 
 

@@ -53,6 +53,11 @@ def _worker(rank, world, port, q):
         for a, b in zip(net.parameters(), ref.parameters()):
             assert torch.equal(a, b)
         assert nd.allreduce_sum_int(rank + 5, dev) == sum(r + 5 for r in range(world))
+        # (3b) ragged shares of the initial live-point likelihoods (contiguous shards, rank order)
+        full = np.random.RandomState(7).normal(size=13)
+        lo, hi = nd.shard_bounds(13, rank, world)
+        assert [nd.shard_bounds(13, r, world) for r in range(world)][-1][1] == 13
+        assert np.array_equal(nd.allgather_ragged(full[lo:hi], 13, dev), full)
         # (4) every rank replays the same bookkeeping on the gathered batch -> identical state everywhere
         logl0 = np.random.RandomState(1).normal(size=16)
         st = onested.NSState(16)

@@ -30,3 +30,7 @@ def test_two_rank_sharding_and_nested_run(tmp_path):
     res = json.load(open(out))
     assert res['world'] == 2 and res['shard_ok'] and res['ranks_identical']
     assert abs(res['logz'] + 5.804) < 0.4 + 3 * res['logzerr']
+    assert res['default_strategy_ranks_identical']
+    assert abs(res['default_strategy_logz'] + 5.804) < 0.4 + 3 * res['default_strategy_logzerr']
+    (tmp_path / 'ok').write_text(json.dumps(res))
+    print('MULTI-GPU RESULT', json.dumps(res))
