@@ -42,10 +42,11 @@ def main(args):
                           batch_size=args.batch_size, log_dir=os.path.join(args.log_dir, 'gaussian'),
                           log_level=logging.INFO if rank == 0 else logging.WARNING, seed=args.seed)
     t0 = time.time()
-    sampler.run(args.mcmc_steps, args.mcmc_num_chains, training, stats_interval=None, train_iters=args.train_iters)
+    sampler.run(args.mcmc_steps, args.mcmc_num_chains, training, stats_interval=None, train_iters=args.train_iters,
+                thin=args.trace_thin)
     elapsed = time.time() - t0
-    burn = args.mcmc_steps // 2
-    tail = sampler.samples[:, burn::args.thin, :d]
+    burn = (args.mcmc_steps // 2) // args.trace_thin
+    tail = sampler.samples[:, burn::max(1, args.thin // args.trace_thin), :d]
     flat = torch.from_numpy(np.ascontiguousarray(tail, dtype=np.float64).reshape(-1, d)).cuda()
     # moments over the chains of ALL ranks: sums are all-reduced (no sample ever leaves its GPU's host)
     stats = torch.cat([flat.sum(0), (flat.T @ flat).reshape(-1),
@@ -88,7 +89,9 @@ if __name__ == '__main__':
     ap.add_argument('--hidden_dim', type=int, default=16)
     ap.add_argument('--num_blocks', type=int, default=3)
     ap.add_argument('--num_layers', type=int, default=1)
-    ap.add_argument('--thin', type=int, default=10)
+    ap.add_argument('--thin', type=int, default=10, help='stride of the states used for the printed moments')
+    ap.add_argument('--trace_thin', type=int, default=1,
+                    help='MCMCSampler.run(thin=...): rows of the trace brought to the host (1 = every state, as the reference)')
     ap.add_argument('--seed', type=int, default=1)
     ap.add_argument('--log_dir', type=str, default='logs')
     main(ap.parse_args())

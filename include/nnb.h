@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 10
+#define NNB_ABI_VERSION 11
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -313,6 +313,13 @@ typedef struct nnb_train_args {
   double* train_loss_sum_out;
   double* val_nll_sum_out;
   int* grid_out;               /* [host] optional: CTAs the epoch kernel ran on */
+  /* Data-parallel fitting over several GPUs (north_star: all-reduce of gradients): with grad_only != 0 the call treats
+   * x_train (n_train rows, batch_size ignored) as THIS rank's share of ONE mini-batch of batch_total samples: it writes
+   * the share's gradient of the mini-batch mean loss to grad_out (required) and adds the share's part of that mean to
+   * train_loss_sum_out; no Adam step, no validation.  The caller all-reduces grad_out over the ranks and applies the
+   * update.  epoch / seed key the jitter noise: give every (rank, step) its own. */
+  int grad_only;
+  int batch_total;
 } nnb_train_args;
 
 int nnb_train_epoch(nnb_handle* h, const nnb_train_args* args, void* stream);

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libnnb.so')
 
-NNB_ABI_VERSION = 10
+NNB_ABI_VERSION = 11
 NNB_MAX_DIM = 128
 NNB_MAX_BLOCKS = 16
 
@@ -57,7 +57,8 @@ class nnb_train_args(C.Structure):
                 ('beta2', C.c_double), ('eps', C.c_double), ('weight_decay', C.c_double), ('step0', C.c_int64),
                 ('params', C.c_void_p), ('adam_m', C.c_void_p), ('adam_v', C.c_void_p), ('n_params', C.c_size_t),
                 ('grad_out', C.c_void_p), ('do_train', C.c_int), ('train_loss_sum_out', _dp),
-                ('val_nll_sum_out', _dp), ('grid_out', C.POINTER(C.c_int))]
+                ('val_nll_sum_out', _dp), ('grid_out', C.POINTER(C.c_int)), ('grad_only', C.c_int),
+                ('batch_total', C.c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/nnb.h declares

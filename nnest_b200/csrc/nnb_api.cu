@@ -157,8 +157,7 @@ extern "C" int nnb_set_flow(nnb_handle* h, int d, int hidden, int num_layers, in
   for (int k = 0; k < num_blocks; ++k) f.cscale[k] = (flags & NNB_FLOW_CONST_SCALE) ? src[k] : 0.f;
   if (smem_bytes(f.total_floats, target_doubles(d, NNB_MAX_LIKE_PARAMS), d, 2) > (size_t)h->max_smem)
     return fail(h, NNB_ERR_UNSUPPORTED, "flow too large for one CTA's shared memory (reduce x_dim / hidden_dim / blocks)");
-  if (h->d_weights) { cudaFree(h->d_weights); h->d_weights = nullptr; }
-  NNB_CUDA(h, cudaMalloc(&h->d_weights, packed.size() * sizeof(float)));
+  NNB_CUDA(h, nnb_reserve(&h->d_weights, &h->weights_cap, packed.size()));
   NNB_CUDA(h, cudaMemcpy(h->d_weights, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
   h->flow = f;
   h->has_flow = true;
@@ -220,8 +219,7 @@ extern "C" int nnb_set_target(nnb_handle* h, int d, const nnb_target* t) {
       ff[3 * d + i] = hi;
     }
   }
-  if (h->d_target) { cudaFree(h->d_target); h->d_target = nullptr; }
-  NNB_CUDA(h, cudaMalloc(&h->d_target, buf.size() * sizeof(double)));
+  NNB_CUDA(h, nnb_reserve(&h->d_target, &h->target_cap, buf.size()));
   NNB_CUDA(h, cudaMemcpy(h->d_target, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
   h->tdesc = td;
   h->has_target = true;

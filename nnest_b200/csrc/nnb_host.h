@@ -15,6 +15,7 @@ struct nnb_handle {
   bool has_flow = false, has_target = false;
   nnb::FlowDesc flow{};
   float* d_weights = nullptr;
+  size_t weights_cap = 0, weights_tc_cap = 0, weights_warp_cap = 0, weights_spline_cap = 0, target_cap = 0;   // floats / doubles allocated
   nnb::TargetDesc tdesc{};
   double* d_target = nullptr;
   // tensor-core (tcgen05) variant of the MCMC kernel: weights pre-split hi/lo in the UMMA layout
@@ -64,6 +65,19 @@ int nnb_spline_mcmc(nnb_handle* h, McmcParams p, int steps, cudaStream_t st);   
     if (e__ != cudaSuccess)                                                                      \
       return nnb_fail((h), NNB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
   } while (0)
+
+// (Re)allocate a device buffer only when it has to grow: cudaFree synchronises the whole device, and the flow weights
+// are re-installed after every retrain (several times per second in a large run).
+template <typename T>
+static inline cudaError_t nnb_reserve(T** ptr, size_t* cap, size_t need) {
+  if (*ptr && *cap >= need) return cudaSuccess;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *cap = 0;
+  cudaError_t e = cudaMalloc(ptr, need * sizeof(T));
+  if (e == cudaSuccess) *cap = need;
+  return e;
+}
 
 template <typename K>
 static inline cudaError_t nnb_set_smem(K kernel, size_t bytes) {

@@ -298,8 +298,7 @@ extern "C" int nnb_set_flow_spline(nnb_handle* h, int d, int hidden, int num_blo
   if (spline_smem_bytes(target_doubles(d, NNB_MAX_LIKE_PARAMS), d) > (size_t)h->max_smem)
     return nnb_fail(h, NNB_ERR_UNSUPPORTED, "x_dim too large for one CTA's shared memory");
   NNB_CUDA(h, cudaSetDevice(h->device));
-  if (h->d_weights_spline) { cudaFree(h->d_weights_spline); h->d_weights_spline = nullptr; }
-  NNB_CUDA(h, cudaMalloc(&h->d_weights_spline, n_floats * sizeof(float)));
+  NNB_CUDA(h, nnb_reserve(&h->d_weights_spline, &h->weights_spline_cap, n_floats));
   NNB_CUDA(h, cudaMemcpy(h->d_weights_spline, packed, n_floats * sizeof(float), cudaMemcpyHostToDevice));
   h->spline_d = d; h->spline_hidden = hidden; h->spline_blocks = num_blocks; h->spline_bins = num_bins;
   h->spline_bound = (float)tail_bound;

@@ -55,8 +55,7 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
       for (int q = 0; q < nout; ++q) bias3[N3 * s + q] = net[s][nat_off + (size_t)d * H + (o0 + 2 * q)];
   }
   if (tc_smem_bytes(t, target_doubles(d, NNB_MAX_LIKE_PARAMS), 1, 2) > (size_t)h->max_smem) return NNB_OK;
-  if (h->d_weights_tc) { cudaFree(h->d_weights_tc); h->d_weights_tc = nullptr; }
-  NNB_CUDA(h, cudaMalloc(&h->d_weights_tc, buf.size() * sizeof(float)));
+  NNB_CUDA(h, nnb_reserve(&h->d_weights_tc, &h->weights_tc_cap, buf.size()));
   NNB_CUDA(h, cudaMemcpy(h->d_weights_tc, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice));
   h->tcflow = t;
   h->tc_ok = true;

@@ -42,6 +42,9 @@ __host__ __device__ inline bool tc_supported(const FlowDesc& f) {
 #ifndef NNB_TC_FAST_TANH
 #define NNB_TC_FAST_TANH 1
 #endif
+#ifndef NNB_TC_SLACK_NOISE
+#define NNB_TC_SLACK_NOISE 0   // 1: draw the next step's noise inside the MMA round trips of the flow (see mcmc_tc_kernel)
+#endif
 // tanh of the s-net.  NNB_TC_FAST_TANH=0: libdevice tanhf (<= 2 ulp).  Default: MUFU ex2/rcp form below.
 __device__ __forceinline__ float tc_tanh(float x) {
 #if NNB_TC_FAST_TANH
@@ -90,8 +93,14 @@ __device__ __forceinline__ void tile_sync(const TcTile& t) { tc::named_bar_sync(
 // (elect.sync: the operands stay in uniform registers, ~23 cycles per tcgen05.mma, csrc/dev/tc_latency.cu), each
 // committing to its own mbarrier.  Only those two warps poll; the other warps sleep on the hardware barrier (letting
 // every warp poll measured slower: the polling costs issue slots).
-template <typename F0, typename F1>
-__device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1) {
+// `slack()` is independent per-thread work that every warp of the tile runs while the tensor core is busy (between the MMA
+// issue and the wait for its completion): the kernel puts one Philox block of the NEXT step's noise there, which takes it
+// off the step's critical path without extra warps or registers.
+struct NoSlack {
+  __device__ __forceinline__ void operator()() const {}
+};
+template <typename F0, typename F1, typename SL>
+__device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1, SL slack) {
   tc::wait_st();
   tc::fence_before_sync();
   tile_sync(t);
@@ -102,6 +111,9 @@ __device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1) {
       tc::mma_commit(t.mbar + t.issuer);
     }
     __syncwarp();
+  }
+  slack();
+  if (t.issuer >= 0) {
     tc::mbar_wait(t.mbar + t.issuer, t.phase);
     __syncwarp();
   }
@@ -176,16 +188,20 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float*
 // Flow inverse of one tile, in place on y (shared memory, stride ys).  Returns this thread's share of
 // log|det dx/dz| of the chain (the sum over the chain's NPART threads is the log-det).  Ends with a tile barrier:
 // afterwards every thread of the tile sees the complete x.
-template <int NPART, int DD>
+// slack(r): work for the r-th MMA round trip of the call (r = 0 .. B (L + 2) - 1); *nrt receives the number of round trips.
+// t_col: TMEM column of the translate net's output (96; 80 when every block transforms at most 16 dims, which leaves
+// columns [96,128) to the kernel).
+template <int NPART, int DD, typename SL>
 __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const float* __restrict__ wsm, uint32_t wsm_u32,
                                                  TcTile& t, float* y, int ys, float* ld_slot, int* bad_slot,
                                                  const float* __restrict__ lof, const float* __restrict__ hif,
-                                                 bool box_check, bool& bad) {
+                                                 bool box_check, bool& bad, SL slack, uint32_t t_col, int* nrt) {
   // DD > 0: x_dim, num_layers = 1 and num_blocks = 3 (the reference's defaults) are compile-time constants: every loop
   // below unrolls and every shared-memory / TMEM offset becomes an immediate
   const int d = DD > 0 ? DD : f.d, L = DD > 0 ? 1 : f.L, nB = DD > 0 ? 3 : f.B;
   float ld = 0.f;
   bad = false;
+  int trip = 0;
 #pragma unroll
   for (int k = nB - 1; k >= 0; --k) {
     const int nin = blk_nin(d, k), i0 = blk_i0(k), nout = blk_nout(d, k), o0 = blk_o0(k);
@@ -217,7 +233,9 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
                       if (t.single) tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, b_hi, b_lo, K1 / 8, 32, false);
                       else tc::mma_3xtf32_n(t.tmem + 64, t.tmem, t.tmem + 32, b_hi, b_lo, K1 / 8, 16, 4, false);
                     },
-                    [&] { tc::mma_3xtf32_n(t.tmem + 80, t.tmem, t.tmem + 32, b_hi + 256u, b_lo + 256u, K1 / 8, 16, 4, false); });
+                    [&] { tc::mma_3xtf32_n(t.tmem + 80, t.tmem, t.tmem + 32, b_hi + 256u, b_lo + 256u, K1 / 8, 16, 4, false); },
+                    [&] { slack(trip); });
+      ++trip;
     }
     int off = base + 64 * K1;   // -> bias1
     tc_hidden_epilogue<NPART>(t, wsm + off);
@@ -230,7 +248,9 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
                       tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, bs_hi, bs_lo, 2, 16, false);
                       if (t.single) tc::mma_3xtf32(t.tmem + 80, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, 16, false);
                     },
-                    [&] { tc::mma_3xtf32(t.tmem + 80, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, 16, false); });
+                    [&] { tc::mma_3xtf32(t.tmem + 80, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, 16, false); },
+                    [&] { slack(trip); });
+      ++trip;
       tc_hidden_epilogue<NPART>(t, wsm + off + 1024);
       off += 1056;
     }
@@ -241,9 +261,11 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
       tc_round_trip(t,
                     [&] {
                       tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, bs_hi, bs_lo, 2, N3, false);
-                      if (t.single) tc::mma_3xtf32(t.tmem + 96, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, N3, false);
+                      if (t.single) tc::mma_3xtf32(t.tmem + t_col, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, N3, false);
                     },
-                    [&] { tc::mma_3xtf32(t.tmem + 96, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, N3, false); });
+                    [&] { tc::mma_3xtf32(t.tmem + t_col, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, N3, false); },
+                    [&] { slack(trip); });
+      ++trip;
     }
     const float* b3s = wsm + off + 64 * N3;
     const float* b3t = b3s + N3;
@@ -254,7 +276,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
       // one thread per chain, at most 16 transformed dims: both output rows arrive before a single wait
       uint32_t rs[16], rt[16];
       tc::tmem_ld16(t.lane_tmem + 64, rs);
-      tc::tmem_ld16(t.lane_tmem + 96, rt);
+      tc::tmem_ld16(t.lane_tmem + t_col, rt);
       tc::wait_ld();
 #pragma unroll
       for (int c0 = 0; c0 < 16; c0 += 8) {
@@ -285,7 +307,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
     for (int c0 = (NPART == 1 ? 0 : 8 * t.part); c0 < nout; c0 += 8 * NPART) {
       uint32_t rs[8], rt[8], hi[8], lo[8];
       tc::tmem_ld8(t.lane_tmem + 64 + c0, rs);
-      tc::tmem_ld8(t.lane_tmem + 96 + c0, rt);
+      tc::tmem_ld8(t.lane_tmem + t_col + c0, rt);
       tc::wait_ld();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -314,6 +336,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
       tile_sync(t);                             // every thread of the tile now sees the complete x
     }
   }
+  *nrt = trip;
   return ld;
 }
 
@@ -494,6 +517,18 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   if (tile_active && active && philox_u && part == NPART - 1) gen_uniform(p.step_offset + (unsigned int)(p.s0 + 1), p.s0);
   // weights have landed (each thread observes every block's mbarrier: phase 0 completes when its bytes are in)
   for (int k = nblk_w - 1; k >= 0; --k) tc::mbar_wait(&wbars[k], 0u);
+  // Noise of step s+1 drawn INSIDE step s's flow (one thread per chain, at most 32 dims, library Philox stream): every MMA
+  // round trip has a slot in which the tile's warps would only wait for the tensor core; block r of the next step's
+  // Philox normals (4 dims) is drawn in the r-th slot and parked in the chain's own TMEM lane, columns [96, 128) -- free
+  // because with at most 16 transformed dims per block the translate net's output moves to columns [80, 96).  The next
+  // step's proposal reads the 32 columns back with one tcgen05.ld.  (Other shapes: the noise is drawn after the accept
+  // phase, overlapping the grid barrier, as before.)
+  // MEASURED (round 2, B200, c4): correct (the whole GPU suite passes with it) but not faster -- 2.76 ms per refill against
+  // 2.60 ms with the noise drawn in the shadow of the per-step grid barrier: with 3.5 tiles per SM the "idle" slot of one
+  // tile is issue time of the others, and the barrier latency is then exposed.  Kept behind NNB_TC_SLACK_NOISE (default 0).
+  const bool small_d = DD > 0 ? DD <= 32 : d <= 32;
+  const uint32_t t_col = small_d ? 80u : 96u;
+  const bool noise_tmem = NNB_TC_SLACK_NOISE && NPART == 1 && philox && small_d;
   // prior box on the flow's own coordinates (nested sampling): tested inside the output epilogues of the flow
   const bool fast_box = MODE == NNB_MODE_HARD && tg.desc.prior_kind == NNB_PRIOR_BOX_U && (DD > 0 || f.B >= 2);
 
@@ -507,8 +542,28 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       if (NPART > 1 || p.coop) tile_sync(t);   // nz complete (written by both threads of the chain); scale published
       const float scale_f = p.coop ? *reinterpret_cast<volatile float*>(co_scale_s)
                                    : (float)(*reinterpret_cast<volatile double*>(&p.ctrl->scale));
+      // this step's accept uniform: read now, the slot is refilled for the next step while the flow runs
+      const float u01_cur = (active && philox_u && part == NPART - 1) ? *u_slot : 0.f;
+      const bool from_tmem = noise_tmem && s > p.s0 + 1;   // (the first step's noise was drawn into shared memory)
+      if (from_tmem) {
+        // tcgen05.ld is warp-collective: every lane of the (tile-active) warp takes part, idle lanes ignore the values
+        uint32_t r[32];
+        tc::wait_st();                                  // the parked noise was written with (asynchronous) tcgen05.st
+        tc::tmem_ld32(t.lane_tmem + 96, r);
+        tc::wait_ld();
+        if (active) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < d) {
+              const float nv = __uint_as_float(r[i]);
+              nz[i * 128] = nv;                         // kept for the accept update (z' is recomputed from it)
+              y[i * 128] = __fadd_rn(zp[i * 128], __fmul_rn(nv, scale_f));
+            }
+        }
+      }
       // ---- proposal z' = z + scale * N(0, I) (sampler.py:310-316), dims dealt to the chain's threads ----------------
-      if (active) {
+      if (from_tmem && active) {
+      } else if (active) {
         if (kZcur) {   // one thread per chain: the current z lives in shared memory (zp), no global traffic per step
           if (philox) {
             for (int i = 0; i < d; ++i) y[i * 128] = __fadd_rn(zp[i * 128], __fmul_rn(nz[i * 128], scale_f));
@@ -540,13 +595,33 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       if (NPART > 1) tile_sync(t);   // layer 1 reads dims written by the partner thread
       // ---- flow inverse on the tensor cores (all threads of the tile, converged) ----------------------------------
       bool bad_part;
+      int nrt = 0;
+      const bool gen_next = noise_tmem && more;
+      const unsigned int step_next = step_abs + 1u;
+      auto slack = [&](int r) {   // r-th MMA round trip of the step: one Philox block of the next step's noise
+        if (!gen_next) return;
+        if (r < nj) {
+          float nrm[4];
+          philox_normals4(r, step_next, chain, kTagNormal, p.seed_lo, p.seed_hi, nrm);
+          const uint32_t v[4] = {__float_as_uint(nrm[0]), __float_as_uint(nrm[1]), __float_as_uint(nrm[2]),
+                                 __float_as_uint(nrm[3])};
+          tc::tmem_st4(t.lane_tmem + 96 + 4 * r, v);
+          if (p.dump_normals && active)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (4 * r + q < d) p.dump_normals[((size_t)s * ns + (size_t)c) * d + 4 * r + q] = nrm[q];
+        } else if (r == nj) {
+          if (active) gen_uniform(step_next, s);
+        }
+      };
       const float ld_part = tc_flow_inverse<NPART, DD>(f, wsm, wsm_u32, t, y, 128, ldp + part * 128, flag, tg.lof, tg.hif,
-                                                   fast_box, bad_part);
+                                                   fast_box, bad_part, slack, t_col, &nrt);
+      for (int r = nrt; r <= nj; ++r) slack(r);   // fewer round trips than Philox blocks (shallow flows): the rest now
       // ---- accept / reject: thread 0 of the chain; thread 1 starts on the next step's noise -------------------------
       if (active && part == 0) {
         float ld_prop = ld_part;
         if (NPART > 1) ld_prop = ld_part + ldp[128];
-        const float u01 = philox_u ? *u_slot : p.replay_uniforms[(size_t)(s - 1) * ns + (size_t)c];
+        const float u01 = philox_u ? (NPART == 1 ? u01_cur : *u_slot) : p.replay_uniforms[(size_t)(s - 1) * ns + (size_t)c];
         double lp = 0.0, logp_prop = 0.0;
         if (MODE == NNB_MODE_HARD) {
           float lr = __fsub_rn(ld_prop, ld_cur);
@@ -686,8 +761,10 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       }
     }
     // ---- rest of the next step's noise (overlaps the grid barrier) --------------------------------------------------------
-    if (tile_active && active && more && philox) gen_normals(jc + part, nj, NPART, step_abs + 1u, s);
-    if (tile_active && active && more && philox_u && part == NPART - 1) gen_uniform(step_abs + 1u, s);
+    if (!noise_tmem) {
+      if (tile_active && active && more && philox) gen_normals(jc + part, nj, NPART, step_abs + 1u, s);
+      if (tile_active && active && more && philox_u && part == NPART - 1) gen_uniform(step_abs + 1u, s);
+    }
     if (p.coop && tile_active && tit == 0) {
       // The CTA's poller waits for the grid-wide count and updates the CTA's copy of (scale, accept, reject) -- identical
       // in every CTA; the other tile leaders wait for the epoch word in shared memory.  The tile barrier at the top of the

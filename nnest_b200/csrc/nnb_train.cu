@@ -56,7 +56,7 @@ extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* str
   if (a->n_params != (size_t)P) return nnb_fail(h, NNB_ERR_ARG, "n_params does not match (x_dim, hidden_dim, num_layers, num_blocks)");
   if (!a->params) return nnb_fail(h, NNB_ERR_ARG, "params is NULL");
   if (a->do_train) {
-    if (!a->adam_m || !a->adam_v) return nnb_fail(h, NNB_ERR_ARG, "adam_m / adam_v are NULL");
+    if (!a->grad_only && (!a->adam_m || !a->adam_v)) return nnb_fail(h, NNB_ERR_ARG, "adam_m / adam_v are NULL");
     if (a->n_train < 0 || (a->n_train > 0 && !a->x_train)) return nnb_fail(h, NNB_ERR_ARG, "x_train");
     if (a->batch_size < 1) return nnb_fail(h, NNB_ERR_ARG, "batch_size must be >= 1");
     if (a->n_train >= (1ll << 32)) return nnb_fail(h, NNB_ERR_ARG, "n_train must be < 2^32");
@@ -64,7 +64,9 @@ extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* str
   if (a->n_valid < 0 || (a->n_valid > 0 && !a->x_valid)) return nnb_fail(h, NNB_ERR_ARG, "x_valid");
   NNB_CUDA(h, cudaSetDevice(h->device));
 
-  long long work = a->do_train ? (long long)a->batch_size : (long long)a->n_valid;
+  const bool grad_only = a->do_train && a->grad_only;
+  if (grad_only && (!a->grad_out || a->n_train <= 0)) return nnb_fail(h, NNB_ERR_ARG, "grad_only needs grad_out and n_train > 0");
+  long long work = a->do_train ? (grad_only ? (long long)a->n_train : (long long)a->batch_size) : (long long)a->n_valid;
   if (a->do_train && a->n_train < work) work = a->n_train;
   long long g = (work + kTrainThreads - 1) / kTrainThreads;
   if (g < 1) g = 1;
@@ -89,8 +91,9 @@ extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* str
   TrainParams p{};
   p.d = d; p.B = B; p.P = P; p.netP = netP;
   p.x_train = a->x_train; p.n_train = a->n_train; p.perm = (const long long*)a->perm;
-  p.batch_size = a->batch_size;
-  p.x_valid = a->x_valid; p.n_valid = a->n_valid;
+  p.batch_size = grad_only ? (int)a->n_train : a->batch_size;
+  p.x_valid = grad_only ? nullptr : a->x_valid; p.n_valid = grad_only ? 0 : a->n_valid;
+  p.grad_only = grad_only ? 1 : 0; p.batch_total = a->batch_total;
   p.noise = a->noise; p.jitter = (float)a->jitter;
   p.seed_lo = (unsigned int)(a->seed & 0xffffffffu); p.seed_hi = (unsigned int)(a->seed >> 32); p.epoch = a->epoch;
   p.lr = (float)a->lr; p.beta1 = (float)a->beta1; p.beta2 = (float)a->beta2; p.eps = (float)a->eps;

@@ -66,6 +66,8 @@ struct TrainParams {
   TrainCtrl* ctrl;
   float* grad_out;              // optional [P]: data gradient of the LAST mini-batch (natural layout)
   int do_train;
+  int grad_only;                // data-parallel mode: one mini-batch, gradient only (no Adam, no validation)
+  int batch_total;              // grad_only: samples of the whole mini-batch over all ranks (loss / gradient scale)
 };
 
 __host__ __device__ inline int train_net_floats(int d, int H, int L) { return H * d + H + L * (H * H + H) + d * H + d; }
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(kTrainCta, 1) train_epoch_kernel(TrainParams p
   const bool multi = gridDim.x > 1;
   float* m_ptr = multi ? p.mv_priv + (size_t)blockIdx.x * 2 * p.P : p.adam_m;
   float* v_ptr = multi ? m_ptr + p.P : p.adam_v;
-  if (multi && p.do_train) {
+  if (multi && p.do_train && !p.grad_only) {
     for (int q = tid; q < p.P; q += kTrainCta) {
       m_ptr[q] = p.adam_m[q];
       v_ptr[q] = p.adam_v[q];
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(kTrainCta, 1) train_epoch_kernel(TrainParams p
   const long long nmb = p.do_train ? (p.n_train + bs - 1) / bs : 0;
   for (long long mb = 0; mb < nmb; ++mb) {
     const long long cnt = (p.n_train - mb * bs) < bs ? (p.n_train - mb * bs) : bs;   // DataLoader keeps the short tail
-    const float inv_bs = 1.0f / (float)cnt;
+    const float inv_bs = 1.0f / (float)(p.grad_only && p.batch_total > 0 ? (long long)p.batch_total : cnt);
     for (int q = tid; q < Psm; q += kTrainCta) G[q] = 0.f;
     float loss_t = 0.f;
     for (long long s0 = (long long)blockIdx.x * kTrainThreads; s0 < cnt; s0 += (long long)gridDim.x * kTrainThreads) {
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(kTrainCta, 1) train_epoch_kernel(TrainParams p
     if (p.grad_out && mb == nmb - 1 && blockIdx.x == 0)
       for (int q = tid; q < p.P; q += kTrainCta) p.grad_out[q] = G[train_perm_index<H>(q, d, netP, netPp)];
     // ---- Adam (torch.optim.Adam, weight decay added to the gradient), identical in every CTA -----------------------------
-    {
+    if (!p.grad_only) {
       const double step = (double)(p.step0 + mb + 1);
       const float bc1 = (float)(1.0 - pow((double)p.beta1, step));
       const float bc2s = (float)sqrt(1.0 - pow((double)p.beta2, step));
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(kTrainCta, 1) train_epoch_kernel(TrainParams p
     }
   }
   // ---- publish ----------------------------------------------------------------------------------------------------------------
-  if (blockIdx.x == 0 && p.do_train) {
+  if (blockIdx.x == 0 && p.do_train && !p.grad_only) {
     for (int q = tid; q < p.P; q += kTrainCta) {
       p.params[q] = W[train_perm_index<H>(q, d, netP, netPp)];
       if (multi) {

@@ -54,8 +54,7 @@ int nnb_warp_pack(nnb_handle* h, const float* weights) {
     }
   }
   if (warp_smem_bytes(w, target_doubles(d, NNB_MAX_LIKE_PARAMS), 2) > (size_t)h->max_smem) return NNB_OK;
-  if (h->d_weights_warp) { cudaFree(h->d_weights_warp); h->d_weights_warp = nullptr; }
-  NNB_CUDA(h, cudaMalloc(&h->d_weights_warp, buf.size() * sizeof(float)));
+  NNB_CUDA(h, nnb_reserve(&h->d_weights_warp, &h->weights_warp_cap, buf.size()));
   NNB_CUDA(h, cudaMemcpy(h->d_weights_warp, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice));
   h->warpflow = w;
   h->warp_ok = true;

@@ -168,7 +168,7 @@ class Engine(object):
 
     def train_epoch(self, arch, params, adam_m, adam_v, step0, x_train, x_valid, batch_size, perm=None, jitter=0.0,
                     lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, seed=0, epoch=0, noise=None,
-                    grad_out=None, do_train=True):
+                    grad_out=None, do_train=True, grad_only=False, batch_total=0):
         """One epoch of Trainer._train + _validate in one kernel launch (include/nnb.h: nnb_train_epoch).
         arch = (d, hidden, num_layers, num_blocks); params / adam_m / adam_v: flat float32 cuda vectors in
         state_dict order, updated in place.  Returns (train_loss_sum, val_nll_sum, grid)."""
@@ -197,6 +197,7 @@ class Engine(object):
         a.params, a.adam_m, a.adam_v, a.n_params = _ptr(params), _ptr(adam_m), _ptr(adam_v), params.numel()
         a.grad_out = _ptr(grad_out)
         a.do_train = 1 if do_train else 0
+        a.grad_only, a.batch_total = (1 if grad_only else 0), int(batch_total)
         tl, vl, grid = C.c_double(0.0), C.c_double(0.0), C.c_int(0)
         a.train_loss_sum_out, a.val_nll_sum_out, a.grid_out = C.pointer(tl), C.pointer(vl), C.pointer(grid)
         self._check(self.lib.nnb_train_epoch(self.h, C.byref(a), _stream()))

@@ -402,14 +402,17 @@ class NestedSampler(Sampler):
 
         saved_v, saved_logl, saved_logwt = bk.dead_points()
         logz, h, it = bk.logz, bk.h, bk.it
-        logvol = -len(saved_logl) / nlive - np.log(nlive)      # nested.py:487-500
-        fin_logwt = np.empty(nlive)
-        for i in range(nlive):
-            logwt = logvol + active_logl[i]
-            logz_new = np.logaddexp(logz, logwt)
-            h = (np.exp(logwt - logz_new) * active_logl[i] + np.exp(logz - logz_new) * (h + logz) - logz_new)
-            logz = logz_new
-            fin_logwt[i] = logwt
+        # nested.py:487-500: the remaining live points, each with the final volume / nlive -- the reference's scalar loop
+        # as sequential NumPy accumulations + the exact host recurrence for H (bit-identical, see bookkeeping.NSBook.bulk)
+        logvol = -len(saved_logl) / nlive - np.log(nlive)
+        fin_logwt = logvol + active_logl
+        lz = np.logaddexp.accumulate(np.concatenate(([logz], fin_logwt)))
+        lz_prev, lz_new = np.ascontiguousarray(lz[:-1]), np.ascontiguousarray(lz[1:])
+        a_term = np.ascontiguousarray(np.exp(fin_logwt - lz_new) * active_logl)
+        b_term = np.ascontiguousarray(np.exp(lz_prev - lz_new))
+        dp = lambda arr: arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        h = lib.nnb_ns_information(float(h), dp(a_term), dp(b_term), dp(lz_prev), dp(lz_new), nlive)
+        logz = lz_new[-1]
 
         self.logz = logz
         self.h = h

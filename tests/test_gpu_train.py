@@ -252,3 +252,27 @@ def test_trainer_recovers_from_a_diverged_epoch(tmp_path):
     assert torch.isfinite(z).all() and torch.isfinite(ld).all()          # weights are still the last good ones
     t.train(x, max_iters=5, jitter=0.0)
     assert np.isfinite(t.best_validation_loss) and t.best_validation_loss <= good * 1.05 + 1e-3
+
+
+def test_gradient_only_shares_sum_to_the_minibatch_gradient(engine):
+    """Data-parallel mode (nnb_train_args.grad_only): the gradients of two ranks' shares of a mini-batch, each scaled by
+    1 / batch_total, add up to the gradient of the whole mini-batch; parameters and Adam moments stay untouched."""
+    g = load('train_d10_big.npz')
+    a = arch(g)
+    x = dev(g['x_train'][:1000])
+    w = dev(flat_of(g, 'sd'))
+    w0 = w.clone()
+    m, v = torch.zeros_like(w), torch.zeros_like(w)
+    full = torch.zeros_like(w)
+    tl, _, _ = engine.train_epoch(a, w.clone(), m, v, 0, x, None, 1000, grad_out=full, **opt_kw(g))
+    parts, loss = [], 0.0
+    for lo, hi in ((0, 430), (430, 1000)):
+        gp = torch.zeros_like(w)
+        tlp, _, _ = engine.train_epoch(a, w, None, None, 0, x[lo:hi], None, hi - lo, grad_out=gp, grad_only=True,
+                                       batch_total=1000, **opt_kw(g))
+        parts.append(gp)
+        loss += tlp
+    assert torch.equal(w, w0)
+    scale = full.abs().max().item()
+    assert (parts[0] + parts[1] - full).abs().max().item() < 2e-6 * scale
+    assert abs(loss - tl) < 1e-5 * abs(tl)
