@@ -383,6 +383,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   uint64_t* mbars = reinterpret_cast<uint64_t*>(flag_all + (size_t)ntiles * 128);
   uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(mbars + 2 * kTcMaxTiles);
   uint64_t* wbars = reinterpret_cast<uint64_t*>(tmem_base_s + 2 + 32);   // one mbarrier per coupling block's weights
+  uint64_t* sbar = wbars + NNB_MAX_BLOCKS;   // per-step hand-off of the new scale from the CTA's poller to the tile leaders
 
   // Weights: TMA bulk copies (cp.async.bulk -> UBLKCP), one per coupling block in the order the flow inverse needs them
   // (last block first), each completing on its own mbarrier.  They land while the CTA allocates TMEM, loads the chains'
@@ -390,6 +391,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   const int nblk_w = DD > 0 ? 3 : f.B;
   if (threadIdx.x == 0) {
     for (int k = 0; k < nblk_w; ++k) tc::mbar_init(&wbars[k], 1);
+    tc::mbar_init(sbar, 1);
     tc::mbar_fence_init();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int k = nblk_w - 1; k >= 0; --k) {
@@ -529,6 +531,8 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   const bool small_d = DD > 0 ? DD <= 32 : d <= 32;
   const uint32_t t_col = small_d ? 80u : 96u;
   const bool noise_tmem = NNB_TC_SLACK_NOISE && NPART == 1 && philox && small_d;
+  // (Also measured and dropped: staggering the tiles of an SM -- odd tiles drawing a step's noise at its start instead of
+  // at the end of the previous step, so that the tiles do not all wait for their MMAs at the same moments: 2.80 ms.)
   // prior box on the flow's own coordinates (nested sampling): tested inside the output epilogues of the flow
   const bool fast_box = MODE == NNB_MODE_HARD && tg.desc.prior_kind == NNB_PRIOR_BOX_U && (DD > 0 || f.B >= 2);
 
@@ -785,8 +789,11 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
         }
         __threadfence_block();
         vw[3] = (unsigned int)(si + 1);
+        tc::mbar_arrive(sbar);                          // completes phase si of the hand-off barrier
       } else {
-        while (vw[3] < (unsigned int)(si + 1)) __nanosleep(32);   // polling costs issue slots the other tiles need
+        // the other tile leaders sleep on the mbarrier (hardware-suspended try_wait) instead of spinning on the epoch
+        // word: the spin loop was 6.7 % of all issued instructions (profiles/r2_tc1_*)
+        tc::mbar_wait(sbar, (uint32_t)(si & 1));
       }
     }
   }
@@ -818,7 +825,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
 __host__ inline size_t tc_smem_bytes(const TcFlowDesc& f, int tdoubles, int ntiles, int npart) {
   return (size_t)f.total_floats * 4 + (size_t)tdoubles * 8 + 3 * (size_t)ntiles * f.d * 128 * 4 +
          (size_t)ntiles * (npart + 1) * 128 * 4 + (size_t)ntiles * 128 * 4 + 2 * kTcMaxTiles * 8 + 8 + 32 * 4 +
-         NNB_MAX_BLOCKS * 8;
+         NNB_MAX_BLOCKS * 8 + 8;
 }
 
 }  // namespace nnb
