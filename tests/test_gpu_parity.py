@@ -367,3 +367,22 @@ def _generic_case(engine, impl, w, d, layers, blocks, steps, n):
     assert rel_err(latent[same], ref[1][same]) < TOL
     assert rel_err(samples[same], ref[0][same]) < TOL
     assert torch.equal(st.z, out['trace_z'][-1]) and torch.equal(st.x, out['trace_x'][-1])
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+def test_long_replay_1024x150_d30_matches_reference(engine, impl):
+    """One long replay recorded from the reference (tests/golden/make_golden_long.py): 1024 chains x 150 steps at the
+    config-4 shape, noise regenerated from the stored seed."""
+    from test_oracle_golden import _long_case, compare_long
+    g, b, normals, uniforms, idx = _long_case()
+    engine.set_flow_from_state_dict({k[3:]: b[k] for k in b.files if k.startswith('sd/')})
+    engine.set_target(30, 0, [], t_scale=5.0, t_shift=0.0, prior_kind=1, prior_lo=-1.0, prior_hi=1.0)
+    au, al = b['active_u'].astype(np.float64), b['active_logl']
+    st, _, _ = engine.mcmc_init(1024, init_u=dev(np.ascontiguousarray(au[idx].astype(np.float32).T)), init_logl=dev(al[idx]))
+    out = engine.mcmc_run(st, int(g['steps']), mode=0, loglstar=float(g['loglstar']), step_size=float(g['step_size']),
+                          dynamic_step_size=False, trace=True, replay=(dev(normals), dev(uniforms)), impl=impl)
+    assert out['impl'] == impl
+    latent = out['trace_z'].permute(2, 0, 1).cpu().numpy()
+    samples = out['trace_x'].permute(2, 0, 1).cpu().numpy()
+    loglikes = out['trace_logl'].permute(1, 0).cpu().numpy()
+    compare_long(g, latent, samples, loglikes, out['ncall'], max_flipped=8)

@@ -152,3 +152,44 @@ def test_nested_bookkeeping_matches_reference():
     assert np.array_equal(loglikes, g['loglikes'])
     with pytest.raises(StopIteration):
         next(it)                                           # every recorded batch was consumed
+
+
+def _long_case():
+    g = load('mcmc_long_rosen30.npz')
+    b = load('bench_c4.npz')
+    rng = np.random.RandomState(int(g['seed']))
+    chains, steps, d = int(g['chains']), int(g['steps']), int(g['d'])
+    normals = rng.normal(size=(steps, chains, d)).astype(np.float32)
+    uniforms = rng.uniform(size=(steps, chains)).astype(np.float32)
+    idx = rng.randint(0, 1024, size=chains)
+    assert np.array_equal(idx, g['idx'])
+    return g, b, normals, uniforms, idx
+
+
+def compare_long(g, latent, samples, loglikes, ncall, max_flipped):
+    """chains whose whole 150-step move pattern equals the reference's must end within 1e-5 of it; a chain may part ways at
+    a near-tie of an accept test: at most `max_flipped` of 1024"""
+    steps = int(g['steps'])
+    moved_ref = np.unpackbits(g['moved_bits'], axis=1)[:, :steps].astype(bool)
+    moved = np.any(latent[:, 1:] != latent[:, :-1], axis=2)
+    same = np.all(moved == moved_ref, axis=1)
+    assert (~same).sum() <= max_flipped, 'accept pattern differs in %d chains' % (~same).sum()
+    assert rel_err(latent[same, -1], g['last_latent'][same]) < 1e-5
+    assert rel_err(samples[same, -1], g['last_samples'][same]) < 1e-5
+    assert rel_err(loglikes[same, -1], g['last_loglikes'][same]) < 1e-5
+    if (~same).sum() == 0:
+        assert ncall == int(g['ncall'])
+    return int((~same).sum())
+
+
+def test_long_replay_1024x150_d30_matches_reference():
+    """one long replay (1024 chains x 150 steps, d = 30) recorded from the reference."""
+    g, b, normals, uniforms, idx = _long_case()
+    w = oflow.NVPWeights.from_state_dict({k[3:]: b[k] for k in b.files if k.startswith('sd/')}, 30)
+    target = omcmc.Target(olike.Rosenbrock(30), transform=lambda x: 5 * x, prior=olike.UniformPrior(30, -1, 1),
+                          transform_prior=False)
+    au, al = b['active_u'].astype(np.float64), b['active_logl']
+    out = omcmc.mcmc_sample(w, target, int(g['steps']), omcmc.ReplayNoise(normals, uniforms), step_size=float(g['step_size']),
+                            dynamic_step_size=False, init_samples=au[idx], init_loglikes=al[idx],
+                            loglstar=float(g['loglstar']))
+    compare_long(g, out[1], out[0], out[3], out[5], max_flipped=2)
