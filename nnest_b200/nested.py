@@ -102,7 +102,8 @@ class NestedSampler(Sampler):
             rejection_cache_interval=10,
             rejection_enlargement_factor=1.1,
             rejection_trials=None,
-            chain_stats=True):
+            chain_stats=True,
+            diagnostics=False):
 
         if strategy is None or len(strategy) == 0:
             strategy = ['rejection_prior', 'mcmc']
@@ -430,7 +431,10 @@ class NestedSampler(Sampler):
                 writer.writerow(['niter', 'ncall', 'logz', 'logzerr', 'h'])
                 writer.writerow([it + 1, total_calls, logz, np.sqrt(h / nlive), h])
             self._save_samples(self.samples, self.loglikes, weights=self.weights)
-            # run diagnostics next to the reference's result files (one row per MCMC refill / per flow fit)
+            self.logger.info("niter: {:d}\n ncall: {:d}\n nsamples: {:d}\n logz: {:6.3f} +/- {:6.3f}\n h: {:6.3f}"
+                             .format(it + 1, int(total_calls), len(self.loglikes), logz, np.sqrt(h / nlive), h))
+        # run diagnostics (NOT part of the reference's layout: only on request): one row per MCMC refill / flow fit
+        if primary and diagnostics:
             with open(os.path.join(self.logs['results'], 'refill_log.csv'), 'w') as f:
                 writer = csv.writer(f)
                 writer.writerow(['iteration', 'loglstar', 'acceptance', 'usable_fraction', 'scale'])
@@ -439,8 +443,6 @@ class NestedSampler(Sampler):
                 writer = csv.writer(f)
                 writer.writerow(['total_epochs', 'samples', 'jitter', 'best_epoch', 'best_validation_loss'])
                 writer.writerows(getattr(self.trainer, 'fit_log', []))
-            self.logger.info("niter: {:d}\n ncall: {:d}\n nsamples: {:d}\n logz: {:6.3f} +/- {:6.3f}\n h: {:6.3f}"
-                             .format(it + 1, int(total_calls), len(self.loglikes), logz, np.sqrt(h / nlive), h))
 
     def _write_checkpoint(self, bk, active_u, active_v, active_logl, active_derived, total_calls, strategy,
                           expired_strategies):

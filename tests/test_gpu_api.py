@@ -233,7 +233,7 @@ def test_run_diagnostics_are_recorded(tmp_path):
     torch.manual_seed(5)
     s = NestedSampler(2, Himmelblau(2), transform=lambda x: 5 * x, num_live_points=300, flow='nvp',
                       log_dir=str(tmp_path), log_level=logging.WARNING)
-    s.run(mcmc_num_chains=200, train_iters=20, strategy=['mcmc'], max_iters=1500)
+    s.run(mcmc_num_chains=200, train_iters=20, strategy=['mcmc'], max_iters=1500, diagnostics=True)
     assert len(s.refill_log) >= 3 and len(s.trainer.fit_log) >= 2
     it, lstar, acc, usable, scale = s.refill_log[-1]
     assert 0.0 < acc < 1.0 and 0.0 < usable <= 1.0 and scale > 0
