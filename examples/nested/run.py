@@ -58,11 +58,13 @@ def main(args):
                 update_interval=args.update_interval, chain_stats=not args.no_chain_stats, max_iters=args.max_iters,
                 strategy=args.strategy.split(',') if args.strategy else None)
     elapsed = time.time() - start_time
+    if not sampler.single_or_primary_process:      # under torchrun: one rank reports
+        return
     print('Run time %s' % datetime.timedelta(seconds=elapsed))
     ana = ANALYTIC.get((name, args.x_dim))
     if name == 'mixture':
         ana = -args.x_dim * np.log(20.0)
-    out = dict(likelihood=name, x_dim=args.x_dim, num_live_points=args.num_live_points,
+    out = dict(likelihood=name, x_dim=args.x_dim, gpus=sampler.mpi_size, num_live_points=args.num_live_points,
                mcmc_num_chains=args.mcmc_num_chains, logz=float(sampler.logz), logzerr=float(sampler.logzerr),
                h=float(sampler.h), niter=int(sampler.niter), ncall=int(sampler.total_calls), seconds=elapsed,
                analytic_logz=ana, sigma=None if ana is None else float((sampler.logz - ana) / sampler.logzerr))

@@ -15,6 +15,29 @@ import torch
 import torch.distributed as dist
 
 
+def ensure_initialized():
+    """The reference probes MPI by itself when a sampler is built (nnest/sampler.py:165-177).  The equivalent here: a
+    process started by torchrun (RANK / WORLD_SIZE / LOCAL_RANK in the environment, world size > 1) joins the default
+    process group -- NCCL with this rank's GPU, gloo without CUDA -- unless the caller has already done so."""
+    import os
+    if not dist.is_available() or dist.is_initialized():
+        return
+    try:
+        world = int(os.environ.get('WORLD_SIZE', '1'))
+    except ValueError:
+        world = 1
+    if world <= 1 or 'RANK' not in os.environ:
+        return
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29500')
+    if torch.cuda.is_available():
+        local = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        dist.init_process_group('gloo')
+
+
 def is_distributed():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 

@@ -113,6 +113,7 @@ class Sampler(object):
         self.sample_prior = sample_prior if callable(sample_prior) else None
 
         # distributed context: one process per GPU (torch.distributed), replaces the reference's mpi4py probe
+        dist.ensure_initialized()
         self.mpi_rank, self.mpi_size = dist.rank_world()
         self.use_mpi = self.mpi_size > 1
         self.single_or_primary_process = self.mpi_rank == 0
