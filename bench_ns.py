@@ -39,7 +39,7 @@ def main(args):
     ns_iters = int(os.environ.get('NNB_NS_ITERS', 3 * nlive))
     train_iters, batch_size = 50, 8192
     steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 1))
+    warmup = max(0, min(args.warmup, 1))
     parts = {}
 
     def timed(obj, name, key, sync=True):
@@ -69,6 +69,8 @@ def main(args):
         timed(s.trainer, '_mean_two_nearest', 'jitter_nn_s')
         timed(s, '_mcmc_refill', 'mcmc_refill_s')
         timed(s, '_refill_to_host', 'gather_d2h_s')
+        timed(s, '_save_samples', 'chain_file_s', sync=False)
+        timed(s, '_write_checkpoint', 'checkpoint_s', sync=False)
         eng = s.engine
         orig_epoch = eng.train_epoch
 

@@ -43,6 +43,8 @@ struct nnb_handle {
   float* d_train_ws = nullptr;    // gradient exchange buffers + per-CTA Adam moments (several CTAs per mini-batch)
   size_t train_ws_floats = 0;
   double* d_nn_part = nullptr;    // per-block partial sums of nnb_mean_nn_distance
+  float* d_nn_ws = nullptr;       // float32 copy of the rows for the prefilter of nnb_mean_nn_distance
+  size_t nn_ws_floats = 0;
   int nn_part_cap = 0;
   double* d_stats_ws = nullptr;   // chain diagnostics (nnb_stats.cu)
   std::string err;

@@ -1,6 +1,7 @@
 // nnb_train.cu -- host side of the fused flow-fitting kernel (nnb_train.cuh): nnb_train_epoch, nnb_mean_nn_distance.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -141,7 +142,32 @@ extern "C" int nnb_mean_nn_distance(nnb_handle* h, const double* x, int64_t n, i
     h->nn_part_cap = grid;
   }
   double* acc = h->d_nn_part;
-  if (d <= 16) {
+  static const bool f64_only = getenv("NNB_NN_F64") != nullptr;
+  if (d <= 32 && !f64_only) {
+    // float32 prefilter + exact float64 refinement (same result as the brute force, ~2.5x faster)
+    const int DP = d <= 8 ? 8 : (d <= 16 ? 16 : 32);
+    // candidate splits: enough blocks for ~8 per SM
+    int splits = (int)((8ll * h->sm_count + grid - 1) / grid);
+    if (splits < 1) splits = 1;
+    if (splits > 16) splits = 16;
+    const size_t nbest = (size_t)splits * n * 2;     // doubles, counted in floats
+    const size_t need = (size_t)n * DP + 8 + nbest;
+    if (h->nn_ws_floats < need) {
+      if (h->d_nn_ws) cudaFree(h->d_nn_ws);
+      h->d_nn_ws = nullptr;
+      NNB_CUDA(h, cudaMalloc(&h->d_nn_ws, need * sizeof(float)));
+      h->nn_ws_floats = need;
+    }
+    unsigned int* mx = reinterpret_cast<unsigned int*>(h->d_nn_ws + (size_t)n * DP);
+    NNB_CUDA(h, cudaMemsetAsync(mx, 0, sizeof(unsigned int), st));
+    nn_prepare_kernel<<<h->sm_count * 4, 256, 0, st>>>(x, n, d, DP, h->d_nn_ws, mx);
+    double* best = reinterpret_cast<double*>(h->d_nn_ws + (((size_t)n * DP + 4 + 1) & ~(size_t)1));   // 8-byte aligned
+    const dim3 g2(grid, splits);
+    if (DP == 8) nn_min_dist_f32_kernel<8><<<g2, 128, 0, st>>>(x, h->d_nn_ws, n, d, mx, best);
+    else if (DP == 16) nn_min_dist_f32_kernel<16><<<g2, 128, 0, st>>>(x, h->d_nn_ws, n, d, mx, best);
+    else nn_min_dist_f32_kernel<32><<<g2, 128, 0, st>>>(x, h->d_nn_ws, n, d, mx, best);
+    nn_reduce_kernel<<<grid, 128, 0, st>>>(best, n, splits, acc);
+  } else if (d <= 16) {
     nn_min_dist_kernel<16><<<grid, 128, 128 * 16 * sizeof(double), st>>>(x, n, d, acc);
   } else if (d <= 32) {
     nn_min_dist_kernel<32><<<grid, 128, 128 * 32 * sizeof(double), st>>>(x, n, d, acc);

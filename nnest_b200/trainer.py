@@ -217,14 +217,16 @@ class Trainer(object):
         samples = np.asarray(samples)
 
         if self.path:
-            np.save(os.path.join(self.path, 'data', 'originals.npy'), samples)
+            self._save_originals(samples)
+        # one upload of the (float64) samples serves the jitter search and the train / validation split
+        x64 = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)).to(self.device)
 
         if jitter < 0:
             # trainer.py:147-150: 0.2 x the mean of the two nearest "neighbour" distances of every sample, the first
             # being the sample itself (distance 0).  The reference builds a k-d tree on the host, which degenerates to
             # brute force in more than a few dimensions; the same quantity is computed exactly (float64, direct
             # differences) on the device in row blocks.
-            training_jitter = .2 * self._mean_two_nearest(samples)
+            training_jitter = .2 * self._mean_two_nearest(samples, x64)
         else:
             training_jitter = jitter
 
@@ -235,8 +237,10 @@ class Trainer(object):
         n = samples.shape[0]
         n_valid = int(math.ceil(validation_fraction * n))      # sklearn train_test_split rounding
         perm = np.random.permutation(n)
-        x_valid = torch.from_numpy(samples[perm[:n_valid]].astype(np.float32)).to(self.device)
-        x_train = torch.from_numpy(samples[perm[n_valid:]].astype(np.float32)).to(self.device)
+        perm_d = torch.from_numpy(perm).to(self.device)
+        x_valid = x64.index_select(0, perm_d[:n_valid]).float()      # samples[perm[:n_valid]].astype(float32)
+        x_train = x64.index_select(0, perm_d[n_valid:]).float()
+        del x64
 
         best_validation_loss = float('inf')
         best_validation_epoch = 0
@@ -309,6 +313,9 @@ class Trainer(object):
                              float(best_validation_loss)))
         _copy_into_params(params, best_state)
         self._sync_device()
+        if getattr(self, '_originals_writer', None) is not None:      # originals.npy is complete when train() returns
+            self._originals_writer.join()
+            self._originals_writer = None
 
     def _fused_epoch(self, flat, x_train, x_valid, jitter, l2_norm):
         """Trainer._train + Trainer._validate (trainer.py:384-418) as one launch of nnb_train_epoch.  The l2 penalty's
@@ -325,10 +332,23 @@ class Trainer(object):
         validation_loss = (vs / n_valid) / n_valid if n_valid else 0.0      # trainer.py:414-418
         return train_loss, validation_loss
 
-    def _mean_two_nearest(self, samples):
+    def _mean_two_nearest(self, samples, x64=None):
         """np.mean(cKDTree(samples).query(samples, 2)[0]): mean over samples of (0 + nearest other sample) / 2."""
-        x = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)).to(self.device)
-        return 0.5 * self.engine.mean_nn_distance(x)
+        if x64 is None:
+            x64 = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)).to(self.device)
+        return 0.5 * self.engine.mean_nn_distance(x64)
+
+    def _save_originals(self, samples):
+        """data/originals.npy (trainer.py:160-161), written by a background thread: at config-4 size it is 16 MB per fit and
+        272 fits per run.  The previous write is joined first, so the file on disk is always a complete array."""
+        import threading
+        prev = getattr(self, '_originals_writer', None)
+        if prev is not None:
+            prev.join()
+        data = np.array(samples, copy=True)
+        path = os.path.join(self.path, 'data', 'originals.npy')
+        self._originals_writer = threading.Thread(target=np.save, args=(path, data), daemon=False)
+        self._originals_writer.start()
 
     def _train(self, epoch, x_train, jitter=0.0, l2_norm=0.0):
         """One epoch (trainer.py:384-403): shuffled mini-batches, jittered inputs, Adam on -mean(log p).  Full batches

@@ -276,3 +276,21 @@ def test_gradient_only_shares_sum_to_the_minibatch_gradient(engine):
     scale = full.abs().max().item()
     assert (parts[0] + parts[1] - full).abs().max().item() < 2e-6 * scale
     assert abs(loss - tl) < 1e-5 * abs(tl)
+
+
+@pytest.mark.parametrize('n,d', [(3000, 2), (5000, 10), (4097, 30), (900, 17)])
+def test_mean_nn_distance_prefilter_is_exact(engine, n, d):
+    """float32 prefilter + float64 refinement == float64 brute force (numpy), also for clustered points far from the origin,
+    duplicated rows (distance 0) and near-ties."""
+    rng = np.random.RandomState(n + d)
+    x = rng.normal(size=(n, d)) * 1e-3 + 0.7                  # a tight cloud away from the origin
+    x[5] = x[6]                                               # an exact duplicate
+    x[7] = x[8] + 1e-9                                        # a near-duplicate below float32 resolution
+    got = engine.mean_nn_distance(torch.from_numpy(x).cuda())
+    best = np.full(n, np.inf)
+    for lo in range(0, n, 512):
+        dd = ((x[lo:lo + 512, None, :] - x[None, :, :]) ** 2).sum(-1)
+        dd[np.arange(min(512, n - lo)), np.arange(lo, min(n, lo + 512))] = np.inf
+        best[lo:lo + 512] = dd.min(1)
+    want = np.sqrt(best).mean()
+    assert abs(got - want) <= 1e-12 * want
