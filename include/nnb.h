@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 11
+#define NNB_ABI_VERSION 12
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -271,6 +271,21 @@ int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, const float* fi
  * b = exp(logz_old - logz_new), zp = logz_old, zn = logz_new (float64, host).  Returns the final h.  Host-side, exact.
  */
 double nnb_ns_information(double h, const double* a, const double* b, const double* zp, const double* zn, int64_t n);
+
+/*
+ * Row movements of a run of nested-sampling iterations (the array side of nnest/nested.py:288-290,432-437 for the iterations
+ * nnb_ns_consume selected), host-side, multi-threaded, exact:
+ *   nnb_gather_rows_f32: out[i][:] = (double) src[idx[i]][:]  for i < n   (new_u = float32 end points of the chains used);
+ *   nnb_ns_apply:        dead_out[i] = prev[i] >= 0 ? new_v[prev[i]] : active_v[worst[i]]   for i < n_ev   (the physical point
+ *                        that sat in slot worst[i] when iteration i started), then for i = 0 .. n_done-1 IN ORDER
+ *                        active_u[worst[i]] = new_u[i], active_v[worst[i]] = new_v[i], active_logl[worst[i]] = new_logl[i]
+ *                        (a later iteration overwrites an earlier one: the last write to a slot wins).
+ * All matrices row-major with d columns.  Return 0 or NNB_ERR_ARG.
+ */
+int nnb_gather_rows_f32(const float* src, int64_t n_src, int d, const int64_t* idx, int64_t n, double* out);
+int nnb_ns_apply(const int64_t* worst, const int64_t* prev, int64_t n_ev, int64_t n_done, int d, const double* new_u,
+                 const double* new_v, const double* new_logl, double* active_u, double* active_v, double* active_logl,
+                 int64_t nlive, double* dead_out);
 
 /*
  * Flow fitting: ONE EPOCH of the reference's Trainer._train + Trainer._validate (nnest/trainer.py:384-418) in one

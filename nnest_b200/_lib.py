@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libnnb.so')
 
-NNB_ABI_VERSION = 11
+NNB_ABI_VERSION = 12
 NNB_MAX_DIM = 128
 NNB_MAX_BLOCKS = 16
 
@@ -84,6 +84,8 @@ SYMBOLS = {
     'nnb_consume_scan': (C.c_int64, [_fp, _fp, _dp, C.c_int64, C.c_int, C.c_double, _ip]),
     'nnb_ns_consume': (C.c_int64, [_dp, C.c_int64, _fp, _fp, _dp, C.c_int64, C.c_int, _ip, C.c_int64, _ip, _ip, _ip, _dp,
                                    _dp, C.POINTER(C.c_int)]),
+    'nnb_gather_rows_f32': (C.c_int, [_fp, C.c_int64, C.c_int, _ip, C.c_int64, _dp]),
+    'nnb_ns_apply': (C.c_int, [_ip, _ip, C.c_int64, C.c_int64, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64, _dp]),
     'nnb_train_epoch': (C.c_int, [C.c_void_p, C.POINTER(nnb_train_args), C.c_void_p]),
     'nnb_train_supported': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     'nnb_mean_nn_distance': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, _dp, C.c_void_p]),

@@ -105,25 +105,30 @@ class NSBook(object):
                                         dp(zp_c), dp(zn_c), n_evid)
         self.logz = lz_new[n_evid - 1]
         # dead points: the physical point sitting in slot `worst` when its iteration started
-        new_u = b_last[chain[:n_done]].astype(np.float64)
-        new_v = np.asarray(transform(new_u), dtype=np.float64).reshape(new_u.shape) if n_done else new_u
-        w, pv = worst[:n_evid], prev[:n_evid]
-        dead = np.array(active_v[w], dtype=np.float64, copy=True)
-        from_batch = pv >= 0
-        dead[from_batch] = new_v[pv[from_batch]]
+        # row movements (gather of the end points, dead points, last-write-wins replacement): exact host routines of the C
+        # ABI, a few threads each (random-row gathers of a 16 MB live set are cache-miss bound)
+        new_u = np.empty((n_done, d), dtype=np.float64)
+        chain_c = np.ascontiguousarray(chain[:n_done])
+        if n_done:
+            rc = lib.nnb_gather_rows_f32(fp(b_last), n_chains, d, ip(chain_c), n_done, dp(new_u))
+            assert rc == 0, rc
+        new_v = np.ascontiguousarray(np.asarray(transform(new_u), dtype=np.float64).reshape(new_u.shape)) if n_done \
+            else new_u
+        new_logl = np.ascontiguousarray(b_logl[chain_c], dtype=np.float64)
+        w = np.ascontiguousarray(worst[:n_evid])
+        pv = np.ascontiguousarray(prev[:n_evid])
+        dead = np.empty((n_evid, d), dtype=np.float64)
+        assert active_u.flags.c_contiguous and active_v.flags.c_contiguous and active_u.dtype == np.float64 \
+            and active_v.dtype == np.float64
+        rc = lib.nnb_ns_apply(ip(w), ip(pv), n_evid, n_done, d, dp(new_u), dp(new_v), dp(new_logl), dp(active_u),
+                              dp(active_v), dp(active_logl), nlive, dp(dead))
+        assert rc == 0, rc
         self.saved_v.append(dead)
         self.saved_logwt.append(np.array(logwt[:n_evid], copy=True))
         self.saved_logl.append(np.array(lstar[:n_evid], copy=True))
         self.last_slots = np.array(worst[:n_done], copy=True)       # (slot, chain) pairs of this call, in order: lets the
         self.last_chains = np.array(chain[:n_done], copy=True)      # caller mirror the replacements elsewhere (device)
         if n_done:
-            # live set: last write to a slot wins
-            wd = worst[:n_done]
-            _, first_rev = np.unique(wd[::-1], return_index=True)
-            lastw = n_done - 1 - first_rev
-            active_u[wd[lastw]] = new_u[lastw]
-            active_v[wd[lastw]] = new_v[lastw]
-            active_logl[wd[lastw]] = b_logl[chain[:n_done]][lastw]
             self.logvol = lv[n_done]
             self.fraction_remain = frac[n_done - 1]
             self.it += n_done

@@ -499,6 +499,61 @@ extern "C" int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, cons
   return k;
 }
 
+// ---- row movements of a run of nested-sampling iterations (include/nnb.h) -----------------------------------------------
+namespace {
+template <typename F>
+void parallel_for(int64_t n, int64_t grain, F fn) {   // fn(begin, end, thread index, thread count)
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, 8u), (n + grain - 1) / grain));
+  if (nt <= 1) { fn((int64_t)0, n, 0, 1); return; }
+  std::vector<std::thread> th;
+  const int64_t per = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) th.emplace_back([=] { fn(std::min(n, t * per), std::min(n, (t + 1) * per), t, nt); });
+  for (auto& x : th) x.join();
+}
+}  // namespace
+
+extern "C" int nnb_gather_rows_f32(const float* src, int64_t n_src, int d, const int64_t* idx, int64_t n, double* out) {
+  if (!src || !idx || !out || d <= 0 || n < 0) return NNB_ERR_ARG;
+  for (int64_t i = 0; i < n; ++i)
+    if (idx[i] < 0 || idx[i] >= n_src) return NNB_ERR_ARG;
+  parallel_for(n, 4096, [=](int64_t a, int64_t b, int, int) {
+    for (int64_t i = a; i < b; ++i) {
+      const float* s = src + idx[i] * d;
+      double* o = out + i * d;
+      for (int j = 0; j < d; ++j) o[j] = (double)s[j];
+    }
+  });
+  return NNB_OK;
+}
+
+extern "C" int nnb_ns_apply(const int64_t* worst, const int64_t* prev, int64_t n_ev, int64_t n_done, int d,
+                            const double* new_u, const double* new_v, const double* new_logl, double* active_u,
+                            double* active_v, double* active_logl, int64_t nlive, double* dead_out) {
+  if (!worst || !prev || !active_u || !active_v || !active_logl || !dead_out || d <= 0 || n_ev < 0 || n_done < 0 ||
+      n_done > n_ev || (n_done > 0 && (!new_u || !new_v || !new_logl)))
+    return NNB_ERR_ARG;
+  for (int64_t i = 0; i < n_ev; ++i)
+    if (worst[i] < 0 || worst[i] >= nlive || prev[i] >= n_done || prev[i] >= i) return NNB_ERR_ARG;
+  const size_t row = sizeof(double) * (size_t)d;
+  // dead points first: they read the live set as it was before this call's replacements
+  parallel_for(n_ev, 4096, [=](int64_t a, int64_t b, int, int) {
+    for (int64_t i = a; i < b; ++i)
+      memcpy(dead_out + i * d, prev[i] >= 0 ? new_v + prev[i] * d : active_v + worst[i] * d, row);
+  });
+  // replacements in iteration order; thread t owns the slots with slot % T == t, so "the last write wins" holds per slot
+  parallel_for(n_done >= 8192 ? 8 * 16384 : (n_done > 0 ? 1 : 0), 16384, [=](int64_t, int64_t, int t, int nt) {
+    for (int64_t i = 0; i < n_done; ++i) {
+      const int64_t s = worst[i];
+      if ((int)(s % nt) != t) continue;
+      memcpy(active_u + s * d, new_u + i * d, row);
+      memcpy(active_v + s * d, new_v + i * d, row);
+      active_logl[s] = new_logl[i];
+    }
+  });
+  return NNB_OK;
+}
+
 // Chain files of the reference (nnest/sampler.py:494-511): one row per sample, every number '%.5E', single spaces.
 // Rows are formatted by several host threads into private buffers and written in order.
 extern "C" int64_t nnb_write_chain_text(const char* path, const char* header, const double* table, int64_t rows,
