@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'lib', 'libnnb.so')
+LIB_PATH = os.path.join(HERE, os.environ.get('NNB_LIB_DIR', 'lib'), 'libnnb.so')   # see build.py
 
 NNB_ABI_VERSION = 12
 NNB_MAX_DIM = 128

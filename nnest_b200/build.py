@@ -13,7 +13,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-LIBDIR = os.path.join(HERE, 'lib')
+# NNB_LIB_DIR: a directory (relative to the package) for a variant build, e.g. NNB_EXTRA_NVCC_FLAGS=-DNNB_TC_TIMING
+# NNB_LIB_DIR=lib_timing -- development A/B runs; the product library is lib/libnnb.so
+LIBDIR = os.path.join(HERE, os.environ.get('NNB_LIB_DIR', 'lib'))
 OBJDIR = os.path.join(LIBDIR, 'obj')
 LIB = os.path.join(LIBDIR, 'libnnb.so')
 UNITS = ['nnb_api.cu', 'nnb_tc.cu', 'nnb_tc_d2.cu', 'nnb_tc_d10.cu', 'nnb_tc_d30.cu', 'nnb_tc_d50.cu', 'nnb_warp.cu', 'nnb_spline.cu', 'nnb_train.cu', 'nnb_stats.cu', 'nnb_h16.cu', 'nnb_h32.cu', 'nnb_h64.cu']

@@ -220,6 +220,7 @@ extern "C" int nnb_set_target(nnb_handle* h, int d, const nnb_target* t) {
       ff[2 * d + i] = lo;
       ff[3 * d + i] = hi;
     }
+    h->target_f32.assign(ff, ff + 4 * d);
   }
   NNB_CUDA(h, nnb_reserve(&h->d_target, &h->target_cap, buf.size()));
   NNB_CUDA(h, cudaMemcpy(h->d_target, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));

@@ -306,6 +306,29 @@ struct Transformed {
   }
 };
 
+// Visit coordinates i = i_begin .. d-1 in order: f(i, v(i)).  With x_dim known at compile time (DFIX > 0) the values of 16
+// coordinates are fetched before the first of them is consumed, so that their shared-memory loads are in flight together
+// -- a rolled `for (i) acc = g(acc, v(i))` loop pays one load latency plus the dependent arithmetic PER coordinate
+// (measured: 2 100 cycles for the 30-dimensional Rosenbrock sum of one warp).  The order of the arithmetic is unchanged.
+template <typename T, int DFIX, typename V, typename F>
+__device__ __forceinline__ void for_each_coord(int d, int i_begin, const V& v, F f) {
+  if constexpr (DFIX > 0) {
+    constexpr int CH = 16;
+#pragma unroll
+    for (int i0 = i_begin; i0 < DFIX; i0 += CH) {
+      T c[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (i0 + j < DFIX) c[j] = v(i0 + j);
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (i0 + j < DFIX) f(i0 + j, c[j]);
+    }
+  } else {
+    for (int i = i_begin; i < d; ++i) f(i, v(i));
+  }
+}
+
 // numpy's pairwise summation of v(i)^2-style terms for n <= 128 (np.sum of a contiguous 1-D array).
 template <typename T, typename F>
 __device__ __forceinline__ T np_pairwise_sum(int n, F term) {
@@ -341,13 +364,12 @@ __device__ __forceinline__ double loglike_T(const TargetSmem& tg, const XG& xg) 
     case NNB_LIKE_ROSENBROCK: {  // likelihoods.py:50-51, left-to-right sum in T
       T acc = (T)0;
       T prev = v(0);
-      for (int i = 1; i < d; ++i) {
-        T cur = v(i);
+      for_each_coord<T, DFIX>(d, 1, v, [&](int, T cur) {
         T t1 = A::sub(cur, A::mul(prev, prev));
         T t2 = A::sub((T)1, prev);
         acc = A::add(acc, A::add(A::mul((T)100, A::mul(t1, t1)), A::mul(t2, t2)));
         prev = cur;
-      }
+      });
       out = -(double)acc;
       f32_typed = sizeof(T) == 4;
       break;
@@ -363,11 +385,11 @@ __device__ __forceinline__ double loglike_T(const TargetSmem& tg, const XG& xg) 
     case NNB_LIKE_GAUSSIAN: {  // likelihoods.py:84-86 ; closed form, always float64 like scipy
       double rho = tg.params[0];
       double s1 = 0.0, s2 = 0.0;
-      for (int i = 0; i < d; ++i) {
-        double xi = (double)v(i);
+      for_each_coord<T, DFIX>(d, 0, v, [&](int, T vi) {
+        double xi = (double)vi;
         s1 += xi;
         s2 = fma(xi, xi, s2);
-      }
+      });
       double a = 1.0 - rho, bden = 1.0 - rho + d * rho;
       double logdet = (d - 1) * log(a) + log(bden);
       double quad = (s2 - rho * s1 * s1 / bden) / a;
@@ -432,10 +454,7 @@ __device__ __forceinline__ double prior_T(const TargetSmem& tg, const XG& xg) {
   bool bad = false;
   if (tg.desc.prior_kind == NNB_PRIOR_BOX_U) {
     if (sizeof(xg(0)) == 4) {   // float32 point against pre-rounded float32 bounds: same truth value, no FP64
-      for (int i = 0; i < d; ++i) {
-        float u = (float)xg(i);
-        bad |= (u < tg.lof[i]) | (u > tg.hif[i]);
-      }
+      for_each_coord<float, DFIX>(d, 0, xg, [&](int i, float u) { bad |= (u < tg.lof[i]) | (u > tg.hif[i]); });
     } else {
       for (int i = 0; i < d; ++i) {
         double u = (double)xg(i);
@@ -444,10 +463,10 @@ __device__ __forceinline__ double prior_T(const TargetSmem& tg, const XG& xg) {
     }
   } else {
     Transformed<T, XG> v{tg, xg};
-    for (int i = 0; i < d; ++i) {
-      double t = (double)v(i);
+    for_each_coord<T, DFIX>(d, 0, v, [&](int i, T vi) {
+      double t = (double)vi;
       bad |= (t < tg.lo[i]) | (t > tg.hi[i]);
-    }
+    });
   }
   return bad ? -INFINITY : 0.0;
 }

@@ -3,8 +3,10 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "nnb_kernels.cuh"
+#include "nnb_tc_consts.h"
 #include "nnb_warp_desc.h"
 
 struct nnb_handle {
@@ -22,6 +24,8 @@ struct nnb_handle {
   bool tc_ok = false;
   nnb::TcFlowDesc tcflow{};
   float* d_weights_tc = nullptr;
+  nnb::TcConsts tc_consts{};               // biases of the flow in the kernel-parameter layout (nnb_tc_kernels.cuh)
+  std::vector<float> target_f32;           // tsf | tbf | lof | hif of the current target (host copy, same values as d_target)
   // neural-spline flow (flow='spline', nnb_spline.cu): parameters stay in global memory
   bool flow_is_spline = false;
   int spline_d = 0, spline_hidden = 0, spline_blocks = 0, spline_bins = 0;

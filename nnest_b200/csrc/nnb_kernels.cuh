@@ -58,6 +58,7 @@ struct McmcParams {
                                      // arrived << 32 | accepted proposals -- ONE atomic per CTA carries both
   int total_tiles;             // tensor-core kernel, coop mode: tiles that arrive at the per-step grid barrier
   int tc_jc;                   // tensor-core kernel: Philox blocks of the next step drawn during the accept phase (-1 = default)
+  int tc_stagger;   // tensor-core kernel: start delay of the odd tiles of an SM, cycles
 };
 
 struct SmemView {

@@ -19,6 +19,7 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
   for (int k = 0; k < B; ++k) { t.off[k] = off; off += tc_block_floats(d, L, k); }
   t.total_floats = off;
   std::vector<float> buf((size_t)off, 0.f);
+  TcConsts cst{};
   const size_t net_nat = (size_t)H * d + H + (size_t)L * (H * H + H) + (size_t)d * H + d;
   for (int k = 0; k < B; ++k) {
     const int nin = blk_nin(d, k), i0 = blk_i0(k), nout = blk_nout(d, k), o0 = blk_o0(k);
@@ -32,14 +33,15 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
         for (int a = 0; a < nin; ++a) w1[(size_t)(16 * s + j) * K1 + a] = net[s][(size_t)j * d + (i0 + 2 * a)];
     tc::host_pack_b(w1.data(), 32, K1, K1, 32, K1, dst, dst + 32 * K1);
     float* bias1 = dst + 64 * K1;
+    float* cb = cst.v + tc_cb_off(d, L, k);          // the same biases in the kernel-parameter layout (TcConsts)
     for (int s = 0; s < 2; ++s)
-      for (int j = 0; j < H; ++j) bias1[16 * s + j] = net[s][(size_t)H * d + j];
+      for (int j = 0; j < H; ++j) cb[16 * s + j] = bias1[16 * s + j] = net[s][(size_t)H * d + j];
     float* o = bias1 + 32;
     size_t nat_off = (size_t)H * d + H;
     for (int l = 0; l < L; ++l) {
       for (int s = 0; s < 2; ++s) tc::host_pack_b(net[s] + nat_off, 16, 16, 16, 16, 16, o + 512 * s, o + 512 * s + 256);
       for (int s = 0; s < 2; ++s)
-        for (int j = 0; j < H; ++j) o[1024 + 16 * s + j] = net[s][nat_off + (size_t)H * H + j];
+        for (int j = 0; j < H; ++j) cb[32 + 32 * l + 16 * s + j] = o[1024 + 16 * s + j] = net[s][nat_off + (size_t)H * H + j];
       o += 1056;
       nat_off += (size_t)H * H + H;
     }
@@ -52,12 +54,14 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
     }
     float* bias3 = o + 64 * N3;
     for (int s = 0; s < 2; ++s)
-      for (int q = 0; q < nout; ++q) bias3[N3 * s + q] = net[s][nat_off + (size_t)d * H + (o0 + 2 * q)];
+      for (int q = 0; q < nout; ++q)
+        cb[32 + 32 * L + N3 * s + q] = bias3[N3 * s + q] = net[s][nat_off + (size_t)d * H + (o0 + 2 * q)];
   }
   if (tc_smem_bytes(t, target_doubles(d, NNB_MAX_LIKE_PARAMS), 1, 2) > (size_t)h->max_smem) return NNB_OK;
   NNB_CUDA(h, nnb_reserve(&h->d_weights_tc, &h->weights_tc_cap, buf.size()));
   NNB_CUDA(h, cudaMemcpy(h->d_weights_tc, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice));
   h->tcflow = t;
+  h->tc_consts = cst;
   h->tc_ok = true;
   return NNB_OK;
 }

@@ -56,6 +56,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Long waits (the per-step hand-off of the scale): try_wait with a suspend-time hint.  Without the hint the instruction
+// returns after a few cycles and the loop is a busy spin -- 2.7 % of ALL executed instructions were this TRYWAIT and
+// another 5.4 % its branch / yield (profiles/r2_final_mcmc_tc_kernel: SASS page), issued by the tile leaders, which all
+// sit on scheduler 0.  With the hint the warp is suspended until the phase completes (or the time runs out).
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "NNB_WAITL:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra NNB_DONEL;\n"
+      "bra NNB_WAITL;\n"
+      "NNB_DONEL:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
 // ---- TMA bulk copy global -> shared (cp.async.bulk, SASS: UBLKCP), completion counted in bytes on an mbarrier -------
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

@@ -18,6 +18,7 @@
 #pragma once
 #include "nnb_kernels.cuh"
 #include "nnb_tc.cuh"
+#include "nnb_tc_consts.h"
 
 namespace nnb {
 
@@ -34,17 +35,34 @@ __host__ __device__ inline int tc_block_floats(int d, int L, int k) {
   const int K1 = round8(blk_nin(d, k)), N3 = round16(blk_nout(d, k));
   return 64 * K1 + 32 + L * 1056 + 64 * N3 + 2 * N3;
 }
+// Warp-uniform constants of a step -- the biases of every layer, the prior box and the affine transform in float32 --
+// travel as a KERNEL PARAMETER: parameters live in constant bank 0, and with x_dim fixed at compile time every index
+// below is an immediate, so an `x + bias` reads its second operand straight from c[0x0][imm] -- no load instruction, no
+// shared-memory bandwidth.  (As shared-memory broadcasts these were 258 of the ~630 shared-memory instructions of a
+// proposal at d = 30, on a pipe that moves 128 B per cycle per SM and bounds the proposal / likelihood / update phases.)
+//   per block k at tc_cb_off(d, L, k):  bias1 [32]  L x bias2 [32]  bias3s [N3]  bias3t [N3]
+//   then  tsf [d]  tbf [d]  lof [d]  hif [d]   (TargetSmem's float32 mirrors)
+// (struct TcConsts: nnb_tc_consts.h)
+__host__ __device__ inline int tc_cb_block_floats(int d, int L, int k) { return 32 + 32 * L + 2 * round16(blk_nout(d, k)); }
+__host__ __device__ inline int tc_cb_off(int d, int L, int k) {
+  int off = 0;
+  for (int j = 0; j < k; ++j) off += tc_cb_block_floats(d, L, j);
+  return off;
+}
+__host__ __device__ inline int tc_cb_floats(int d, int L, int B) { return tc_cb_off(d, L, B) + 4 * d; }
 __host__ __device__ inline bool tc_supported(const FlowDesc& f) {
   return f.H == 16 && f.d >= 2 && blk_nin(f.d, 0) <= 32 && blk_nin(f.d, 1) <= 32 && blk_nout(f.d, 0) <= 32 &&
-         blk_nout(f.d, 1) <= 32 && !(f.flags & (NNB_FLOW_TRANSLATE_ONLY | NNB_FLOW_CONST_SCALE));
+         blk_nout(f.d, 1) <= 32 && !(f.flags & (NNB_FLOW_TRANSLATE_ONLY | NNB_FLOW_CONST_SCALE)) &&
+         tc_cb_floats(f.d, f.L, f.B) <= kTcConstFloats;
 }
 
 #ifndef NNB_TC_FAST_TANH
 #define NNB_TC_FAST_TANH 1
 #endif
-#ifndef NNB_TC_SLACK_NOISE
-#define NNB_TC_SLACK_NOISE 0   // 1: draw the next step's noise inside the MMA round trips of the flow (see mcmc_tc_kernel)
+#ifndef NNB_TC_PHILOX_ILP
+#define NNB_TC_PHILOX_ILP 4
 #endif
+constexpr int kTcPhiloxIlp = NNB_TC_PHILOX_ILP;
 // tanh of the s-net.  NNB_TC_FAST_TANH=0: libdevice tanhf (<= 2 ulp).  Default: MUFU ex2/rcp form below.
 __device__ __forceinline__ float tc_tanh(float x) {
 #if NNB_TC_FAST_TANH
@@ -74,6 +92,41 @@ __device__ __forceinline__ float tc_exp(float x) {
 #endif
 }
 
+#ifdef NNB_TC_TIMING
+// development probe (NNB_EXTRA_NVCC_FLAGS=-DNNB_TC_TIMING): clock64 stamps of every tile leader at five points of every
+// step -- [0] step start (scale read) [1] flow inverse done [2] accept + state update done [3] next step's noise drawn
+// [4] grid barrier released -- plus [5] globaltimer at step start, [6] proposal written, [7] likelihood done,
+// [8] tile's accept count known.  Each translation unit has its own copy.
+constexpr int kTimeSteps = 160, kTimeSlots = 10;
+static __device__ unsigned long long g_tc_time[160 * kTcMaxTiles * kTimeSteps * kTimeSlots];
+#define NNB_TSTAMP(slot)                                                                                              \
+  do {                                                                                                               \
+    if (tit == 0 && si_t < kTimeSteps)                                                                               \
+      g_tc_time[(((size_t)blockIdx.x * kTcMaxTiles + tile) * kTimeSteps + si_t) * kTimeSlots + (slot)] = clock64();  \
+  } while (0)
+#else
+#define NNB_TSTAMP(slot) do {} while (0)
+#endif
+
+// Shared-memory read-modify-write loops over a chain's coordinates: the pointers involved (y, zp, nz, the global state)
+// may alias as far as the compiler can tell, so a loop of the form `dst[i] = f(src[i])` keeps every load behind the
+// previous iteration's store -- one shared-memory latency (~30 cycles) per coordinate, 30 coordinates, several loops per
+// step, all of it on the step's critical path.  batched<CH>() evaluates `ld` for CH coordinates first (all loads in
+// flight together) and only then runs the stores.
+template <int CH, typename LD, typename ST>
+__device__ __forceinline__ void batched(int d, LD ld, ST st) {
+#pragma unroll
+  for (int i0 = 0; i0 < d; i0 += CH) {
+    float v[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (i0 + j < d) v[j] = ld(i0 + j);
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (i0 + j < d) st(i0 + j, v[j]);
+  }
+}
+
 struct TcTile {
   uint32_t tmem;        // TMEM address of the tile's column 0 (lane 0)
   uint32_t lane_tmem;   // + this warp's lane quarter
@@ -93,14 +146,11 @@ __device__ __forceinline__ void tile_sync(const TcTile& t) { tc::named_bar_sync(
 // (elect.sync: the operands stay in uniform registers, ~23 cycles per tcgen05.mma, csrc/dev/tc_latency.cu), each
 // committing to its own mbarrier.  Only those two warps poll; the other warps sleep on the hardware barrier (letting
 // every warp poll measured slower: the polling costs issue slots).
-// `slack()` is independent per-thread work that every warp of the tile runs while the tensor core is busy (between the MMA
-// issue and the wait for its completion): the kernel puts one Philox block of the NEXT step's noise there, which takes it
-// off the step's critical path without extra warps or registers.
-struct NoSlack {
-  __device__ __forceinline__ void operator()() const {}
-};
-template <typename F0, typename F1, typename SL>
-__device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1, SL slack) {
+// MEASURED alternatives (round 2, B200, c4; all correct, all slower, removed): every warp of the tile sleeping on the two
+// mbarriers (try_wait with a suspend-time hint) instead of the second tile barrier: +3 %; one Philox block of the next
+// step's noise between the MMA issue and the wait ("slack" work, parked in spare TMEM columns): +6 %.
+template <typename F0, typename F1>
+__device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1) {
   tc::wait_st();
   tc::fence_before_sync();
   tile_sync(t);
@@ -112,7 +162,6 @@ __device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1, S
     }
     __syncwarp();
   }
-  slack();
   if (t.issuer >= 0) {
     tc::mbar_wait(t.mbar + t.issuer, t.phase);
     __syncwarp();
@@ -136,16 +185,9 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float*
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t hi[8], lo[8];
-      const float4* b4 = reinterpret_cast<const float4*>(bias + 8 * c);
       float v[8];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        float4 b = b4[q];
-        v[4 * q + 0] = __uint_as_float(r[8 * c + 4 * q + 0]) + b.x;
-        v[4 * q + 1] = __uint_as_float(r[8 * c + 4 * q + 1]) + b.y;
-        v[4 * q + 2] = __uint_as_float(r[8 * c + 4 * q + 2]) + b.z;
-        v[4 * q + 3] = __uint_as_float(r[8 * c + 4 * q + 3]) + b.w;
-      }
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * c + j]) + bias[8 * c + j];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = c < 2 ? tc_tanh(v[j]) : fmaxf(v[j], 0.f);
 #pragma unroll
@@ -161,16 +203,9 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float*
     uint32_t r[8], hi[8], lo[8];
     tc::tmem_ld8(t.lane_tmem + 64 + 8 * c, r);
     tc::wait_ld();
-    const float4* b4 = reinterpret_cast<const float4*>(bias + 8 * c);
     float v[8];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      float4 b = b4[q];
-      v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b.x;
-      v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b.y;
-      v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b.z;
-      v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b.w;
-    }
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + bias[8 * c + j];
     if (c < 2) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = tc_tanh(v[j]);
@@ -188,20 +223,23 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float*
 // Flow inverse of one tile, in place on y (shared memory, stride ys).  Returns this thread's share of
 // log|det dx/dz| of the chain (the sum over the chain's NPART threads is the log-det).  Ends with a tile barrier:
 // afterwards every thread of the tile sees the complete x.
-// slack(r): work for the r-th MMA round trip of the call (r = 0 .. B (L + 2) - 1); *nrt receives the number of round trips.
+// zsrc(i): the flow's input z'_i.  fused == false: the caller has written z' to y and zsrc is not used.  fused == true
+// (needs at least two blocks): y holds NO input -- the first block reads its inputs, and the first two blocks the dims they
+// transform, through zsrc (every dim is transformed by one of the first two blocks and read exactly once before that), so
+// the proposal z' = z + scale * noise is formed where it is consumed instead of making a round trip through shared memory.
 // t_col: TMEM column of the translate net's output (96; 80 when every block transforms at most 16 dims, which leaves
 // columns [96,128) to the kernel).
-template <int NPART, int DD, typename SL>
+template <int NPART, int DD, typename ZS>
 __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const float* __restrict__ wsm, uint32_t wsm_u32,
                                                  TcTile& t, float* y, int ys, float* ld_slot, int* bad_slot,
-                                                 const float* __restrict__ lof, const float* __restrict__ hif,
-                                                 bool box_check, bool& bad, SL slack, uint32_t t_col, int* nrt) {
+                                                 const float* __restrict__ cb, const float* __restrict__ lof,
+                                                 const float* __restrict__ hif, bool box_check, bool& bad, uint32_t t_col,
+                                                 bool fused, ZS zsrc) {
   // DD > 0: x_dim, num_layers = 1 and num_blocks = 3 (the reference's defaults) are compile-time constants: every loop
   // below unrolls and every shared-memory / TMEM offset becomes an immediate
   const int d = DD > 0 ? DD : f.d, L = DD > 0 ? 1 : f.L, nB = DD > 0 ? 3 : f.B;
   float ld = 0.f;
   bad = false;
-  int trip = 0;
 #pragma unroll
   for (int k = nB - 1; k >= 0; --k) {
     const int nin = blk_nin(d, k), i0 = blk_i0(k), nout = blk_nout(d, k), o0 = blk_o0(k);
@@ -217,7 +255,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int a = c0 + j;
-          float v = a < nin ? y[(i0 + 2 * a) * ys] : 0.f;
+          float v = a < nin ? (fused ? zsrc(i0 + 2 * a) : y[(i0 + 2 * a) * ys]) : 0.f;
           tc::split_tf32(v, hi[j], lo[j]);
         }
         tc::tmem_st8(t.lane_tmem + c0, hi);
@@ -233,13 +271,12 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
                       if (t.single) tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, b_hi, b_lo, K1 / 8, 32, false);
                       else tc::mma_3xtf32_n(t.tmem + 64, t.tmem, t.tmem + 32, b_hi, b_lo, K1 / 8, 16, 4, false);
                     },
-                    [&] { tc::mma_3xtf32_n(t.tmem + 80, t.tmem, t.tmem + 32, b_hi + 256u, b_lo + 256u, K1 / 8, 16, 4, false); },
-                    [&] { slack(trip); });
-      ++trip;
+                    [&] { tc::mma_3xtf32_n(t.tmem + 80, t.tmem, t.tmem + 32, b_hi + 256u, b_lo + 256u, K1 / 8, 16, 4, false); });
     }
-    int off = base + 64 * K1;   // -> bias1
-    tc_hidden_epilogue<NPART>(t, wsm + off);
-    off += 32;
+    int off = base + 64 * K1 + 32;   // past B1 and (the shared-memory copy of) bias1
+    // biases: constant bank (cb), see TcConsts
+    const int cbk = DD > 0 ? tc_cb_off(DD, 1, k) : tc_cb_off(d, L, k);
+    tc_hidden_epilogue<NPART>(t, cb + cbk);
     // ---- hidden layers: block diagonal, s-net cols [0,16), t-net cols [16,32) --------------------------------
     for (int l = 0; l < L; ++l) {
       const uint32_t bs_hi = wsm_u32 + 4u * off, bs_lo = bs_hi + 1024u, bt_hi = bs_hi + 2048u, bt_lo = bs_hi + 3072u;
@@ -248,10 +285,8 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
                       tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, bs_hi, bs_lo, 2, 16, false);
                       if (t.single) tc::mma_3xtf32(t.tmem + 80, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, 16, false);
                     },
-                    [&] { tc::mma_3xtf32(t.tmem + 80, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, 16, false); },
-                    [&] { slack(trip); });
-      ++trip;
-      tc_hidden_epilogue<NPART>(t, wsm + off + 1024);
+                    [&] { tc::mma_3xtf32(t.tmem + 80, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, 16, false); });
+      tc_hidden_epilogue<NPART>(t, cb + cbk + 32 + 32 * l);
       off += 1056;
     }
     // ---- output layer: log_s -> D cols [64, 64+N3), t -> D cols [96, 96+N3) ------------------------------------
@@ -263,11 +298,9 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
                       tc::mma_3xtf32(t.tmem + 64, t.tmem, t.tmem + 32, bs_hi, bs_lo, 2, N3, false);
                       if (t.single) tc::mma_3xtf32(t.tmem + t_col, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, N3, false);
                     },
-                    [&] { tc::mma_3xtf32(t.tmem + t_col, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, N3, false); },
-                    [&] { slack(trip); });
-      ++trip;
+                    [&] { tc::mma_3xtf32(t.tmem + t_col, t.tmem + 16, t.tmem + 48, bt_hi, bt_lo, 2, N3, false); });
     }
-    const float* b3s = wsm + off + 64 * N3;
+    const float* b3s = cb + cbk + 32 + 32 * L;
     const float* b3t = b3s + N3;
     // x = (z - t) * exp(-log_s), ld -= log_s on the dims with mask == 0   (networks.py:300-309).  The values a dim keeps
     // (its last update: blocks 1 and 0) are tested against the prior box right here (priors.py:39-43).
@@ -277,6 +310,10 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
       uint32_t rs[16], rt[16];
       tc::tmem_ld16(t.lane_tmem + 64, rs);
       tc::tmem_ld16(t.lane_tmem + t_col, rt);
+      float yv[16];   // the dims this block transforms, read before any of them is written back (see batched<>)
+#pragma unroll
+      for (int o = 0; o < 16; ++o)
+        if (o < nout) yv[o] = (fused && k >= nB - 2) ? zsrc(o0 + 2 * o) : y[(o0 + 2 * o) * ys];
       tc::wait_ld();
 #pragma unroll
       for (int c0 = 0; c0 < 16; c0 += 8) {
@@ -290,7 +327,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
               const float ls = __uint_as_float(rs[o]) + b3s[o];
               const float tt = __uint_as_float(rt[o]) + b3t[o];
               float* yp = y + (o0 + 2 * o) * ys;
-              xv = (*yp - tt) * tc_exp(-ls);
+              xv = (yv[o] - tt) * tc_exp(-ls);
               *yp = xv;
               ld -= ls;
               if (chk) bad |= (xv < lof[o0 + 2 * o]) | (xv > hif[o0 + 2 * o]);
@@ -308,6 +345,10 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
       uint32_t rs[8], rt[8], hi[8], lo[8];
       tc::tmem_ld8(t.lane_tmem + 64 + c0, rs);
       tc::tmem_ld8(t.lane_tmem + t_col + c0, rt);
+      float yv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < nout) yv[j] = (fused && k >= nB - 2) ? zsrc(o0 + 2 * (c0 + j)) : y[(o0 + 2 * (c0 + j)) * ys];
       tc::wait_ld();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -317,7 +358,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
           const float ls = __uint_as_float(rs[j]) + b3s[o];
           const float tt = __uint_as_float(rt[j]) + b3t[o];
           float* yp = y + (o0 + 2 * o) * ys;
-          xv = (*yp - tt) * tc_exp(-ls);
+          xv = (yv[j] - tt) * tc_exp(-ls);
           *yp = xv;
           ld -= ls;
           if (chk) bad |= (xv < lof[o0 + 2 * o]) | (xv > hif[o0 + 2 * o]);
@@ -336,7 +377,6 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
       tile_sync(t);                             // every thread of the tile now sees the complete x
     }
   }
-  *nrt = trip;
   return ld;
 }
 
@@ -364,12 +404,13 @@ static __device__ __noinline__ double tc_prior(TargetDesc td, const double* td_s
 template <int MODE, int NPART, int DD>
 __global__ void __launch_bounds__(kTcMaxTiles * 128 * NPART, 1)
 mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, const double* __restrict__ tgt_g,
-               McmcParams p) {
+               McmcParams p, const __grid_constant__ TcConsts cst) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // A CTA owns p.cpc chains (a multiple of 32): full tiles of 128 plus, possibly, a partial last tile, so that
   // the batch can be spread evenly over all SMs (65 536 chains = 148 x 448 - a few).  Threads are laid out
   // tile-major, then part-major; a partial tile simply has fewer warps per part (lane quarters).
   const int d = DD > 0 ? DD : f.d;
+  const float* cst_t = cst.v + (DD > 0 ? tc_cb_off(DD, 1, 3) : tc_cb_off(f.d, f.L, f.B));   // tsf | tbf | lof | hif
   const int cpc = p.cpc;
   const int ntiles = (cpc + 127) >> 7;
   float* wsm = reinterpret_cast<float*>(smem_raw);
@@ -433,7 +474,13 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   t.bar_id = 1 + tile;
   t.bar_threads = rows * NPART;
   t.part = tit >> 7;
-  t.issuer = tit < 32 ? 0 : (tit < 64 && rows > 32 ? 1 : -1);
+  // the two MMA-issuing warps of a tile: tiles 1 and 2 use their warps 2 and 3 (schedulers 2 and 3), tiles 0 and 3 their
+  // warps 0 and 1 -- every tcgen05.mma keeps its warp's scheduler busy for ~23 cycles, and with all issuers on
+  // schedulers 0 and 1 those two carried half as much work again as the others
+  {
+    const int wq = tit >> 5, first = (rows == 128 && (tile == 1 || tile == 2)) ? 2 : 0;
+    t.issuer = wq == first ? 0 : (wq == first + 1 && rows > 32 ? 1 : -1);
+  }
   t.single = rows <= 32;   // a 32-chain tile has only one warp per part
   const int part = NPART == 1 ? 0 : t.part;
   const uint32_t wsm_u32 = tc::smem_u32(wsm);
@@ -483,12 +530,47 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
 
   // one thread per chain: the current latent point stays in shared memory for all steps of the launch
   constexpr bool kZcur = NPART == 1;
-  if (kZcur && active)
-    for (int i = 0; i < d; ++i) zp[i * 128] = p.z[(size_t)c + (size_t)i * ns];
+  constexpr int kCh = DD > 0 ? 16 : 8;   // coordinates per batch of the shared-memory loops (batched<>)
+  if (kZcur && tile_active)   // (idle lanes of a live warp: zeros, so that their rows of the MMAs stay finite)
+    for (int i = 0; i < d; ++i) {
+      zp[i * 128] = active ? p.z[(size_t)c + (size_t)i * ns] : 0.f;
+      if (!active) nz[i * 128] = 0.f;
+    }
 
   // raw N(0,1) draws of Philox blocks j = j0, j0 + jstep, ... < j1 of step `step_abs` into nz (and the dump buffer)
   auto gen_normals = [&](int j0, int j1, int jstep, unsigned int step_abs, int sidx) {
-#pragma unroll(DD > 0 ? 2 : 1)   // two independent Philox chains in flight (each is a serial chain of ten rounds)
+    if (DD > 0 && NPART == 1) {
+      // one thread per chain, x_dim fixed: all blocks 0 .. nj-1, kTcPhiloxIlp of them at a time -- the Philox rounds and the
+      // Box-Muller transforms of a group are straight-line code (one basic block) that the scheduler interleaves; the
+      // stores and the optional dump follow the group.  (A block is a serial chain: ten dependent rounds, then
+      // lg2 -> sqrt and sin / cos; one at a time it runs at ~330 cycles per block.)
+      constexpr int NJ = DD > 0 ? (DD + 3) / 4 : 1;
+#pragma unroll
+      for (int jb = 0; jb < NJ; jb += kTcPhiloxIlp) {
+        float nrm[kTcPhiloxIlp][4];
+#pragma unroll
+        for (int u = 0; u < kTcPhiloxIlp; ++u)
+          if (jb + u < NJ) philox_normals4(jb + u, step_abs, chain, kTagNormal, p.seed_lo, p.seed_hi, nrm[u]);
+#pragma unroll
+        for (int u = 0; u < kTcPhiloxIlp; ++u)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int i = 4 * (jb + u) + q;
+            if (jb + u < NJ && i < DD) nz[i * 128] = nrm[u][q];
+          }
+        if (p.dump_normals) {
+#pragma unroll
+          for (int u = 0; u < kTcPhiloxIlp; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = 4 * (jb + u) + q;
+              if (jb + u < NJ && i < DD) p.dump_normals[((size_t)sidx * ns + (size_t)c) * d + i] = nrm[u][q];
+            }
+        }
+      }
+      return;
+    }
+#pragma unroll(DD > 0 ? 2 : 1)
     for (int j = j0; j < j1; j += jstep) {
       float nrm[4];
       philox_normals4(j, step_abs, chain, kTagNormal, p.seed_lo, p.seed_hi, nrm);
@@ -519,20 +601,11 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   if (tile_active && active && philox_u && part == NPART - 1) gen_uniform(p.step_offset + (unsigned int)(p.s0 + 1), p.s0);
   // weights have landed (each thread observes every block's mbarrier: phase 0 completes when its bytes are in)
   for (int k = nblk_w - 1; k >= 0; --k) tc::mbar_wait(&wbars[k], 0u);
-  // Noise of step s+1 drawn INSIDE step s's flow (one thread per chain, at most 32 dims, library Philox stream): every MMA
-  // round trip has a slot in which the tile's warps would only wait for the tensor core; block r of the next step's
-  // Philox normals (4 dims) is drawn in the r-th slot and parked in the chain's own TMEM lane, columns [96, 128) -- free
-  // because with at most 16 transformed dims per block the translate net's output moves to columns [80, 96).  The next
-  // step's proposal reads the 32 columns back with one tcgen05.ld.  (Other shapes: the noise is drawn after the accept
-  // phase, overlapping the grid barrier, as before.)
-  // MEASURED (round 2, B200, c4): correct (the whole GPU suite passes with it) but not faster -- 2.76 ms per refill against
-  // 2.60 ms with the noise drawn in the shadow of the per-step grid barrier: with 3.5 tiles per SM the "idle" slot of one
-  // tile is issue time of the others, and the barrier latency is then exposed.  Kept behind NNB_TC_SLACK_NOISE (default 0).
+  // TMEM column of the translate net's output: 80 when every block transforms at most 16 dims, else 96
   const bool small_d = DD > 0 ? DD <= 32 : d <= 32;
   const uint32_t t_col = small_d ? 80u : 96u;
-  const bool noise_tmem = NNB_TC_SLACK_NOISE && NPART == 1 && philox && small_d;
-  // (Also measured and dropped: staggering the tiles of an SM -- odd tiles drawing a step's noise at its start instead of
-  // at the end of the previous step, so that the tiles do not all wait for their MMAs at the same moments: 2.80 ms.)
+  // One thread per chain and at least two coupling blocks: the proposal is formed inside the flow (tc_flow_inverse: zsrc)
+  const bool fused = NPART == 1 && (DD > 0 || f.B >= 2);
   // prior box on the flow's own coordinates (nested sampling): tested inside the output epilogues of the flow
   const bool fast_box = MODE == NNB_MODE_HARD && tg.desc.prior_kind == NNB_PRIOR_BOX_U && (DD > 0 || f.B >= 2);
 
@@ -542,85 +615,69 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
     bool accept = false;
     unsigned int ncall = 0, tile_cnt = 0;
     bool acc_chain = false;
+#ifdef NNB_TC_TIMING
+    const int si_t = s - p.s0 - 1;
+#endif
     if (tile_active) {
       if (NPART > 1 || p.coop) tile_sync(t);   // nz complete (written by both threads of the chain); scale published
+      NNB_TSTAMP(0);
+      // The tiles of an SM leave the grid barrier together and would then all run their epilogues at the same moments and
+      // all wait for their MMAs at the same moments; odd tiles therefore start the step about half a round trip late
+      // (p.tc_stagger cycles, NNB_TC_STAGGER; measured on the B200 at c4: 2.23 ms -> 2.14 ms per refill at 700 cycles)
+      if (p.tc_stagger > 0 && (tile & 1)) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)p.tc_stagger) {}
+      }
+#ifdef NNB_TC_TIMING
+      if (tit == 0 && si_t < kTimeSteps) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        g_tc_time[(((size_t)blockIdx.x * kTcMaxTiles + tile) * kTimeSteps + si_t) * kTimeSlots + 5] = gt;
+      }
+#endif
       const float scale_f = p.coop ? *reinterpret_cast<volatile float*>(co_scale_s)
                                    : (float)(*reinterpret_cast<volatile double*>(&p.ctrl->scale));
       // this step's accept uniform: read now, the slot is refilled for the next step while the flow runs
       const float u01_cur = (active && philox_u && part == NPART - 1) ? *u_slot : 0.f;
-      const bool from_tmem = noise_tmem && s > p.s0 + 1;   // (the first step's noise was drawn into shared memory)
-      if (from_tmem) {
-        // tcgen05.ld is warp-collective: every lane of the (tile-active) warp takes part, idle lanes ignore the values
-        uint32_t r[32];
-        tc::wait_st();                                  // the parked noise was written with (asynchronous) tcgen05.st
-        tc::tmem_ld32(t.lane_tmem + 96, r);
-        tc::wait_ld();
-        if (active) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < d) {
-              const float nv = __uint_as_float(r[i]);
-              nz[i * 128] = nv;                         // kept for the accept update (z' is recomputed from it)
-              y[i * 128] = __fadd_rn(zp[i * 128], __fmul_rn(nv, scale_f));
-            }
+      // ---- proposal z' = z + scale * N(0, I) (sampler.py:310-316) ---------------------------------------------------
+      if (kZcur) {
+        // one thread per chain: the current z (zp) and the step's noise (nz) live in shared memory; replayed noise is
+        // copied into nz first so that the flow and the accept update have a single source
+        if (!philox && active) {
+          const float* nr = p.replay_normals + ((size_t)(s - 1) * ns + (size_t)c) * d;
+          batched<kCh>(d, [&](int i) { return nr[i]; }, [&](int i, float v) { nz[i * 128] = v; });
         }
-      }
-      // ---- proposal z' = z + scale * N(0, I) (sampler.py:310-316), dims dealt to the chain's threads ----------------
-      if (from_tmem && active) {
-      } else if (active) {
-        if (kZcur) {   // one thread per chain: the current z lives in shared memory (zp), no global traffic per step
-          if (philox) {
-            for (int i = 0; i < d; ++i) y[i * 128] = __fadd_rn(zp[i * 128], __fmul_rn(nz[i * 128], scale_f));
-          } else {
-            const float* nr = p.replay_normals + ((size_t)(s - 1) * ns + (size_t)c) * d;
-            for (int i = 0; i < d; ++i) y[i * 128] = __fadd_rn(zp[i * 128], __fmul_rn(nr[i], scale_f));
+        if (!fused)   // (single-block flows: z' goes through y; idle lanes hold zeros in zp and nz)
+          batched<kCh>(d, [&](int i) { return __fadd_rn(zp[i * 128], __fmul_rn(nz[i * 128], scale_f)); },
+                       [&](int i, float v) { y[i * 128] = v; });
+      } else if (active) {   // dims dealt to the chain's threads
+        const float* pz = p.z + (size_t)c + (size_t)part * ns;
+        if (philox) {
+          for (int i = part; i < d; i += NPART, pz += NPART * ns) {
+            float v = __fadd_rn(*pz, __fmul_rn(nz[i * 128], scale_f));
+            y[i * 128] = v;
+            zp[i * 128] = v;
           }
         } else {
-          const float* pz = p.z + (size_t)c + (size_t)part * ns;
-          if (philox) {
-            for (int i = part; i < d; i += NPART, pz += NPART * ns) {
-              float v = __fadd_rn(*pz, __fmul_rn(nz[i * 128], scale_f));
-              y[i * 128] = v;
-              zp[i * 128] = v;
-            }
-          } else {
-            const float* nr = p.replay_normals + ((size_t)(s - 1) * ns + (size_t)c) * d;
-            for (int i = part; i < d; i += NPART, pz += NPART * ns) {
-              float v = __fadd_rn(*pz, __fmul_rn(nr[i], scale_f));
-              y[i * 128] = v;
-              zp[i * 128] = v;
-            }
+          const float* nr = p.replay_normals + ((size_t)(s - 1) * ns + (size_t)c) * d;
+          for (int i = part; i < d; i += NPART, pz += NPART * ns) {
+            float v = __fadd_rn(*pz, __fmul_rn(nr[i], scale_f));
+            y[i * 128] = v;
+            zp[i * 128] = v;
           }
         }
       } else {
         for (int i = part; i < d; i += NPART) y[i * 128] = 0.f;
       }
       __syncwarp();
+      NNB_TSTAMP(6);
       if (NPART > 1) tile_sync(t);   // layer 1 reads dims written by the partner thread
       // ---- flow inverse on the tensor cores (all threads of the tile, converged) ----------------------------------
       bool bad_part;
-      int nrt = 0;
-      const bool gen_next = noise_tmem && more;
-      const unsigned int step_next = step_abs + 1u;
-      auto slack = [&](int r) {   // r-th MMA round trip of the step: one Philox block of the next step's noise
-        if (!gen_next) return;
-        if (r < nj) {
-          float nrm[4];
-          philox_normals4(r, step_next, chain, kTagNormal, p.seed_lo, p.seed_hi, nrm);
-          const uint32_t v[4] = {__float_as_uint(nrm[0]), __float_as_uint(nrm[1]), __float_as_uint(nrm[2]),
-                                 __float_as_uint(nrm[3])};
-          tc::tmem_st4(t.lane_tmem + 96 + 4 * r, v);
-          if (p.dump_normals && active)
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (4 * r + q < d) p.dump_normals[((size_t)s * ns + (size_t)c) * d + 4 * r + q] = nrm[q];
-        } else if (r == nj) {
-          if (active) gen_uniform(step_next, s);
-        }
-      };
-      const float ld_part = tc_flow_inverse<NPART, DD>(f, wsm, wsm_u32, t, y, 128, ldp + part * 128, flag, tg.lof, tg.hif,
-                                                   fast_box, bad_part, slack, t_col, &nrt);
-      for (int r = nrt; r <= nj; ++r) slack(r);   // fewer round trips than Philox blocks (shallow flows): the rest now
+      const float ld_part = tc_flow_inverse<NPART, DD>(
+          f, wsm, wsm_u32, t, y, 128, ldp + part * 128, flag, cst.v, cst_t + 2 * d, cst_t + 3 * d, fast_box, bad_part, t_col,
+          fused, [&](int i) { return __fadd_rn(zp[i * 128], __fmul_rn(nz[i * 128], scale_f)); });
+      NNB_TSTAMP(1);
       // ---- accept / reject: thread 0 of the chain; thread 1 starts on the next step's noise -------------------------
       if (active && part == 0) {
         float ld_prop = ld_part;
@@ -641,7 +698,23 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
           if (ratio > 1.0f) ratio = 1.0f;
           const bool m1 = u01 < ratio;
           if (m1) {
-            lp = tc_loglike<DD>(td, td_s, y);
+            if (DD > 0 && td.like_id == NNB_LIKE_ROSENBROCK && !td.compute_f64 && td.has_transform) {
+              // the config-4 target inline (same arithmetic as loglike_T<float>: likelihoods.py:50-51 after the float32
+              // affine transform), transform coefficients as constant-bank operands
+              constexpr int D1 = DD > 0 ? DD : 1;
+              float acc = 0.f, prev = __fadd_rn(__fmul_rn(y[0], cst_t[0]), cst_t[D1]);
+              batched<kCh>(D1 - 1, [&](int i) { return __fadd_rn(__fmul_rn(y[(i + 1) * 128], cst_t[i + 1]), cst_t[D1 + i + 1]); },
+                           [&](int, float cur) {
+                             const float t1 = __fsub_rn(cur, __fmul_rn(prev, prev));
+                             const float t2 = __fsub_rn(1.f, prev);
+                             acc = __fadd_rn(acc, __fadd_rn(__fmul_rn(100.f, __fmul_rn(t1, t1)), __fmul_rn(t2, t2)));
+                             prev = cur;
+                           });
+              const double out = -(double)acc;
+              lp = isfinite(out) ? out : (double)-INFINITY;   // float32-typed result: sampler.py:128 leaves -inf
+            } else {
+              lp = tc_loglike<DD>(td, td_s, y);
+            }
             ncall = 1;
             accept = isfinite(lp) && (lp > p.loglstar);
           }
@@ -665,6 +738,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
         gen_normals(0, jc, 1, step_abs + 1u, s);
       }
       __syncwarp();
+      NNB_TSTAMP(7);
       acc_chain = accept;
       if (p.coop) {   // the tile barrier doubles as the count of the tile's accepted proposals
         tile_cnt = tc::named_bar_popc(t.bar_id, t.bar_threads, accept);
@@ -673,26 +747,23 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
         tile_sync(t);
         acc_chain = active && (*flag != 0);
       }
+      NNB_TSTAMP(8);
       // ---- state / trace update, dims dealt to the chain's threads (sampler.py:433-444) -------------------------------
       if (active && kZcur) {
         // z' is recomputed from the same operands as the proposal (bit-identical); this step's noise is still intact
         // because the next step's is drawn after this point
         float* px = p.x + (size_t)c;
         if (acc_chain) {
-          const float* nr = philox ? nullptr : p.replay_normals + ((size_t)(s - 1) * ns + (size_t)c) * d;
-          for (int i = 0; i < d; ++i, px += ns) {
-            zp[i * 128] = __fadd_rn(zp[i * 128], __fmul_rn(philox ? nz[i * 128] : nr[i], scale_f));
-            *px = y[i * 128];
-          }
+          batched<kCh>(d, [&](int i) { return __fadd_rn(zp[i * 128], __fmul_rn(nz[i * 128], scale_f)); },
+                       [&](int i, float v) { zp[i * 128] = v; });
+          batched<kCh>(d, [&](int i) { return y[i * 128]; }, [&](int i, float v) { px[(size_t)i * ns] = v; });
         }
         if (p.trace_z) {
           float* tz = p.trace_z + (size_t)s * d * ns + (size_t)c;
           float* tx = p.trace_x + (size_t)s * d * ns + (size_t)c;
-          px = p.x + (size_t)c;
-          for (int i = 0; i < d; ++i, tz += ns, tx += ns, px += ns) {
-            *tz = zp[i * 128];
-            *tx = acc_chain ? y[i * 128] : *px;
-          }
+          batched<kCh>(d, [&](int i) { return zp[i * 128]; }, [&](int i, float v) { tz[(size_t)i * ns] = v; });
+          batched<kCh>(d, [&](int i) { return acc_chain ? y[i * 128] : px[(size_t)i * ns]; },
+                      [&](int i, float v) { tx[(size_t)i * ns] = v; });
         }
       } else if (active) {
         float* pz = p.z + (size_t)c + (size_t)part * ns;
@@ -724,6 +795,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
     }
     acc_total += accept ? 1u : 0u;
     ncall_total += ncall;
+    NNB_TSTAMP(2);
 
     // ---- global accept count of the step -> scale adaptation (sampler.py:418-430) ------------------------------------
     const int si = s - p.s0 - 1;
@@ -765,10 +837,9 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       }
     }
     // ---- rest of the next step's noise (overlaps the grid barrier) --------------------------------------------------------
-    if (!noise_tmem) {
-      if (tile_active && active && more && philox) gen_normals(jc + part, nj, NPART, step_abs + 1u, s);
-      if (tile_active && active && more && philox_u && part == NPART - 1) gen_uniform(step_abs + 1u, s);
-    }
+    if (tile_active && active && more && philox) gen_normals(jc + part, nj, NPART, step_abs + 1u, s);
+    if (tile_active && active && more && philox_u && part == NPART - 1) gen_uniform(step_abs + 1u, s);
+    NNB_TSTAMP(3);
     if (p.coop && tile_active && tit == 0) {
       // The CTA's poller waits for the grid-wide count and updates the CTA's copy of (scale, accept, reject) -- identical
       // in every CTA; the other tile leaders wait for the epoch word in shared memory.  The tile barrier at the top of the
@@ -793,8 +864,13 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       } else {
         // the other tile leaders sleep on the mbarrier (hardware-suspended try_wait) instead of spinning on the epoch
         // word: the spin loop was 6.7 % of all issued instructions (profiles/r2_tc1_*)
+#ifdef NNB_TC_WAIT_HINT
+        tc::mbar_wait_long(sbar, (uint32_t)(si & 1));
+#else
         tc::mbar_wait(sbar, (uint32_t)(si & 1));
+#endif
       }
+      NNB_TSTAMP(4);
     }
   }
   if (kZcur && active)

@@ -11,6 +11,17 @@ namespace nnb {
 template <int MODE, int NPART, int DD>
 static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t st) {
   const int tdoubles = target_doubles(h->tdesc.d, h->tdesc.n_params);
+  // kernel-parameter constants: the flow's biases (filled by nnb_tc_pack) + the target's float32 mirrors.  All parameters
+  // together stay below 4 KB: larger parameter blocks take a slow launch path in the driver (measured with a 5 KB
+  // block: +1.4 ms per cooperative launch).
+  static_assert(sizeof(TcFlowDesc) + sizeof(TargetDesc) + sizeof(McmcParams) + sizeof(TcConsts) + 2 * sizeof(void*) + 32 <= 4096,
+                "kernel parameters of mcmc_tc_kernel exceed 4 KB");
+  TcConsts cst = h->tc_consts;
+  {
+    const int d = h->tcflow.d, t0 = tc_cb_off(d, h->tcflow.L, h->tcflow.B);
+    if ((int)h->target_f32.size() != 4 * d) return nnb_fail(h, NNB_ERR_STATE, "target float32 mirrors missing");
+    for (int i = 0; i < 4 * d; ++i) cst.v[t0 + i] = h->target_f32[i];
+  }
   // chains per CTA: spread the batch evenly over all SMs in units of a warp (32 chains), at most 4 tiles of 128
   long long cpc = ((p.n + h->sm_count - 1) / h->sm_count + 31) / 32 * 32;
   if (cpc > 128 * kTcMaxTiles) cpc = 128 * kTcMaxTiles;
@@ -29,6 +40,8 @@ static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t s
   p.cpc = (int)cpc;
   static const int jc_env = [] { const char* e = getenv("NNB_TC_JC"); return e ? atoi(e) : -1; }();
   p.tc_jc = jc_env;
+  static const int stagger_env = [] { const char* e = getenv("NNB_TC_STAGGER"); return e ? atoi(e) : 700; }();
+  p.tc_stagger = ntiles > 1 ? stagger_env : 0;
   // Persistent path: all steps in ONE cooperative launch (every CTA resident, one per SM), the global accept count
   // of each step travels through a grid barrier.  Needs grid <= SM count; otherwise one launch per step.
   static const bool no_coop = getenv("NNB_NO_COOP") != nullptr;
@@ -48,7 +61,8 @@ static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t s
       tiles += (mine + 127) / 128;
     }
     p.total_tiles = (int)tiles;
-    void* args[] = {(void*)&h->tcflow, (void*)&h->d_weights_tc, (void*)&h->tdesc, (void*)&h->d_target, (void*)&p};
+    void* args[] = {(void*)&h->tcflow, (void*)&h->d_weights_tc, (void*)&h->tdesc, (void*)&h->d_target, (void*)&p,
+                    (void*)&cst};
     NNB_CUDA(h, cudaLaunchCooperativeKernel((const void*)mcmc_tc_kernel<MODE, NPART, DD>, dim3(grid), dim3(block), args, sm, st));
     h->last_launches = 1;
     return NNB_OK;
@@ -57,11 +71,11 @@ static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t s
   if (p.dynamic) {
     for (int s = 0; s < steps; ++s) {
       p.s0 = s; p.nsteps = 1;
-      mcmc_tc_kernel<MODE, NPART, DD><<<grid, block, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p);
+      mcmc_tc_kernel<MODE, NPART, DD><<<grid, block, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p, cst);
     }
   } else {
     p.s0 = 0; p.nsteps = steps;
-    mcmc_tc_kernel<MODE, NPART, DD><<<grid, block, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p);
+    mcmc_tc_kernel<MODE, NPART, DD><<<grid, block, sm, st>>>(h->tcflow, h->d_weights_tc, h->tdesc, h->d_target, p, cst);
   }
   NNB_CUDA(h, cudaGetLastError());
   h->last_launches = p.dynamic ? steps : 1;
