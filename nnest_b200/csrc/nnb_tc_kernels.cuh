@@ -223,18 +223,19 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float*
 // Flow inverse of one tile, in place on y (shared memory, stride ys).  Returns this thread's share of
 // log|det dx/dz| of the chain (the sum over the chain's NPART threads is the log-det).  Ends with a tile barrier:
 // afterwards every thread of the tile sees the complete x.
-// zsrc(i): the flow's input z'_i.  fused == false: the caller has written z' to y and zsrc is not used.  fused == true
-// (needs at least two blocks): y holds NO input -- the first block reads its inputs, and the first two blocks the dims they
-// transform, through zsrc (every dim is transformed by one of the first two blocks and read exactly once before that), so
-// the proposal z' = z + scale * noise is formed where it is consumed instead of making a round trip through shared memory.
+// fused == false: the caller has written the flow's input z' to y.  fused == true (needs at least two blocks): y holds NO
+// input -- the proposal z'_i = zc[i] + scale * nz[i] (sampler.py:310-316) is formed where the flow first consumes dim i
+// (the first block's inputs and the dims it transforms) and is written back over the noise, nz[i] = z'_i: the second
+// block reads the dims it transforms from there, and after an accepted step the caller just swaps its zc / nz pointers
+// instead of copying.  Every dim is transformed by one of the first two blocks, so y is complete at the end.
 // t_col: TMEM column of the translate net's output (96; 80 when every block transforms at most 16 dims, which leaves
 // columns [96,128) to the kernel).
-template <int NPART, int DD, typename ZS>
+template <int NPART, int DD>
 __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const float* __restrict__ wsm, uint32_t wsm_u32,
                                                  TcTile& t, float* y, int ys, float* ld_slot, int* bad_slot,
                                                  const float* __restrict__ cb, const float* __restrict__ lof,
                                                  const float* __restrict__ hif, bool box_check, bool& bad, uint32_t t_col,
-                                                 bool fused, ZS zsrc) {
+                                                 bool fused, const float* zc, float* nz, float scale) {
   // DD > 0: x_dim, num_layers = 1 and num_blocks = 3 (the reference's defaults) are compile-time constants: every loop
   // below unrolls and every shared-memory / TMEM offset becomes an immediate
   const int d = DD > 0 ? DD : f.d, L = DD > 0 ? 1 : f.L, nB = DD > 0 ? 3 : f.B;
@@ -252,11 +253,17 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
     if (k == nB - 1) {
       for (int c0 = (NPART == 1 ? 0 : 8 * t.part); c0 < K1; c0 += 8 * NPART) {
         uint32_t hi[8], lo[8];
+        float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int a = c0 + j;
-          float v = a < nin ? (fused ? zsrc(i0 + 2 * a) : y[(i0 + 2 * a) * ys]) : 0.f;
-          tc::split_tf32(v, hi[j], lo[j]);
+          const int a = c0 + j, i = i0 + 2 * a;
+          v[j] = a < nin ? (fused ? __fadd_rn(zc[i * ys], __fmul_rn(nz[i * ys], scale)) : y[i * ys]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {   // (stores after all loads of the chunk: see batched<>)
+          const int a = c0 + j, i = i0 + 2 * a;
+          if (fused && a < nin) nz[i * ys] = v[j];
+          tc::split_tf32(v[j], hi[j], lo[j]);
         }
         tc::tmem_st8(t.lane_tmem + c0, hi);
         tc::tmem_st8(t.lane_tmem + 32 + c0, lo);
@@ -312,8 +319,17 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
       tc::tmem_ld16(t.lane_tmem + t_col, rt);
       float yv[16];   // the dims this block transforms, read before any of them is written back (see batched<>)
 #pragma unroll
-      for (int o = 0; o < 16; ++o)
-        if (o < nout) yv[o] = (fused && k >= nB - 2) ? zsrc(o0 + 2 * o) : y[(o0 + 2 * o) * ys];
+      for (int o = 0; o < 16; ++o) {
+        const int i = o0 + 2 * o;
+        if (o < nout)
+          yv[o] = (fused && k == nB - 1) ? __fadd_rn(zc[i * ys], __fmul_rn(nz[i * ys], scale))
+                                         : ((fused && k == nB - 2) ? nz[i * ys] : y[i * ys]);
+      }
+      if (fused && k == nB - 1) {
+#pragma unroll
+        for (int o = 0; o < 16; ++o)
+          if (o < nout) nz[(o0 + 2 * o) * ys] = yv[o];
+      }
       tc::wait_ld();
 #pragma unroll
       for (int c0 = 0; c0 < 16; c0 += 8) {
@@ -347,8 +363,17 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
       tc::tmem_ld8(t.lane_tmem + t_col + c0, rt);
       float yv[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (c0 + j < nout) yv[j] = (fused && k >= nB - 2) ? zsrc(o0 + 2 * (c0 + j)) : y[(o0 + 2 * (c0 + j)) * ys];
+      for (int j = 0; j < 8; ++j) {
+        const int i = o0 + 2 * (c0 + j);
+        if (c0 + j < nout)
+          yv[j] = (fused && k == nB - 1) ? __fadd_rn(zc[i * ys], __fmul_rn(nz[i * ys], scale))
+                                         : ((fused && k == nB - 2) ? nz[i * ys] : y[i * ys]);
+      }
+      if (fused && k == nB - 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < nout) nz[(o0 + 2 * (c0 + j)) * ys] = yv[j];
+      }
       tc::wait_ld();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -609,9 +634,18 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
   // prior box on the flow's own coordinates (nested sampling): tested inside the output epilogues of the flow
   const bool fast_box = MODE == NNB_MODE_HARD && tg.desc.prior_kind == NNB_PRIOR_BOX_U && (DD > 0 || f.B >= 2);
 
-  for (int s = p.s0 + 1; s <= p.s0 + p.nsteps; ++s) {
+  // x = flow^-1(z) of a chain is needed only when the launch ends (or for a trace): with all steps in one launch, an
+  // accepted proposal just marks the chain as moved, and ONE extra pass of the flow after the last step -- the step loop's
+  // own code with scale = 0, i.e. z' = z exactly -- recomputes x of the moved chains from their final z.  Same thread, same
+  // tile slot, same instruction sequence on the same z bits as the step that accepted it: the same x bits, without 30
+  // shared-memory loads + 30 global stores per accepted step.
+  const bool defer_x = fused && p.nsteps > 1 && p.trace_z == nullptr;
+  bool moved = false;
+  const int s_end = p.s0 + p.nsteps + (defer_x ? 1 : 0);
+  for (int s = p.s0 + 1; s <= s_end; ++s) {
     const unsigned int step_abs = p.step_offset + (unsigned int)s;
     const bool more = s < p.s0 + p.nsteps;
+    const bool x_pass = s > p.s0 + p.nsteps;   // the extra pass (defer_x)
     bool accept = false;
     unsigned int ncall = 0, tile_cnt = 0;
     bool acc_chain = false;
@@ -635,15 +669,16 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
         g_tc_time[(((size_t)blockIdx.x * kTcMaxTiles + tile) * kTimeSteps + si_t) * kTimeSlots + 5] = gt;
       }
 #endif
-      const float scale_f = p.coop ? *reinterpret_cast<volatile float*>(co_scale_s)
-                                   : (float)(*reinterpret_cast<volatile double*>(&p.ctrl->scale));
+      const float scale_f = x_pass ? 0.f
+                                   : (p.coop ? *reinterpret_cast<volatile float*>(co_scale_s)
+                                             : (float)(*reinterpret_cast<volatile double*>(&p.ctrl->scale)));
       // this step's accept uniform: read now, the slot is refilled for the next step while the flow runs
       const float u01_cur = (active && philox_u && part == NPART - 1) ? *u_slot : 0.f;
       // ---- proposal z' = z + scale * N(0, I) (sampler.py:310-316) ---------------------------------------------------
       if (kZcur) {
         // one thread per chain: the current z (zp) and the step's noise (nz) live in shared memory; replayed noise is
         // copied into nz first so that the flow and the accept update have a single source
-        if (!philox && active) {
+        if (!philox && active && !x_pass) {
           const float* nr = p.replay_normals + ((size_t)(s - 1) * ns + (size_t)c) * d;
           batched<kCh>(d, [&](int i) { return nr[i]; }, [&](int i, float v) { nz[i * 128] = v; });
         }
@@ -676,8 +711,15 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       bool bad_part;
       const float ld_part = tc_flow_inverse<NPART, DD>(
           f, wsm, wsm_u32, t, y, 128, ldp + part * 128, flag, cst.v, cst_t + 2 * d, cst_t + 3 * d, fast_box, bad_part, t_col,
-          fused, [&](int i) { return __fadd_rn(zp[i * 128], __fmul_rn(nz[i * 128], scale_f)); });
+          fused, zp, nz, scale_f);
       NNB_TSTAMP(1);
+      if (x_pass) {   // (uniform over the grid)
+        if (active && moved) {
+          float* px = p.x + (size_t)c;
+          batched<kCh>(d, [&](int i) { return y[i * 128]; }, [&](int i, float v) { px[(size_t)i * ns] = v; });
+        }
+        break;
+      }
       // ---- accept / reject: thread 0 of the chain; thread 1 starts on the next step's noise -------------------------
       if (active && part == 0) {
         float ld_prop = ld_part;
@@ -754,9 +796,16 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
         // because the next step's is drawn after this point
         float* px = p.x + (size_t)c;
         if (acc_chain) {
-          batched<kCh>(d, [&](int i) { return __fadd_rn(zp[i * 128], __fmul_rn(nz[i * 128], scale_f)); },
-                       [&](int i, float v) { zp[i * 128] = v; });
-          batched<kCh>(d, [&](int i) { return y[i * 128]; }, [&](int i, float v) { px[(size_t)i * ns] = v; });
+          if (fused) {   // the flow left z' in nz: the accepted point becomes the current one by a swap of the two pointers
+            float* tmp = zp;
+            zp = nz;
+            nz = tmp;
+          } else {
+            batched<kCh>(d, [&](int i) { return __fadd_rn(zp[i * 128], __fmul_rn(nz[i * 128], scale_f)); },
+                         [&](int i, float v) { zp[i * 128] = v; });
+          }
+          if (defer_x) moved = true;
+          else batched<kCh>(d, [&](int i) { return y[i * 128]; }, [&](int i, float v) { px[(size_t)i * ns] = v; });
         }
         if (p.trace_z) {
           float* tz = p.trace_z + (size_t)s * d * ns + (size_t)c;
@@ -793,6 +842,7 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
         }
       }
     }
+    if (x_pass) break;
     acc_total += accept ? 1u : 0u;
     ncall_total += ncall;
     NNB_TSTAMP(2);
