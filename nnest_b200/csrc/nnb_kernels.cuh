@@ -58,7 +58,7 @@ struct McmcParams {
                                      // arrived << 32 | accepted proposals -- ONE atomic per CTA carries both
   int total_tiles;             // tensor-core kernel, coop mode: tiles that arrive at the per-step grid barrier
   int tc_jc;                   // tensor-core kernel: Philox blocks of the next step drawn during the accept phase (-1 = default)
-  int tc_stagger;   // tensor-core kernel: start delay of the odd tiles of an SM, cycles
+  int tc_delay[4];  // tensor-core kernel: start delay of tile slot j of a CTA at every step, cycles (see mcmc_tc_kernel)
 };
 
 struct SmemView {

@@ -148,7 +148,9 @@ __device__ __forceinline__ void tile_sync(const TcTile& t) { tc::named_bar_sync(
 // every warp poll measured slower: the polling costs issue slots).
 // MEASURED alternatives (round 2, B200, c4; all correct, all slower, removed): every warp of the tile sleeping on the two
 // mbarriers (try_wait with a suspend-time hint) instead of the second tile barrier: +3 %; one Philox block of the next
-// step's noise between the MMA issue and the wait ("slack" work, parked in spare TMEM columns): +6 %.
+// step's noise between the MMA issue and the wait ("slack" work, parked in spare TMEM columns), by every warp: +6 %, by
+// the two non-issuing warps only (which otherwise sleep at the tile barrier): +1.5 % -- the noise phase shrinks by what
+// the flow phase grows; four tanh sharing one MUFU.RCP (5 MUFU + 9 FMUL instead of 8 MUFU): +2 %.
 template <typename F0, typename F1>
 __device__ __forceinline__ void tc_round_trip(TcTile& t, F0 issue0, F1 issue1) {
   tc::wait_st();
@@ -657,10 +659,10 @@ mcmc_tc_kernel(TcFlowDesc f, const float* __restrict__ wglob, TargetDesc td, con
       NNB_TSTAMP(0);
       // The tiles of an SM leave the grid barrier together and would then all run their epilogues at the same moments and
       // all wait for their MMAs at the same moments; odd tiles therefore start the step about half a round trip late
-      // (p.tc_stagger cycles, NNB_TC_STAGGER; measured on the B200 at c4: 2.23 ms -> 2.14 ms per refill at 700 cycles)
-      if (p.tc_stagger > 0 && (tile & 1)) {
+      // (p.tc_delay, NNB_TC_DELAYS; measured on the B200 at c4: 2.23 ms -> 2.14 ms per refill at 700 cycles)
+      if (p.tc_delay[tile & 3] > 0) {
         const long long t0 = clock64();
-        while (clock64() - t0 < (long long)p.tc_stagger) {}
+        while (clock64() - t0 < (long long)p.tc_delay[tile & 3]) {}
       }
 #ifdef NNB_TC_TIMING
       if (tit == 0 && si_t < kTimeSteps) {

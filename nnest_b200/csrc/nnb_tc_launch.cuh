@@ -1,6 +1,7 @@
 // nnb_tc_launch.cuh -- launch logic of the tensor-core MCMC kernel, shared by the generic translation unit (nnb_tc.cu)
 // and the per-dimension specialisations (nnb_tc_d*.cu: x_dim fixed at compile time, num_layers = 1, num_blocks = 3).
 #pragma once
+#include <cstdio>
 #include <cstdlib>
 
 #include "nnb_host.h"
@@ -40,8 +41,15 @@ static int launch_tc_mode(nnb_handle* h, McmcParams p, int steps, cudaStream_t s
   p.cpc = (int)cpc;
   static const int jc_env = [] { const char* e = getenv("NNB_TC_JC"); return e ? atoi(e) : -1; }();
   p.tc_jc = jc_env;
-  static const int stagger_env = [] { const char* e = getenv("NNB_TC_STAGGER"); return e ? atoi(e) : 700; }();
-  p.tc_stagger = ntiles > 1 ? stagger_env : 0;
+  // start delays of the four tile slots (cycles): NNB_TC_DELAYS="d0,d1,d2,d3"; default: odd slots half a round trip late
+  // (sweep on the B200 at c4: 0,700,0,700 and 0,600,0,600 best; four distinct phases or no delay are 1 - 7 % slower)
+  struct Delays { int v[4]; };
+  static const Delays delays_env = [] {
+    Delays dl{{0, 700, 0, 700}};
+    if (const char* e = getenv("NNB_TC_DELAYS")) sscanf(e, "%d,%d,%d,%d", &dl.v[0], &dl.v[1], &dl.v[2], &dl.v[3]);
+    return dl;
+  }();
+  for (int j = 0; j < 4; ++j) p.tc_delay[j] = ntiles > 1 ? delays_env.v[j] : 0;
   // Persistent path: all steps in ONE cooperative launch (every CTA resident, one per SM), the global accept count
   // of each step travels through a grid barrier.  Needs grid <= SM count; otherwise one launch per step.
   static const bool no_coop = getenv("NNB_NO_COOP") != nullptr;
