@@ -28,20 +28,27 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
     float* dst = buf.data() + t.off[k];
     // layer 1: rows 0-15 scale net, 16-31 translate net; columns = masked inputs
     std::vector<float> w1((size_t)32 * K1, 0.f);
+    // (scale net: constants of its activations folded into the weights, see kTcTanhScale / kTcExpScale)
+    const float sc_h[2] = {kTcTanhScale, 1.0f}, sc_o[2] = {kTcExpScale, 1.0f};
     for (int s = 0; s < 2; ++s)
       for (int j = 0; j < H; ++j)
-        for (int a = 0; a < nin; ++a) w1[(size_t)(16 * s + j) * K1 + a] = net[s][(size_t)j * d + (i0 + 2 * a)];
+        for (int a = 0; a < nin; ++a) w1[(size_t)(16 * s + j) * K1 + a] = sc_h[s] * net[s][(size_t)j * d + (i0 + 2 * a)];
     tc::host_pack_b(w1.data(), 32, K1, K1, 32, K1, dst, dst + 32 * K1);
     float* bias1 = dst + 64 * K1;
     float* cb = cst.v + tc_cb_off(d, L, k);          // the same biases in the kernel-parameter layout (TcConsts)
     for (int s = 0; s < 2; ++s)
-      for (int j = 0; j < H; ++j) cb[16 * s + j] = bias1[16 * s + j] = net[s][(size_t)H * d + j];
+      for (int j = 0; j < H; ++j) cb[16 * s + j] = bias1[16 * s + j] = sc_h[s] * net[s][(size_t)H * d + j];
     float* o = bias1 + 32;
     size_t nat_off = (size_t)H * d + H;
     for (int l = 0; l < L; ++l) {
-      for (int s = 0; s < 2; ++s) tc::host_pack_b(net[s] + nat_off, 16, 16, 16, 16, 16, o + 512 * s, o + 512 * s + 256);
+      for (int s = 0; s < 2; ++s) {
+        std::vector<float> w2((size_t)H * H);
+        for (int q = 0; q < H * H; ++q) w2[(size_t)q] = sc_h[s] * net[s][nat_off + q];
+        tc::host_pack_b(w2.data(), 16, 16, 16, 16, 16, o + 512 * s, o + 512 * s + 256);
+      }
       for (int s = 0; s < 2; ++s)
-        for (int j = 0; j < H; ++j) cb[32 + 32 * l + 16 * s + j] = o[1024 + 16 * s + j] = net[s][nat_off + (size_t)H * H + j];
+        for (int j = 0; j < H; ++j)
+          cb[32 + 32 * l + 16 * s + j] = o[1024 + 16 * s + j] = sc_h[s] * net[s][nat_off + (size_t)H * H + j];
       o += 1056;
       nat_off += (size_t)H * H + H;
     }
@@ -49,13 +56,13 @@ int nnb_tc_pack(nnb_handle* h, const float* weights) {
     for (int s = 0; s < 2; ++s) {
       std::fill(w3.begin(), w3.end(), 0.f);
       for (int q = 0; q < nout; ++q)
-        for (int j = 0; j < H; ++j) w3[(size_t)q * 16 + j] = net[s][nat_off + (size_t)(o0 + 2 * q) * H + j];
+        for (int j = 0; j < H; ++j) w3[(size_t)q * 16 + j] = sc_o[s] * net[s][nat_off + (size_t)(o0 + 2 * q) * H + j];
       tc::host_pack_b(w3.data(), N3, 16, 16, N3, 16, o + (size_t)32 * N3 * s, o + (size_t)32 * N3 * s + 16 * N3);
     }
     float* bias3 = o + 64 * N3;
     for (int s = 0; s < 2; ++s)
       for (int q = 0; q < nout; ++q)
-        cb[32 + 32 * L + N3 * s + q] = bias3[N3 * s + q] = net[s][nat_off + (size_t)d * H + (o0 + 2 * q)];
+        cb[32 + 32 * L + N3 * s + q] = bias3[N3 * s + q] = sc_o[s] * net[s][nat_off + (size_t)d * H + (o0 + 2 * q)];
   }
   if (tc_smem_bytes(t, target_doubles(d, NNB_MAX_LIKE_PARAMS), 1, 2) > (size_t)h->max_smem) return NNB_OK;
   NNB_CUDA(h, nnb_reserve(&h->d_weights_tc, &h->weights_tc_cap, buf.size()));

@@ -56,46 +56,35 @@ __host__ __device__ inline bool tc_supported(const FlowDesc& f) {
          tc_cb_floats(f.d, f.L, f.B) <= kTcConstFloats;
 }
 
-#ifndef NNB_TC_FAST_TANH
-#define NNB_TC_FAST_TANH 1
-#endif
+// The scale net's constants are folded into its weights by the host (nnb_tc_pack): the layers that feed a tanh are packed
+// times 2 log2(e), the output layer times -log2(e), so that the tensor core delivers x' = 2 log2(e) x and l' = -log2(e) log_s
+// and the epilogues need no multiply in front of MUFU.EX2:
+//   tanh(x) = 1 - 2 / (2^{x'} + 1)   (e -> inf gives 1, e -> 0 gives -1; near 0 the ABSOLUTE error stays ~2e-7, which is what
+//   matters for the sums the activations feed),   exp(-log_s) = 2^{l'},   log-det = ln 2 * sum l'.
+constexpr float kTcTanhScale = 2.885390081777927f;    // 2 log2(e)
+constexpr float kTcExpScale = -1.4426950408889634f;   // -log2(e)
+__device__ __forceinline__ float tc_tanh_scaled(float xs) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xs));
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(e + 1.0f));
+  return fmaf(-2.0f, rc, 1.0f);
+}
+__device__ __forceinline__ float tc_exp2(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+
 #ifndef NNB_TC_PHILOX_ILP
 #define NNB_TC_PHILOX_ILP 4
 #endif
 constexpr int kTcPhiloxIlp = NNB_TC_PHILOX_ILP;
-// tanh of the s-net.  NNB_TC_FAST_TANH=0: libdevice tanhf (<= 2 ulp).  Default: MUFU ex2/rcp form below.
-__device__ __forceinline__ float tc_tanh(float x) {
-#if NNB_TC_FAST_TANH
-  // 1 - 2 / (e^{2x} + 1) for every x: e -> inf gives 1, e -> 0 gives -1; near 0 the ABSOLUTE error stays ~2e-7
-  // (what matters for the sums the activations feed), so no small-argument branch is needed.  5 instructions.
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
-  float rc;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(e + 1.0f));
-  return fmaf(-2.0f, rc, 1.0f);
-#else
-  return tanhf(x);
-#endif
-}
-
-#ifndef NNB_TC_FAST_EXP
-#define NNB_TC_FAST_EXP 1
-#endif
-// exp of the coupling scale.  NNB_TC_FAST_EXP: ex2.approx(x * log2 e) (2 ulp + |x| * 2^-24)
-__device__ __forceinline__ float tc_exp(float x) {
-#if NNB_TC_FAST_EXP
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
-  return e;
-#else
-  return expf(x);
-#endif
-}
 
 #ifdef NNB_TC_TIMING
-// development probe (NNB_EXTRA_NVCC_FLAGS=-DNNB_TC_TIMING): clock64 stamps of every tile leader at five points of every
-// step -- [0] step start (scale read) [1] flow inverse done [2] accept + state update done [3] next step's noise drawn
-// [4] grid barrier released -- plus [5] globaltimer at step start, [6] proposal written, [7] likelihood done,
+// development probe (NNB_EXTRA_NVCC_FLAGS=-DNNB_TC_TIMING, scripts/dev/tc_timing.py): clock64 stamps of every tile leader at
+// points of every step -- [0] step start (scale read) [1] flow inverse done [2] accept + state update done [3] next step's
+// noise drawn [4] grid barrier released -- plus [5] globaltimer at step start, [6] proposal written, [7] likelihood done,
 // [8] tile's accept count known.  Each translation unit has its own copy.
 constexpr int kTimeSteps = 160, kTimeSlots = 10;
 static __device__ unsigned long long g_tc_time[160 * kTcMaxTiles * kTimeSteps * kTimeSlots];
@@ -191,7 +180,7 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float*
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * c + j]) + bias[8 * c + j];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = c < 2 ? tc_tanh(v[j]) : fmaxf(v[j], 0.f);
+      for (int j = 0; j < 8; ++j) v[j] = c < 2 ? tc_tanh_scaled(v[j]) : fmaxf(v[j], 0.f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) tc::split_tf32(v[j], hi[j], lo[j]);
       tc::tmem_st8(t.lane_tmem + 8 * c, hi);
@@ -210,7 +199,7 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcTile& t, const float*
     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]) + bias[8 * c + j];
     if (c < 2) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = tc_tanh(v[j]);
+      for (int j = 0; j < 8; ++j) v[j] = tc_tanh_scaled(v[j]);
     } else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -345,9 +334,9 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
               const float ls = __uint_as_float(rs[o]) + b3s[o];
               const float tt = __uint_as_float(rt[o]) + b3t[o];
               float* yp = y + (o0 + 2 * o) * ys;
-              xv = (yv[o] - tt) * tc_exp(-ls);
+              xv = (yv[o] - tt) * tc_exp2(ls);   // ls = -log2(e) log_s
               *yp = xv;
-              ld -= ls;
+              ld += ls;
               if (chk) bad |= (xv < lof[o0 + 2 * o]) | (xv > hif[o0 + 2 * o]);
             }
             tc::split_tf32(xv, hi[j], lo[j]);
@@ -385,9 +374,9 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
           const float ls = __uint_as_float(rs[j]) + b3s[o];
           const float tt = __uint_as_float(rt[j]) + b3t[o];
           float* yp = y + (o0 + 2 * o) * ys;
-          xv = (yv[j] - tt) * tc_exp(-ls);
+          xv = (yv[j] - tt) * tc_exp2(ls);   // ls = -log2(e) log_s
           *yp = xv;
-          ld -= ls;
+          ld += ls;
           if (chk) bad |= (xv < lof[o0 + 2 * o]) | (xv > hif[o0 + 2 * o]);
         }
         tc::split_tf32(xv, hi[j], lo[j]);
@@ -398,6 +387,7 @@ __device__ __forceinline__ float tc_flow_inverse(const TcFlowDesc& f, const floa
       }
     }
     }
+    if (k == 0) ld *= 0.6931471805599453f;   // sum of -log2(e) log_s  ->  -sum log_s
     if (NPART > 1 && k == 0) {
       ld_slot[0] = ld;                          // the chain's threads exchange their log-det shares and box flags through
       if (t.part == 1) *bad_slot = bad;         // shared memory (the flag slot carries the accept decision later on)
