@@ -116,7 +116,16 @@ class ClockSampler(object):
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.first = [], None, gpu_index, 0
+
+    def mark(self, wait_s=3.0):
+        """Call right before the timed region: waits until nvidia-smi delivers samples (its start-up -- process creation, NVML
+        initialisation under the driver's global lock -- stalls CUDA launches for tens of milliseconds and must not fall
+        into a timed region that is itself only ~100 ms long) and discards what was sampled before."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < wait_s:
+            time.sleep(0.01)
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -140,10 +149,11 @@ class ClockSampler(object):
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        rows = self.rows[self.first:] or self.rows[-1:]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i] == 'Active'})
+        reasons = sorted({names[i] for r in rows if len(r) >= 9 for i in range(4) if r[5 + i] == 'Active'})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'reasons': reasons, 'samples': len(sm)}
 
@@ -376,11 +386,17 @@ def run_gpu(args, name, wl):
         hsh.update(t.cpu().numpy().tobytes())
     shard_hash = hsh.hexdigest()[:16]
 
-    for it in range(args.warmup):
-        one_refill(it)
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.start()                      # (before the warm-up: see ClockSampler.mark)
+    for it in range(args.warmup + 8):       # (+ 8 untimed refills: allocator pools, lazy module loads, clocks)
+        # keep the results alive as the timed loop does: the previous refill's tensors are released only after the next one
+        # has allocated its own, and the caching allocator must own that second set of blocks BEFORE the timed region (a
+        # cudaMalloc inside an event pair drains the queue and showed up as one step of 6 - 190 ms)
+        st, out, ends = one_refill(it)
+    torch.cuda.synchronize()
+    if rank == 0:
+        clocks.mark()
     launches0 = eng.gpu_launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -394,6 +410,8 @@ def run_gpu(args, name, wl):
     naccept, ncall = last['naccept'], last['ncall']
     launches = eng.gpu_launches - launches0
     ms = [a.elapsed_time(b) for a, b in ev]
+    step_ms = {'min': float(min(ms)), 'median': float(np.median(ms)), 'max': float(max(ms)),   # of this rank's steps
+               'outliers': [(i, round(v, 3)) for i, v in enumerate(ms) if v > 1.5 * float(np.median(ms))][:8]}
     total_ms = float(sum(ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -479,6 +497,7 @@ def run_gpu(args, name, wl):
 
     def time_loop(fn, parts):
         fn(0)
+        fn(0)                               # two untimed calls: the first allocates pinned staging buffers
         parts.clear()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -557,7 +576,7 @@ def run_gpu(args, name, wl):
                     if wl['mode'] == 'hard' else 'MCMCSampler._mcmc_sample(thin=%d): host start points -> host trace' % args.thin,
                     'ms_per_step_parts': e2e_parts},
             'ns_loop': ns_loop,
-            'gpu_launches': launches,
+            'gpu_launches': launches, 'step_ms': step_ms,
             'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
         }))
     if world > 1:
@@ -575,7 +594,7 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--kernel', default='auto', choices=['auto', 'ffma', 'tcgen05', 'warp'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--e2e-steps', type=int, default=10, help='timed steps of the end-to-end arm (<= --steps)')
+    ap.add_argument('--e2e-steps', type=int, default=20, help='timed steps of the end-to-end arm (<= --steps)')
     ap.add_argument('--thin', type=int, default=10, help='c5 end-to-end arm: keep every thin-th state of the trace')
     ap.add_argument('--chains', type=int, default=0, help='development: override the chains of the workload')
     ap.add_argument('--mcmc-steps', type=int, default=0, help='development: override the MCMC steps per refill')

@@ -1,3 +1,4 @@
 #!/bin/bash
-timeout 120 python scripts/dev/tc_timing.py 2>&1 | grep "kernel ms"
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_stress.py tests/test_gpu_api.py -x -q 2>&1 | tail -8
+run() { timeout 300 python bench.py --no-cpu-baseline --e2e-steps 1 2>/dev/null | tail -1 | python -c "import sys,json; j=json.loads(sys.stdin.read()); print('$1', 'value %.4g' % j['value'], 'ms %.3f' % j['ms_per_step'], j.get('step_ms'))"; }
+for i in 1 2 3 4 5 6; do run base; done
+for i in 1 2 3; do NNB_BENCH_NOSLEEP=1 run nosleep; done
