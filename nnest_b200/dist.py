@@ -36,6 +36,16 @@ def ensure_initialized():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     else:
         dist.init_process_group('gloo')
+    import atexit
+    atexit.register(_shutdown)      # the group was created here, so it is torn down here
+
+
+def _shutdown():
+    try:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 def is_distributed():

@@ -20,3 +20,5 @@ import json
 r=json.loads([l for l in open('gpurun_out/r2_m2_bench_n1.json') if l.startswith('{')][-1])
 print('n1', 'value %.3e'%r['value'], 'ms %.3f'%r['ms_per_step'], r['config']['shard_check']['hash'], 'e2e %.3e'%r['e2e']['value'])
 PY
+# the reference's CLI under torchrun (every rank builds the sampler; rank 0 alone owns the run directory)
+(time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29516 examples/nested/run.py --x_dim 10 --likelihood mixture --num_live_points 16384 --mcmc_num_chains 4096 --train_iters 100 --batch_size 1024 --seed 1 --strategy mcmc --log_dir /tmp/logs2) > gpurun_out/r2_m2_c3_run.log 2>&1; tail -6 gpurun_out/r2_m2_c3_run.log | cut -c 1-400; ls /tmp/logs2 | head
