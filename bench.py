@@ -436,9 +436,10 @@ def run_gpu(args, name, wl):
         smp = NestedSampler(d, like, transform=lambda x: ts * x, flow='nvp', num_live_points=n_total, log_dir=log_dir,
                             log_level=logging.WARNING, seed=args.seed)
         smp.trainer.load_state_dict(sd_t)
-        my_u = np.ascontiguousarray(prob['init_u'][sl], dtype=np.float32)     # float32(active_u[idx]) (trainer.py:249)
-        my_l = np.ascontiguousarray(prob['init_logl'][sl])
-        h2d = my_u.size * 4 + my_l.size * 8
+        # this rank's start points in PINNED host memory (float32(active_u[idx]), trainer.py:249) and their loglikes
+        my_u = torch.from_numpy(np.ascontiguousarray(prob['init_u'][sl], dtype=np.float32)).pin_memory()
+        my_l = torch.from_numpy(np.ascontiguousarray(prob['init_logl'][sl])).pin_memory()
+        h2d = my_u.numel() * 4 + my_l.numel() * 8
         d2h = n_total * (2 * d * 4 + 8)
 
         def one_e2e(it):
@@ -571,7 +572,7 @@ def run_gpu(args, name, wl):
                                        '--gpus N' % n_total}},
             'e2e': {'value': e2e_value, 'unit': 'proposals/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': e2e_steps, 'ms_per_step': e2e_ms,
-                    'api': 'Sampler._mcmc_refill(host float32 start points, host loglikes) + Sampler._refill_to_host '
+                    'api': 'Sampler._mcmc_refill(pinned host float32 start points, pinned host loglikes) + Sampler._refill_to_host '
                            '(all_gather over ranks + pinned D2H of first x, last x, last logl)'
                     if wl['mode'] == 'hard' else 'MCMCSampler._mcmc_sample(thin=%d): host start points -> host trace' % args.thin,
                     'ms_per_step_parts': e2e_parts},

@@ -269,15 +269,19 @@ class Sampler(object):
                                                     seed=self.seed, chain_offset=offset)
             return st, ncall
         if init_samples is not None:
-            init_samples = np.asarray(init_samples)
-            hu = self._pinned('init_u', init_samples.shape, torch.float32)
-            hu.numpy()[...] = init_samples                      # float64 -> float32 (trainer.py:249) into pinned memory
-            u = hu.to(self.device, non_blocking=True)
+            def staged(name, arr, dtype, shape):
+                # page-locked torch tensors of the right dtype go to the device as they are; anything else (NumPy arrays,
+                # float64) is converted into a reusable pinned staging buffer first (trainer.py:249: float32 start points)
+                if isinstance(arr, torch.Tensor) and arr.dtype == dtype and arr.is_pinned() and arr.is_contiguous():
+                    return arr.to(self.device, non_blocking=True)
+                h = self._pinned(name, shape, dtype)
+                h.numpy()[...] = arr.numpy() if isinstance(arr, torch.Tensor) else np.asarray(arr)
+                return h.to(self.device, non_blocking=True)
+            shape = tuple(init_samples.shape)
+            u = staged('init_u', init_samples, torch.float32, shape)
             logl = None
             if init_loglikes is not None:
-                hl = self._pinned('init_logl', (init_samples.shape[0],), torch.float64)
-                hl.numpy()[...] = init_loglikes
-                logl = hl.to(self.device, non_blocking=True)
+                logl = staged('init_logl', init_loglikes, torch.float64, (shape[0],))
             st, nbad, ncall = self.engine.mcmc_init(u.shape[0], init_u=u.t().contiguous(), init_logl=logl,
                                                     seed=self.seed, chain_offset=offset)
             return st, ncall
