@@ -7,6 +7,7 @@
 
 #include "nnb_host.h"
 #include "nnb_train.cuh"
+#include "nnb_nn_tc.cuh"
 
 using namespace nnb;
 
@@ -143,7 +144,69 @@ extern "C" int nnb_mean_nn_distance(nnb_handle* h, const double* x, int64_t n, i
   }
   double* acc = h->d_nn_part;
   static const bool f64_only = getenv("NNB_NN_F64") != nullptr;
-  if (d <= 32 && !f64_only) {
+  static const bool no_tc = getenv("NNB_NN_NO_TC") != nullptr;
+  const int K = nn_tc_k(d);
+  // query tiles per CTA (4, 2 or 1) and ring stages (4 or 3): the largest that fit the shared memory
+  int nn_qt = 0, nn_stages = 3;
+  for (int qt : {4, 2, 1})
+    if (!nn_qt && nn_tc_smem_bytes(K, qt, 3) <= (size_t)h->max_smem) nn_qt = qt;
+  if (nn_qt && nn_tc_smem_bytes(K, nn_qt, 4) <= (size_t)h->max_smem) nn_stages = 4;
+  if (const char* e = getenv("NNB_NN_QT")) {          // development override: query tiles per CTA
+    const int q = atoi(e);
+    if ((q == 1 || q == 2 || q == 4) && nn_tc_smem_bytes(K, q, 3) <= (size_t)h->max_smem) {
+      nn_qt = q;
+      nn_stages = nn_tc_smem_bytes(K, q, 4) <= (size_t)h->max_smem ? 4 : 3;
+    }
+  }
+  if (const char* e = getenv("NNB_NN_STAGES")) {
+    const int q = atoi(e);
+    if ((q == 3 || q == 4) && nn_qt && nn_tc_smem_bytes(K, nn_qt, q) <= (size_t)h->max_smem) nn_stages = q;
+  }
+  if (n >= 8192 && nn_qt && !f64_only && !no_tc) {
+    // tensor-core ratings (3xTF32, one augmented dot product per pair) + exact float64 refinement: nnb_nn_tc.cuh
+    const int tiles = grid;   // 128 rows per tile
+    const int qgroups = (tiles + nn_qt - 1) / nn_qt;
+    // candidate splits: ONE wave of CTAs.  Every (query, split, column half) costs at least one exact evaluation, so more
+    // splits than it takes to fill the SMs only add work (65 536 x 30, QT = 4: 3.4 / 3.9 / 4.2 ms at 1 / 2 / 3 splits)
+    int splits = h->sm_count / qgroups;
+    if (splits < 1) splits = 1;
+    if (splits > 32) splits = 32;
+    if (const char* e = getenv("NNB_NN_SPLITS")) splits = atoi(e) > 0 ? atoi(e) : splits;   // development override
+    const int tps = (tiles + splits - 1) / splits;
+    splits = (tiles + tps - 1) / tps;
+    const int nparts = 64;
+    const size_t tile_fl = (size_t)tiles * 128 * K;
+    // workspace (floats): 4 packed arrays | centre partials (doubles) | R2 bits | best [splits][n] (doubles)
+    const size_t part_off = 4 * tile_fl, r2_off = part_off + (size_t)2 * nparts * d + 2, best_off = (r2_off + 4 + 1) & ~(size_t)1;
+    const size_t need = best_off + (size_t)2 * (2 * splits) * n + 4;   // two column halves per split
+    if (h->nn_ws_floats < need) {
+      if (h->d_nn_ws) cudaFree(h->d_nn_ws);
+      h->d_nn_ws = nullptr;
+      h->nn_ws_floats = 0;
+      NNB_CUDA(h, cudaMalloc(&h->d_nn_ws, need * sizeof(float)));
+      h->nn_ws_floats = need;
+    }
+    float* ws = h->d_nn_ws;
+    float *a_hi = ws, *a_lo = ws + tile_fl, *b_hi = ws + 2 * tile_fl, *b_lo = ws + 3 * tile_fl;
+    double* part = reinterpret_cast<double*>(ws + part_off);
+    unsigned int* r2 = reinterpret_cast<unsigned int*>(ws + r2_off);
+    double* best = reinterpret_cast<double*>(ws + best_off);
+    NNB_CUDA(h, cudaMemsetAsync(r2, 0, sizeof(unsigned int), st));
+    nn_tc_centre_kernel<<<nparts, 256, 0, st>>>(x, n, d, part);
+    nn_tc_pack_kernel<<<tiles, 128, (size_t)d * sizeof(double), st>>>(x, n, d, K, part, nparts, a_hi, a_lo, b_hi, b_lo, r2);
+    const size_t smem = nn_tc_smem_bytes(K, nn_qt, nn_stages);
+    const dim3 g2(qgroups, splits);
+#define NNB_NN_LAUNCH(QT)                                                                                             \
+  do {                                                                                                               \
+    NNB_CUDA(h, nnb_set_smem(nn_tc_kernel<QT>, smem));                                                               \
+    nn_tc_kernel<QT><<<g2, kNnThreads, smem, st>>>(a_hi, a_lo, b_hi, b_lo, x, n, d, K, r2, tiles, tps, nn_stages, best); \
+  } while (0)
+    if (nn_qt == 4) NNB_NN_LAUNCH(4);
+    else if (nn_qt == 2) NNB_NN_LAUNCH(2);
+    else NNB_NN_LAUNCH(1);
+#undef NNB_NN_LAUNCH
+    nn_reduce_kernel<<<grid, 128, 0, st>>>(best, n, 2 * splits, acc);
+  } else if (d <= 32 && !f64_only) {
     // float32 prefilter + exact float64 refinement (same result as the brute force, ~2.5x faster)
     const int DP = d <= 8 ? 8 : (d <= 16 ? 16 : 32);
     // candidate splits: enough blocks for ~8 per SM

@@ -294,3 +294,30 @@ def test_mean_nn_distance_prefilter_is_exact(engine, n, d):
         best[lo:lo + 512] = dd.min(1)
     want = np.sqrt(best).mean()
     assert abs(got - want) <= 1e-12 * want
+
+
+@pytest.mark.parametrize('n,d,kind', [(20000, 30, 'uniform'), (9000, 12, 'two_clusters'), (8300, 52, 'uniform'),
+                                      (8200, 1, 'uniform'), (9000, 30, 'tight'), (8300, 36, 'uniform')])
+def test_mean_nn_distance_tensor_core_path_is_exact(engine, n, d, kind):
+    """n >= 8192: the pairs are rated on the tensor cores (3xTF32, csrc/nnb_nn_tc.cuh) and the candidates within the error
+    bound of the running minimum re-evaluated in float64 -- the same minimum as the float64 brute force (numpy), for a
+    typical live set, for two far-apart tight clusters (the slack then covers a whole cluster: many exact evaluations, same
+    answer), for K = 56 (one query tile per CTA), K = 40 (two) and K = 8 operands, with duplicates and near-ties."""
+    rng = np.random.RandomState(n + d)
+    if kind == 'uniform':
+        x = rng.uniform(-1, 1, size=(n, d))
+    elif kind == 'tight':
+        x = rng.normal(size=(n, d)) * 1e-3 + 0.7
+    else:
+        x = rng.normal(size=(n, d)) * 1e-3
+        x[n // 2:] += 10.0
+    x[5] = x[6]
+    x[7] = x[8] + 1e-9
+    got = engine.mean_nn_distance(torch.from_numpy(x).cuda())
+    best = np.full(n, np.inf)
+    for lo in range(0, n, 256):
+        dd = ((x[lo:lo + 256, None, :] - x[None, :, :]) ** 2).sum(-1)
+        dd[np.arange(min(256, n - lo)), np.arange(lo, min(n, lo + 256))] = np.inf
+        best[lo:lo + 256] = dd.min(1)
+    want = np.sqrt(best).mean()
+    assert abs(got - want) <= 1e-12 * want
