@@ -29,6 +29,19 @@ class NSBook(object):
             return np.empty((0, 0)), np.empty((0,)), np.empty((0,))
         return np.concatenate(self.saved_v), np.concatenate(self.saved_logl), np.concatenate(self.saved_logwt)
 
+    def samples_with(self, active_v):
+        """np.concatenate((dead points, active_v)) built with ONE copy of the dead points (they are kept as chunks; at
+        config-4 size the dead points are 2.1 GB and concatenating them twice costs a second of page faults)."""
+        active_v = np.asarray(active_v, dtype=np.float64)
+        m = sum(c.shape[0] for c in self.saved_v)
+        out = np.empty((m + active_v.shape[0], active_v.shape[1]), dtype=np.float64)
+        pos = 0
+        for c in self.saved_v:
+            out[pos:pos + c.shape[0]] = c.reshape(c.shape[0], -1)
+            pos += c.shape[0]
+        out[m:] = active_v
+        return out
+
     def num_dead(self):
         return int(sum(len(a) for a in self.saved_logl))
 

@@ -401,7 +401,8 @@ class NestedSampler(Sampler):
                     self.weights = np.exp(logwt - bk.logz)
                     self._save_samples(self.samples, self.loglikes, weights=self.weights)
 
-        saved_v, saved_logl, saved_logwt = bk.dead_points()
+        saved_logl = np.concatenate(bk.saved_logl) if bk.saved_logl else np.empty((0,))
+        saved_logwt = np.concatenate(bk.saved_logwt) if bk.saved_logwt else np.empty((0,))
         logz, h, it = bk.logz, bk.h, bk.it
         # nested.py:487-500: the remaining live points, each with the final volume / nlive -- the reference's scalar loop
         # as sequential NumPy accumulations + the exact host recurrence for H (bit-identical, see bookkeeping.NSBook.bulk)
@@ -419,8 +420,7 @@ class NestedSampler(Sampler):
         self.h = h
         self.logzerr = np.sqrt(h / nlive)
         self.niter = it + 1
-        self.samples = np.concatenate((saved_v.reshape(-1, self.x_dim), active_v)) if len(saved_logl) else \
-            np.array(active_v, copy=True)
+        self.samples = bk.samples_with(active_v)        # dead points followed by the remaining live points
         self.weights = np.exp(np.concatenate((saved_logwt, fin_logwt)) - logz)
         self.loglikes = np.concatenate((saved_logl, active_logl))
         self.active_u, self.active_logl = active_u, active_logl

@@ -106,3 +106,26 @@ def test_chain_text_writer_matches_reference_format(lib, tmp_path):
     # append mode, no header
     n2 = lib.nnb_write_chain_text(path.encode(), None, table.ctypes.data_as(_lib._dp), 3, 5, 1)
     assert n2 > 0 and len(open(path).read().splitlines()) == table.shape[0] + 4
+
+
+def test_save_samples_in_blocks_writes_the_same_bytes(tmp_path):
+    """Sampler._save_samples hands the rows to nnb_write_chain_text in blocks (appending): the file is byte for byte what
+    the reference's '%.5E' loop writes (nnest/sampler.py:494-511), whatever the block size, with header and derived columns."""
+    import types
+    from nnest_b200.sampler import Sampler
+    rng = np.random.RandomState(0)
+    for n, d, names, nder in ((1000, 5, None, 0), (37, 3, ['a', 'b', 'c'], 0), (0, 4, None, 0), (50, 2, None, 2)):
+        smp = rng.normal(size=(n, d)) * 10 ** rng.uniform(-8, 8, size=(n, 1))
+        lgl = rng.normal(size=n) * 100
+        w = rng.uniform(size=n) * 10 ** rng.uniform(-40, 0, size=n)
+        der = rng.normal(size=(n, nder)) if nder else None
+        cols = [np.maximum(w, 1e-30)[:, None], -lgl[:, None], smp] + ([der] if nder else [])
+        want = ''.join(' '.join('%.5E' % v for v in row) + '\n' for row in np.concatenate(cols, axis=1))
+        if names:
+            want = '#weight minusloglike ' + ' '.join(names) + '\n' + want
+        for step in (1 << 20, 7):
+            out = tmp_path / ('c_%d_%d' % (n, step))
+            out.mkdir()
+            me = types.SimpleNamespace(param_names=names, logs={'chains': str(out)}, _CHAIN_ROWS_PER_CALL=step)
+            Sampler._save_samples(me, smp, lgl, weights=w, derived_samples=der)
+            assert (out / 'chain.txt').read_bytes().decode() == want

@@ -142,3 +142,19 @@ def test_information_recurrence_is_bit_exact(lib):
     got = lib.nnb_ns_information(0.0, dp(a), dp(b), dp(zp), dp(zn), n)
     assert got == h
     assert lib.nnb_ns_information(1.5, dp(a), dp(b), dp(zp), dp(zn), 0) == 1.5
+
+
+def test_samples_with_is_the_concatenation_of_dead_and_live_points():
+    """NSBook.samples_with (one copy of the chunked dead points) == np.concatenate((dead points, active_v)), the array the
+    reference builds at the end of a run (nested.py:487-500)."""
+    from nnest_b200.bookkeeping import NSBook
+    rng = np.random.RandomState(3)
+    bk = NSBook(10)
+    av = rng.normal(size=(10, 3))
+    assert np.array_equal(bk.samples_with(av), av)
+    for k in (1, 5, 2):
+        bk.saved_v.append(rng.normal(size=(k, 3)))
+        bk.saved_logl.append(np.zeros(k))
+        bk.saved_logwt.append(np.zeros(k))
+    want = np.concatenate((bk.dead_points()[0].reshape(-1, 3), av))
+    assert np.array_equal(bk.samples_with(av), want)
