@@ -112,6 +112,7 @@ def test_save_samples_in_blocks_writes_the_same_bytes(tmp_path):
     """Sampler._save_samples hands the rows to nnb_write_chain_text in blocks (appending): the file is byte for byte what
     the reference's '%.5E' loop writes (nnest/sampler.py:494-511), whatever the block size, with header and derived columns."""
     import types
+    import numpy as np
     from nnest_b200.sampler import Sampler
     rng = np.random.RandomState(0)
     for n, d, names, nder in ((1000, 5, None, 0), (37, 3, ['a', 'b', 'c'], 0), (0, 4, None, 0), (50, 2, None, 2)):
