@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NNB_ABI_VERSION 12
+#define NNB_ABI_VERSION 13
 #define NNB_MAX_DIM 128      /* x_dim */
 #define NNB_MAX_BLOCKS 16    /* num_blocks */
 #define NNB_MAX_LIKE_PARAMS 160
@@ -338,6 +338,17 @@ typedef struct nnb_train_args {
 } nnb_train_args;
 
 int nnb_train_epoch(nnb_handle* h, const nnb_train_args* args, void* stream);
+/*
+ * The same epoch in two halves, so that the device does not idle while the host looks at the losses (the reference's loop,
+ * trainer.py:170-207, decides after EVERY epoch whether the validation loss improved and whether patience ran out):
+ *   nnb_train_epoch_begin queues the epoch on `stream` (the *_out members of args are ignored) and returns;
+ *   nnb_train_epoch_end   waits for the OLDEST epoch in flight and returns its losses.
+ * At most two epochs may be in flight.  A caller that knows epoch e cannot end the fit (patience cannot run out at e, e is
+ * not the last one) begins epoch e + 1 before it ends epoch e; weights it may still need (the best-so-far copy) have to
+ * be snapshotted by stream-ordered copies between the two begins.  nnb_train_epoch == begin + end.
+ */
+int nnb_train_epoch_begin(nnb_handle* h, const nnb_train_args* args, void* stream);
+int nnb_train_epoch_end(nnb_handle* h, double* train_loss_sum, double* val_nll_sum, int* grid);
 /* 1 when nnb_train_epoch handles this architecture with max_smem_bytes of shared memory per CTA (B200: 232448) */
 int nnb_train_supported(int x_dim, int hidden_dim, int num_layers, int num_blocks, int max_smem_bytes);
 
@@ -374,6 +385,15 @@ int nnb_chain_autocorr(nnb_handle* h, const float* trace_x, int64_t T, int d, in
  */
 int64_t nnb_write_chain_text(const char* path, const char* header, const double* table, int64_t rows, int cols,
                              int append);
+/*
+ * The same file written straight from the arrays `_save_samples` receives (no (rows, cols) table in between): row r is
+ * max(weights[r], min_weight), -loglikes[r], samples[r][0..d), derived[r][0..n_derived).  All arrays [host] float64,
+ * row-major; weights may be NULL (all ones, sampler.py:495-496), derived may be NULL when n_derived == 0.  NaN is spelled
+ * "NAN" whatever its sign bit, as Python's '%.5E' does.
+ */
+int64_t nnb_write_chain_rows(const char* path, const char* header, const double* weights, const double* loglikes,
+                             const double* samples, int d, const double* derived, int n_derived, int64_t rows,
+                             double min_weight, int append);
 
 #ifdef __cplusplus
 }

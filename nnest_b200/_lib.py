@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, os.environ.get('NNB_LIB_DIR', 'lib'), 'libnnb.so')   # see build.py
 
-NNB_ABI_VERSION = 12
+NNB_ABI_VERSION = 13
 NNB_MAX_DIM = 128
 NNB_MAX_BLOCKS = 16
 
@@ -87,6 +87,8 @@ SYMBOLS = {
     'nnb_gather_rows_f32': (C.c_int, [_fp, C.c_int64, C.c_int, _ip, C.c_int64, _dp]),
     'nnb_ns_apply': (C.c_int, [_ip, _ip, C.c_int64, C.c_int64, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64, _dp]),
     'nnb_train_epoch': (C.c_int, [C.c_void_p, C.POINTER(nnb_train_args), C.c_void_p]),
+    'nnb_train_epoch_begin': (C.c_int, [C.c_void_p, C.POINTER(nnb_train_args), C.c_void_p]),
+    'nnb_train_epoch_end': (C.c_int, [C.c_void_p, _dp, _dp, C.POINTER(C.c_int)]),
     'nnb_train_supported': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     'nnb_mean_nn_distance': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, _dp, C.c_void_p]),
     'nnb_chain_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp,
@@ -95,6 +97,8 @@ SYMBOLS = {
                                      C.c_int, _dp, C.c_void_p]),
     'nnb_ns_information': (C.c_double, [C.c_double, _dp, _dp, _dp, _dp, C.c_int64]),
     'nnb_write_chain_text': (C.c_int64, [C.c_char_p, C.c_char_p, _dp, C.c_int64, C.c_int, C.c_int]),
+    'nnb_write_chain_rows': (C.c_int64, [C.c_char_p, C.c_char_p, _dp, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int64,
+                                         C.c_double, C.c_int]),
 }
 
 _lib = None

@@ -77,6 +77,8 @@ extern "C" void nnb_destroy(nnb_handle* h) {
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
   if (h->d_train_ctrl) cudaFree(h->d_train_ctrl);
   if (h->h_train_ctrl) cudaFreeHost(h->h_train_ctrl);
+  for (cudaEvent_t e : h->train_ev)
+    if (e) cudaEventDestroy(e);
   if (h->d_train_ws) cudaFree(h->d_train_ws);
   if (h->d_stats_ws) cudaFree(h->d_stats_ws);
   if (h->d_nn_part) cudaFree(h->d_nn_part);
@@ -430,31 +432,41 @@ extern "C" int64_t nnb_consume_scan(const float* first, const float* last, const
   return -1;
 }
 
-// Min-heap over (logl, index): the top is np.argmin's answer (first index among equal minima).
+// Min-heap over (logl, index): the top is np.argmin's answer (first index among equal minima).  The key travels with the
+// slot index in the heap node: a sift-down step reads the two children from ONE cache line instead of chasing
+// heap[] -> key[] twice per level (65 536 live points: 2.4x faster per replacement).
 namespace {
 struct LiveHeap {
-  std::vector<double> key;
-  std::vector<int64_t> heap;   // heap of slot indices
-  explicit LiveHeap(const double* logl, int64_t n) : key(logl, logl + n), heap((size_t)n) {
-    for (int64_t i = 0; i < n; ++i) heap[(size_t)i] = i;
+  struct Node { double key; int64_t slot; };
+  std::vector<Node> heap;
+  explicit LiveHeap(const double* logl, int64_t n) : heap((size_t)n) {
+    for (int64_t i = 0; i < n; ++i) heap[(size_t)i] = Node{logl[i], i};
     for (int64_t i = n / 2 - 1; i >= 0; --i) sift_down(i);
   }
-  bool less(int64_t a, int64_t b) const { return key[(size_t)a] < key[(size_t)b] || (key[(size_t)a] == key[(size_t)b] && a < b); }
+  static bool less(const Node& a, const Node& b) { return a.key < b.key || (a.key == b.key && a.slot < b.slot); }
   void sift_down(int64_t i) {
     const int64_t n = (int64_t)heap.size();
+    const Node x = heap[(size_t)i];
     for (;;) {
-      int64_t l = 2 * i + 1, r = l + 1, m = i;
-      if (l < n && less(heap[(size_t)l], heap[(size_t)m])) m = l;
-      if (r < n && less(heap[(size_t)r], heap[(size_t)m])) m = r;
-      if (m == i) return;
-      std::swap(heap[(size_t)i], heap[(size_t)m]);
-      i = m;
+      int64_t c = 2 * i + 1;
+      if (c >= n) break;
+      if (c + 1 < n && less(heap[(size_t)c + 1], heap[(size_t)c])) ++c;
+      if (!less(heap[(size_t)c], x)) break;
+      heap[(size_t)i] = heap[(size_t)c];
+      i = c;
     }
+    heap[(size_t)i] = x;
   }
-  int64_t top() const { return heap[0]; }
+  int64_t top() const { return heap[0].slot; }
+  double top_key() const { return heap[0].key; }
   void replace_top(double v) {   // the slot at the top takes a new (larger) key
-    key[(size_t)heap[0]] = v;
+    heap[0].key = v;
     sift_down(0);
+  }
+  double max_key() const {
+    double m = heap[0].key;
+    for (const Node& nd : heap) m = nd.key > m ? nd.key : m;
+    return m;
   }
 };
 }  // namespace
@@ -476,7 +488,7 @@ extern "C" int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, cons
   int64_t k = 0;
   for (; k < max_iters; ++k) {
     const int64_t worst = hp.top();
-    const double loglstar = hp.key[(size_t)worst];
+    const double loglstar = hp.top_key();
     worst_out[k] = worst;
     loglstar_out[k] = loglstar;
     prev_out[k] = writer[(size_t)worst];
@@ -490,8 +502,7 @@ extern "C" int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, cons
     writer[(size_t)worst] = k;
     hp.replace_top(nl);
     if (loglstar == maxl) {   // every live point was equal: recompute (np.max after the replacement)
-      maxl = hp.key[0];
-      for (int64_t i = 1; i < nlive; ++i) maxl = hp.key[(size_t)i] > maxl ? hp.key[(size_t)i] : maxl;
+      maxl = hp.max_key();
     } else if (nl > maxl) {
       maxl = nl;
     }
@@ -556,43 +567,52 @@ extern "C" int nnb_ns_apply(const int64_t* worst, const int64_t* prev, int64_t n
 }
 
 // Chain files of the reference (nnest/sampler.py:494-511): one row per sample, every number '%.5E', single spaces.
-// Rows are formatted by several host threads into private buffers and written in order.
-extern "C" int64_t nnb_write_chain_text(const char* path, const char* header, const double* table, int64_t rows,
-                                        int cols, int append) {
-  if (!path || (!table && rows > 0) || rows < 0 || cols <= 0) return NNB_ERR_ARG;
+// Rows are formatted by several host threads into private buffers, batch by batch, and written in order by the calling
+// thread WHILE the next batch is being formatted (two sets of buffers): a config-4 chain is 3.6 GB of text, and the
+// page-cache write of a batch takes about as long as formatting it.
+namespace {
+// One value as printf("%.5E") / Python's '%.5E' % v spell it; returns the end of the text.
+inline char* format_5e(char* w, double v) {
+  if (std::isfinite(v)) {
+    // std::to_chars(scientific, 5) is the correctly rounded form printf("%.5e") prints (identical bytes, 3x faster than
+    // snprintf); the reference writes an upper-case E
+    auto r = std::to_chars(w, w + 16, v, std::chars_format::scientific, 5);
+    for (char* q = w; q < r.ptr; ++q)
+      if (*q == 'e') *q = 'E';
+    return r.ptr;
+  }
+  if (v != v) { memcpy(w, "NAN", 3); return w + 3; }     // Python prints NAN whatever the sign bit (printf: "-NAN")
+  return w + snprintf(w, 16, "%.5E", v);                  // INF / -INF
+}
+
+// fill(r, out): the `cols` values of row r.
+template <typename Fill>
+int64_t write_chain(const char* path, const char* header, int64_t rows, int cols, int append, Fill fill) {
   FILE* f = fopen(path, append ? "a" : "w");
   if (!f) return NNB_ERR_ARG;
   int64_t written = 0;
   if (header && header[0]) written += fprintf(f, "%s\n", header);
-  const int64_t chunk = 1 << 16;   // rows per batch of threads' work items
+  const int64_t chunk = 1 << 15;   // rows per work item
   unsigned hw = std::thread::hardware_concurrency();
   const int nthreads = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
   const size_t per_row = (size_t)cols * 14 + 2;   // "-1.23456E+308 " is 14 characters at most
-  std::vector<std::string> bufs((size_t)nthreads);
+  std::vector<std::string> bufs[2] = {std::vector<std::string>((size_t)nthreads), std::vector<std::string>((size_t)nthreads)};
   bool ok = true;
-  for (int64_t r0 = 0; r0 < rows && ok; r0 += chunk * nthreads) {
+  auto format_batch = [&](int64_t r0, std::vector<std::string>& set) {
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; ++t) {
       const int64_t a = r0 + t * chunk, b = std::min(rows, a + chunk);
-      bufs[(size_t)t].clear();
+      set[(size_t)t].clear();
       if (a >= b) continue;
-      th.emplace_back([&, t, a, b] {
-        std::string& out = bufs[(size_t)t];
+      th.emplace_back([&set, &fill, t, a, b, cols, per_row] {
+        std::string& out = set[(size_t)t];
         out.resize((size_t)(b - a) * per_row);
+        std::vector<double> rowbuf((size_t)cols);
         char* w = &out[0];
         for (int64_t r = a; r < b; ++r) {
-          const double* row = table + r * cols;
+          fill(r, rowbuf.data());
           for (int c = 0; c < cols; ++c) {
-            // std::to_chars(scientific, 5) is the correctly rounded shortest-width form printf("%.5e") prints (identical
-            // bytes, 3x faster than snprintf); the reference writes an upper-case E
-            if (std::isfinite(row[c])) {
-              auto r = std::to_chars(w, w + 16, row[c], std::chars_format::scientific, 5);
-              for (char* q = w; q < r.ptr; ++q)
-                if (*q == 'e') *q = 'E';
-              w = r.ptr;
-            } else {
-              w += snprintf(w, 16, "%.5E", row[c]);   // INF / NAN spelled as printf does
-            }
+            w = format_5e(w, rowbuf[(size_t)c]);
             *w++ = c + 1 < cols ? ' ' : '\n';
           }
         }
@@ -600,16 +620,53 @@ extern "C" int64_t nnb_write_chain_text(const char* path, const char* header, co
       });
     }
     for (auto& x : th) x.join();
+  };
+  const int64_t batch = chunk * nthreads;
+  int cur = 0;
+  if (rows > 0) format_batch(0, bufs[0]);
+  for (int64_t r0 = 0; r0 < rows && ok; r0 += batch) {
+    std::thread next;
+    if (r0 + batch < rows) next = std::thread([&, r0, cur] { format_batch(r0 + batch, bufs[cur ^ 1]); });
     for (int t = 0; t < nthreads; ++t) {
-      const std::string& o = bufs[(size_t)t];
+      const std::string& o = bufs[cur][(size_t)t];
       if (!o.empty()) {
-        if (fwrite(o.data(), 1, o.size(), f) != o.size()) ok = false;
+        if (ok && fwrite(o.data(), 1, o.size(), f) != o.size()) ok = false;
         written += (int64_t)o.size();
       }
     }
+    if (next.joinable()) next.join();
+    cur ^= 1;
   }
   if (fclose(f) != 0) ok = false;
   return ok ? written : (int64_t)NNB_ERR_ARG;
+}
+}  // namespace
+
+extern "C" int64_t nnb_write_chain_text(const char* path, const char* header, const double* table, int64_t rows,
+                                        int cols, int append) {
+  if (!path || (!table && rows > 0) || rows < 0 || cols <= 0) return NNB_ERR_ARG;
+  return write_chain(path, header, rows, cols, append, [=](int64_t r, double* out) {
+    memcpy(out, table + r * cols, sizeof(double) * (size_t)cols);
+  });
+}
+
+// The same file straight from the arrays the sampler holds (sampler.py:494-511: np.column_stack of the clipped weights,
+// -loglikes, samples, derived), without materialising that table: row r = max(weights[r], min_weight), -loglikes[r],
+// samples[r][0..d), derived[r][0..n_derived).  weights == NULL means all ones.
+extern "C" int64_t nnb_write_chain_rows(const char* path, const char* header, const double* weights,
+                                        const double* loglikes, const double* samples, int d, const double* derived,
+                                        int n_derived, int64_t rows, double min_weight, int append) {
+  if (!path || rows < 0 || d <= 0 || n_derived < 0 || (rows > 0 && (!loglikes || !samples)) ||
+      (n_derived > 0 && rows > 0 && !derived))
+    return NNB_ERR_ARG;
+  const int cols = 2 + d + n_derived;
+  return write_chain(path, header, rows, cols, append, [=](int64_t r, double* out) {
+    const double w = weights ? weights[r] : 1.0;
+    out[0] = w < min_weight ? min_weight : w;            // max(w, min_weight) of the reference: NaN stays NaN
+    out[1] = -loglikes[r];
+    memcpy(out + 2, samples + r * d, sizeof(double) * (size_t)d);
+    if (n_derived) memcpy(out + 2 + d, derived + r * n_derived, sizeof(double) * (size_t)n_derived);
+  });
 }
 
 // Information recurrence of nested sampling (nnest/nested.py:283), sequential over the iterations of a run:

@@ -43,7 +43,10 @@ struct nnb_handle {
   Ctrl* h_ctrl = nullptr;  // pinned
   // flow fitting (nnb_train.cu)
   void* d_train_ctrl = nullptr;
-  void* h_train_ctrl = nullptr;   // pinned
+  void* h_train_ctrl = nullptr;   // pinned: two result slots (an epoch may be queued behind the one whose losses are read)
+  cudaEvent_t train_ev[2] = {nullptr, nullptr};   // "slot k holds the losses of its epoch"
+  int train_slot_grid[2] = {0, 0};
+  unsigned train_begun = 0, train_ended = 0;      // epochs begun / collected (begun - ended <= 2)
   float* d_train_ws = nullptr;    // gradient exchange buffers + per-CTA Adam moments (several CTAs per mini-batch)
   size_t train_ws_floats = 0;
   double* d_nn_part = nullptr;    // per-block partial sums of nnb_mean_nn_distance

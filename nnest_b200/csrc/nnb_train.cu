@@ -19,7 +19,9 @@ size_t train_ctrl_bytes(const nnb_handle* h) { return kLossOff + (size_t)2 * h->
 
 int ensure_train_ctrl(nnb_handle* h) {
   if (!h->d_train_ctrl) NNB_CUDA(h, cudaMalloc(&h->d_train_ctrl, train_ctrl_bytes(h)));
-  if (!h->h_train_ctrl) NNB_CUDA(h, cudaMallocHost(&h->h_train_ctrl, train_ctrl_bytes(h)));
+  if (!h->h_train_ctrl) NNB_CUDA(h, cudaMallocHost(&h->h_train_ctrl, 2 * train_ctrl_bytes(h)));
+  for (cudaEvent_t& e : h->train_ev)
+    if (!e) NNB_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return NNB_OK;
 }
 
@@ -45,8 +47,13 @@ extern "C" int nnb_train_supported(int x_dim, int hidden_dim, int num_layers, in
   return train_smem_bytes(x_dim, hidden_dim, num_layers, num_blocks) <= (size_t)max_smem_bytes ? 1 : 0;
 }
 
-extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* stream) {
+// The epoch is queued on the stream and its losses travel to a pinned slot; nnb_train_epoch_end collects them.  Up to two
+// epochs may be in flight: the caller queues epoch e + 1 BEFORE it reads the losses of epoch e whenever the outcome of
+// epoch e cannot end the fit, so the device never waits for the host between epochs (include/nnb.h).
+extern "C" int nnb_train_epoch_begin(nnb_handle* h, const nnb_train_args* a, void* stream) {
   if (!h || !a) return NNB_ERR_ARG;
+  if (h->train_begun - h->train_ended >= 2)
+    return nnb_fail(h, NNB_ERR_STATE, "nnb_train_epoch_begin: two epochs are already in flight (call nnb_train_epoch_end)");
   cudaStream_t st = (cudaStream_t)stream;
   const int d = a->x_dim, H = a->hidden_dim, L = a->num_layers, B = a->num_blocks;
   if (!nnb_train_supported(d, H, L, B, h->max_smem))
@@ -117,16 +124,40 @@ extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* str
   else if (H == 32 && L == 1) rc = launch_train<32, 1>(h, p, grid, smem, st);
   else rc = launch_train<32, 2>(h, p, grid, smem, st);
   if (rc) return rc;
-  NNB_CUDA(h, cudaMemcpyAsync(h->h_train_ctrl, h->d_train_ctrl, train_ctrl_bytes(h), cudaMemcpyDeviceToHost, st));
-  NNB_CUDA(h, cudaStreamSynchronize(st));
+  const int slot = (int)(h->train_begun & 1u);
+  NNB_CUDA(h, cudaMemcpyAsync(static_cast<char*>(h->h_train_ctrl) + slot * train_ctrl_bytes(h), h->d_train_ctrl,
+                              train_ctrl_bytes(h), cudaMemcpyDeviceToHost, st));
+  NNB_CUDA(h, cudaEventRecord(h->train_ev[slot], st));
+  h->train_slot_grid[slot] = grid;
+  ++h->train_begun;
+  return NNB_OK;
+}
+
+extern "C" int nnb_train_epoch_end(nnb_handle* h, double* train_loss_sum, double* val_nll_sum, int* grid_out) {
+  if (!h) return NNB_ERR_ARG;
+  if (h->train_begun == h->train_ended) return nnb_fail(h, NNB_ERR_STATE, "nnb_train_epoch_end: no epoch in flight");
+  const int slot = (int)(h->train_ended & 1u);
+  ++h->train_ended;                                   // the slot is given up even if the wait fails
+  NNB_CUDA(h, cudaEventSynchronize(h->train_ev[slot]));
+  const int grid = h->train_slot_grid[slot];
   // losses: per-CTA partials added in CTA order (deterministic, unlike floating-point atomics)
-  const double* lp = reinterpret_cast<const double*>(reinterpret_cast<const char*>(h->h_train_ctrl) + kLossOff);
+  const double* lp = reinterpret_cast<const double*>(static_cast<const char*>(h->h_train_ctrl) +
+                                                     slot * train_ctrl_bytes(h) + kLossOff);
   double tl = 0.0, vl = 0.0;
   for (int c = 0; c < grid; ++c) { tl += lp[2 * c]; vl += lp[2 * c + 1]; }
-  if (a->train_loss_sum_out) *a->train_loss_sum_out = tl;
-  if (a->val_nll_sum_out) *a->val_nll_sum_out = vl;
-  if (a->grid_out) *a->grid_out = grid;
+  if (train_loss_sum) *train_loss_sum = tl;
+  if (val_nll_sum) *val_nll_sum = vl;
+  if (grid_out) *grid_out = grid;
   return NNB_OK;
+}
+
+extern "C" int nnb_train_epoch(nnb_handle* h, const nnb_train_args* a, void* stream) {
+  if (!h || !a) return NNB_ERR_ARG;
+  if (h->train_begun != h->train_ended)
+    return nnb_fail(h, NNB_ERR_STATE, "nnb_train_epoch: asynchronous epochs are in flight (call nnb_train_epoch_end first)");
+  const int rc = nnb_train_epoch_begin(h, a, stream);
+  if (rc) return rc;
+  return nnb_train_epoch_end(h, a->train_loss_sum_out, a->val_nll_sum_out, a->grid_out);
 }
 
 extern "C" int nnb_mean_nn_distance(nnb_handle* h, const double* x, int64_t n, int d, double* out, void* stream) {

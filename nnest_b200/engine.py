@@ -166,12 +166,9 @@ class Engine(object):
     def train_supported(self, d, hidden, num_layers, num_blocks):
         return bool(self.lib.nnb_train_supported(d, hidden, num_layers, num_blocks, self.B200_MAX_SMEM))
 
-    def train_epoch(self, arch, params, adam_m, adam_v, step0, x_train, x_valid, batch_size, perm=None, jitter=0.0,
+    def _train_args(self, arch, params, adam_m, adam_v, step0, x_train, x_valid, batch_size, perm=None, jitter=0.0,
                     lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, seed=0, epoch=0, noise=None,
                     grad_out=None, do_train=True, grad_only=False, batch_total=0):
-        """One epoch of Trainer._train + _validate in one kernel launch (include/nnb.h: nnb_train_epoch).
-        arch = (d, hidden, num_layers, num_blocks); params / adam_m / adam_v: flat float32 cuda vectors in
-        state_dict order, updated in place.  Returns (train_loss_sum, val_nll_sum, grid)."""
         d, hidden, nl, nb = arch
         a = L.nnb_train_args()
         a.x_dim, a.hidden_dim, a.num_layers, a.num_blocks = d, hidden, nl, nb
@@ -198,11 +195,38 @@ class Engine(object):
         a.grad_out = _ptr(grad_out)
         a.do_train = 1 if do_train else 0
         a.grad_only, a.batch_total = (1 if grad_only else 0), int(batch_total)
+        return a
+
+    def train_epoch(self, *args, **kwargs):
+        """One epoch of Trainer._train + _validate in one kernel launch (include/nnb.h: nnb_train_epoch).
+        arch = (d, hidden, num_layers, num_blocks); params / adam_m / adam_v: flat float32 cuda vectors in
+        state_dict order, updated in place.  Returns (train_loss_sum, val_nll_sum, grid)."""
+        a = self._train_args(*args, **kwargs)
         tl, vl, grid = C.c_double(0.0), C.c_double(0.0), C.c_int(0)
         a.train_loss_sum_out, a.val_nll_sum_out, a.grid_out = C.pointer(tl), C.pointer(vl), C.pointer(grid)
         self._check(self.lib.nnb_train_epoch(self.h, C.byref(a), _stream()))
         self.gpu_launches += 1
         return tl.value, vl.value, grid.value
+
+    def train_epoch_begin(self, *args, **kwargs):
+        """Queue the epoch without waiting for it (nnb_train_epoch_begin; same arguments as train_epoch); at most two may
+        be in flight.  The tensors involved are only touched by stream-ordered work, so the caller may drop them."""
+        a = self._train_args(*args, **kwargs)
+        self._check(self.lib.nnb_train_epoch_begin(self.h, C.byref(a), _stream()))
+        self.gpu_launches += 1
+        self._epochs_in_flight = getattr(self, '_epochs_in_flight', 0) + 1
+
+    def train_epoch_end(self):
+        """Losses of the oldest epoch in flight: (train_loss_sum, val_nll_sum, grid)."""
+        tl, vl, grid = C.c_double(0.0), C.c_double(0.0), C.c_int(0)
+        self._epochs_in_flight = max(0, getattr(self, '_epochs_in_flight', 0) - 1)     # the library gives the slot up too
+        self._check(self.lib.nnb_train_epoch_end(self.h, C.byref(tl), C.byref(vl), C.byref(grid)))
+        return tl.value, vl.value, grid.value
+
+    def train_epoch_drain(self):
+        """Collect (and drop) whatever epochs an interrupted fit left in flight."""
+        while getattr(self, '_epochs_in_flight', 0) > 0:
+            self.train_epoch_end()
 
     def mean_nn_distance(self, x):
         """x (n, d) float64 cuda -> mean distance to the nearest other row (nnb_mean_nn_distance)."""

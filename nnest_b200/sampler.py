@@ -475,8 +475,6 @@ class Sampler(object):
                              (step, acceptance, np.min(ess), np.max(ess), jump_distance))
         return acceptance, ess, jump_distance
 
-    _CHAIN_ROWS_PER_CALL = 1 << 20
-
     def _save_samples(self, samples, loglikes, weights=None, derived_samples=None, min_weight=1e-30,
                       outfile='chain'):
         """Chain files in the reference's text format (sampler.py:494-527): weight, -loglike, parameters,
@@ -485,29 +483,23 @@ class Sampler(object):
             weights = np.ones_like(loglikes)
 
         def write(path, smp, lgl, wts, der):
-            # rows go to the formatter in blocks of _CHAIN_ROWS_PER_CALL through ONE reused staging table (appending to the
-            # file): a config-4 chain is 8.9 M rows, and a single (rows, 2 + d) float64 table of it would be another 2.3 GB
-            # of freshly faulted pages next to the samples themselves
-            smp, lgl, wts = np.asarray(smp), np.asarray(lgl), np.asarray(wts)
-            n, ncol = smp.shape[0], 2 + smp.shape[1] + (0 if der is None else np.asarray(der).shape[1])
+            # the formatter reads the arrays as they are (nnb_write_chain_rows): a config-4 chain is 8.9 M rows, and the
+            # (rows, 2 + d) float64 table np.column_stack would build is another 2.3 GB of freshly faulted pages
+            f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+            smp, lgl, wts = f64(smp), f64(lgl), f64(wts)
+            n, d = smp.shape
+            nder = 0
+            if der is not None:
+                der = f64(der).reshape(n, -1)
+                nder = der.shape[1]
             header = None
             if self.param_names is not None:
                 header = ('#weight minusloglike ' + ' '.join(self.param_names)).encode()
-            step = max(1, int(self._CHAIN_ROWS_PER_CALL))
-            table = np.empty((min(n, step), ncol), dtype=np.float64)
-            lib = L.load()
-            for lo in range(0, max(n, 1), step):
-                hi = min(n, lo + step)
-                t = table[:hi - lo]
-                np.maximum(wts[lo:hi], min_weight, out=t[:, 0])
-                np.negative(lgl[lo:hi], out=t[:, 1])
-                t[:, 2:2 + smp.shape[1]] = smp[lo:hi]
-                if der is not None:
-                    t[:, 2 + smp.shape[1]:] = np.asarray(der)[lo:hi]
-                rc = lib.nnb_write_chain_text(path.encode(), header if lo == 0 else None, t.ctypes.data_as(L._dp),
-                                              hi - lo, ncol, 0 if lo == 0 else 1)
-                if rc < 0:
-                    raise IOError('could not write %s' % path)
+            rc = L.load().nnb_write_chain_rows(path.encode(), header, wts.ctypes.data_as(L._dp), lgl.ctypes.data_as(L._dp),
+                                               smp.ctypes.data_as(L._dp), d, der.ctypes.data_as(L._dp) if nder else None,
+                                               nder, n, float(min_weight), 0)
+            if rc < 0:
+                raise IOError('could not write %s' % path)
 
         if len(samples.shape) == 2:
             write(os.path.join(self.logs['chains'], outfile + '.txt'), samples, loglikes, weights, derived_samples)

@@ -256,21 +256,47 @@ class Trainer(object):
                 self._train_seed = int(torch.randint(0, 2 ** 62, (1,)).item())    # follows torch.manual_seed
             best_state = flat.clone()
             x_train, x_valid = x_train.contiguous(), x_valid.contiguous()
+            # Epochs are queued ahead of the host (nnb_train_epoch_begin / _end): whenever the outcome of epoch e cannot end
+            # the fit (patience cannot run out at e, e is not the last epoch) epoch e + 1 is queued BEFORE the losses of e
+            # are read, so the device does not idle while the host compares losses, logs and draws the next permutation.
+            # `snap[e % 2]` = the weights after epoch e (a stream-ordered copy queued right behind the epoch): what the
+            # sequential loop would see in `flat` while it handles epoch e.
+            self.engine.train_epoch_drain()
+            snap = (torch.empty_like(flat), torch.empty_like(flat))
+            queued = 0                          # last epoch of this fit that has been queued
+            total0 = self.total_iters
+
+            def begin(e):
+                self._fused_begin(flat, x_train, x_valid, training_jitter, l2_norm, total0 + e)
+                snap[e % 2].copy_(flat)
 
         for epoch in range(1, max_iters + 1):
             self.total_iters += 1
             if fused:
-                train_loss, validation_loss = self._fused_epoch(flat, x_train, x_valid, training_jitter, l2_norm)
+                if queued < epoch:
+                    begin(epoch)
+                    queued = epoch
+                if epoch < max_iters and counter + 1 <= patience:
+                    begin(epoch + 1)
+                    queued = epoch + 1
+                train_loss, validation_loss = self._fused_end(x_train.shape[0], x_valid.shape[0])
+                flat_now = snap[epoch % 2]
                 if not (math.isfinite(train_loss) and math.isfinite(validation_loss)):
                     # A diverged step (inf / NaN loss) would poison the Adam moments for the rest of the run -- every later
                     # retrain would return the old weights.  Go back to the best weights seen and restart the moments.
                     # (The reference has no such guard; with it a rare divergence costs one epoch instead of the run.)
+                    # An epoch already queued behind the diverged one started from the poisoned weights: its result is
+                    # dropped and the epoch is queued again after the restore.
                     self.logger.warning('Epoch [%i] non-finite loss: restoring the best weights, resetting Adam' % epoch)
+                    if queued > epoch:
+                        self.engine.train_epoch_end()
+                        queued = epoch
                     flat.copy_(best_state)
                     self._adam_m.zero_()
                     self._adam_v.zero_()
                     self._adam_step = 0
                     validation_loss = float('inf')
+                    flat_now = flat
             else:
                 train_loss = self._train(epoch, x_train, jitter=training_jitter, l2_norm=l2_norm)
                 validation_loss = self._validate(epoch, x_valid)
@@ -279,7 +305,7 @@ class Trainer(object):
                 best_validation_epoch = epoch
                 best_validation_loss = validation_loss
                 if fused:
-                    best_state.copy_(flat)
+                    best_state.copy_(flat_now)
                 else:
                     best_state = torch.nn.utils.parameters_to_vector(params).detach().clone()
                 counter = 0
@@ -292,7 +318,7 @@ class Trainer(object):
                 self.writer.add_scalar('loss', validation_loss, self.total_iters)
                 if epoch % save_interval == 0:
                     if fused:
-                        _copy_into_params(params, flat)
+                        _copy_into_params(params, flat_now)
                     torch.save(self.netG.state_dict(), os.path.join(self.path, 'models', 'netG.pt'))
 
             counter += 1
@@ -300,7 +326,7 @@ class Trainer(object):
                 self.logger.info('Epoch [%i] ran out of patience' % (epoch))
                 if self.path:
                     if fused:
-                        _copy_into_params(params, flat)
+                        _copy_into_params(params, flat_now)
                     torch.save(self.netG.state_dict(), os.path.join(self.path, 'models', 'netG.pt'))
                 break
 
@@ -317,17 +343,21 @@ class Trainer(object):
             self._originals_writer.join()
             self._originals_writer = None
 
-    def _fused_epoch(self, flat, x_train, x_valid, jitter, l2_norm):
-        """Trainer._train + Trainer._validate (trainer.py:384-418) as one launch of nnb_train_epoch.  The l2 penalty's
-        gradient 2 * l2_norm * w is folded into the weight-decay term (identical update; the reported loss excludes
-        the penalty in the reference too, trainer.py:396-397)."""
+    def _fused_begin(self, flat, x_train, x_valid, jitter, l2_norm, epoch_id):
+        """Trainer._train + Trainer._validate (trainer.py:384-418) as one launch of the fused fitting kernel, queued without
+        waiting (nnb_train_epoch_begin).  The l2 penalty's gradient 2 * l2_norm * w is folded into the weight-decay term
+        (identical update; the reported loss excludes the penalty in the reference too, trainer.py:396-397)."""
         n, n_valid = x_train.shape[0], x_valid.shape[0]
         perm = torch.randperm(n, device=x_train.device) if n else None     # DataLoader(shuffle=True)
-        tl, vs, _ = self.engine.train_epoch(
+        self.engine.train_epoch_begin(
             self._arch, flat, self._adam_m, self._adam_v, self._adam_step, x_train if n else None,
             x_valid if n_valid else None, self.batch_size, perm=perm, jitter=jitter, lr=self._lr,
-            weight_decay=self._wd + 2.0 * l2_norm, seed=self._train_seed, epoch=self.total_iters)
+            weight_decay=self._wd + 2.0 * l2_norm, seed=self._train_seed, epoch=epoch_id)
         self._adam_step += (n + self.batch_size - 1) // self.batch_size
+
+    def _fused_end(self, n, n_valid):
+        """(train loss, validation loss) of the oldest queued epoch, normalised as the reference does."""
+        tl, vs, _ = self.engine.train_epoch_end()
         train_loss = tl / n if n else 0.0
         validation_loss = (vs / n_valid) / n_valid if n_valid else 0.0      # trainer.py:414-418
         return train_loss, validation_loss

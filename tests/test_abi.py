@@ -108,25 +108,35 @@ def test_chain_text_writer_matches_reference_format(lib, tmp_path):
     assert n2 > 0 and len(open(path).read().splitlines()) == table.shape[0] + 4
 
 
-def test_save_samples_in_blocks_writes_the_same_bytes(tmp_path):
-    """Sampler._save_samples hands the rows to nnb_write_chain_text in blocks (appending): the file is byte for byte what
-    the reference's '%.5E' loop writes (nnest/sampler.py:494-511), whatever the block size, with header and derived columns."""
+def test_save_samples_writes_the_reference_bytes(tmp_path):
+    """Sampler._save_samples hands the arrays to nnb_write_chain_rows (no staging table; rows formatted in batches while the
+    previous batch is written): the file is byte for byte what the reference's '%.5E' loop writes (nnest/sampler.py:
+    494-511), with header, derived columns, clipped weights, non-finite values, and across batch boundaries."""
     import types
     import numpy as np
     from nnest_b200.sampler import Sampler
     rng = np.random.RandomState(0)
-    for n, d, names, nder in ((1000, 5, None, 0), (37, 3, ['a', 'b', 'c'], 0), (0, 4, None, 0), (50, 2, None, 2)):
+    for n, d, names, nder in ((1000, 5, None, 0), (37, 3, ['a', 'b', 'c'], 0), (0, 4, None, 0), (50, 2, None, 2),
+                              (600001, 1, None, 0)):
         smp = rng.normal(size=(n, d)) * 10 ** rng.uniform(-8, 8, size=(n, 1))
         lgl = rng.normal(size=n) * 100
         w = rng.uniform(size=n) * 10 ** rng.uniform(-40, 0, size=n)
+        if n >= 37:
+            lgl[3], lgl[4], lgl[5] = np.inf, -np.inf, np.nan
+            w[6], smp[7, 0] = np.nan, -np.nan
         der = rng.normal(size=(n, nder)) if nder else None
-        cols = [np.maximum(w, 1e-30)[:, None], -lgl[:, None], smp] + ([der] if nder else [])
+        wmax = [max(v, 1e-30) for v in w]                      # the reference's Python max(): NaN stays NaN
+        cols = [np.array(wmax).reshape(n, 1), -lgl[:, None], smp] + ([der] if nder else [])
         want = ''.join(' '.join('%.5E' % v for v in row) + '\n' for row in np.concatenate(cols, axis=1))
         if names:
             want = '#weight minusloglike ' + ' '.join(names) + '\n' + want
-        for step in (1 << 20, 7):
-            out = tmp_path / ('c_%d_%d' % (n, step))
-            out.mkdir()
-            me = types.SimpleNamespace(param_names=names, logs={'chains': str(out)}, _CHAIN_ROWS_PER_CALL=step)
-            Sampler._save_samples(me, smp, lgl, weights=w, derived_samples=der)
-            assert (out / 'chain.txt').read_bytes().decode() == want
+        out = tmp_path / ('c_%d' % n)
+        out.mkdir()
+        me = types.SimpleNamespace(param_names=names, logs={'chains': str(out)})
+        Sampler._save_samples(me, smp, lgl, weights=w, derived_samples=der)
+        assert (out / 'chain.txt').read_bytes().decode() == want
+        if n == 37:          # weights=None: all ones; float32 / non-contiguous inputs are converted
+            Sampler._save_samples(me, smp.astype(np.float32)[:, ::-1], lgl, outfile='c2')
+            want2 = ''.join(' '.join('%.5E' % v for v in [1.0, -lgl[i]] + list(smp.astype(np.float32)[i, ::-1])) + '\n'
+                            for i in range(n))
+            assert (out / 'c2.txt').read_bytes().decode() == '#weight minusloglike a b c\n' + want2

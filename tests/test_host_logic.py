@@ -77,3 +77,114 @@ def test_samplers_and_trainer_refuse_to_run_without_a_gpu(tmp_path):
         Trainer(2, flow='choleksy', log_dir=None)          # only 'nvp' and 'spline' are implemented on the device
     with pytest.raises(NotImplementedError):
         Trainer(2, flow='spline', num_slow=1, log_dir=None)
+
+
+class _ScriptedEngine(object):
+    """Stands in for the device in the test of the fit loop's HOST logic: an epoch adds 1 to every weight when it is queued
+    and reports the scripted validation loss when it is collected.  Records what was queued and how many epochs were in
+    flight."""
+
+    def __init__(self, val_losses):
+        self.device = torch.device('cpu')
+        self.val = list(val_losses)
+        self.begun, self.pending, self.max_in_flight, self.dropped = [], [], 0, 0
+        self.gpu_launches = 0
+
+    def train_supported(self, *arch):
+        return True
+
+    def set_flow_from_state_dict(self, sd, scale=''):
+        self.installed = {k: v.clone() for k, v in sd.items()}
+
+    def mean_nn_distance(self, x):
+        return 0.0
+
+    def train_epoch_begin(self, arch, flat, m, v, step0, x_train, x_valid, batch, perm=None, epoch=0, **kw):
+        assert len(self.pending) < 2                                     # the library's limit
+        assert sorted(perm.tolist()) == list(range(x_train.shape[0]))
+        k = len(self.begun)
+        self.begun.append((int(epoch), int(step0), float(flat[0])))
+        flat += 1.0
+        self.pending.append(self.val[k] if k < len(self.val) else self.val[-1])
+        self.max_in_flight = max(self.max_in_flight, len(self.pending))
+
+    def train_epoch_end(self):
+        v = self.pending.pop(0)
+        return 1.0, v, 1
+
+    def train_epoch_drain(self):
+        self.dropped += len(self.pending)
+        del self.pending[:]
+
+
+def _sequential_fit(val_losses, max_iters, patience):
+    """the reference's loop (nnest/trainer.py:170-207) on a list of validation losses: (best epoch, epochs run)"""
+    best, best_epoch, counter = float('inf'), 0, 0
+    for epoch in range(1, max_iters + 1):
+        v = val_losses[min(epoch, len(val_losses)) - 1]
+        if v < best:
+            best, best_epoch, counter = v, epoch, 0
+        counter += 1
+        if counter > patience:
+            return best_epoch, epoch
+    return best_epoch, max_iters
+
+
+@pytest.mark.parametrize('case', ['improving', 'patience', 'patience_short', 'plateau', 'one_epoch'])
+def test_fit_loop_queues_epochs_ahead_without_changing_the_decisions(case, monkeypatch):
+    """Trainer.train queues epoch e + 1 before it reads the losses of epoch e whenever epoch e cannot end the fit.  The
+    decisions (best epoch, weights kept, epoch at which patience runs out, Adam step numbering, no epoch left in flight or
+    run in excess) must be those of the sequential loop of nnest/trainer.py:170-207."""
+    from nnest_b200.trainer import Trainer
+    rng = np.random.RandomState(3)
+    if case == 'improving':
+        vals, max_iters, patience = list(np.linspace(5, 1, 12)), 12, 50
+    elif case == 'patience':
+        vals, max_iters, patience = [5, 4, 3] + [3.5] * 30, 30, 4
+    elif case == 'patience_short':
+        vals, max_iters, patience = [5, 6, 7, 8], 10, 1
+    elif case == 'plateau':
+        vals, max_iters, patience = list(rng.uniform(1, 2, size=40)), 40, 6
+    else:
+        vals, max_iters, patience = [2.0], 1, 50
+    eng = _ScriptedEngine(vals)
+    monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)     # the scripted engine stands in for the device
+    t = Trainer(3, flow='nvp', log_dir=None, log_level=logging.ERROR, batch_size=10, engine=eng)
+    assert t._fused
+    w0 = torch.nn.utils.parameters_to_vector(list(t.netG.parameters())).detach().clone()
+    x = rng.uniform(-1, 1, size=(50, 3))
+    t.train(x, max_iters=max_iters, jitter=0.01, patience=patience)
+    best_epoch, ran = _sequential_fit(vals, max_iters, patience)
+    assert t.best_validation_epoch == best_epoch
+    assert len(eng.begun) == ran and not eng.pending and eng.dropped == 0       # nothing queued in excess
+    if ran > 2 and patience > 1:
+        assert eng.max_in_flight == 2                                            # ... and epochs WERE queued ahead
+    n_train = 50 - 5
+    steps = (n_train + 9) // 10
+    assert [b[0] for b in eng.begun] == list(range(1, ran + 1))                  # epoch ids = total_iters
+    assert [b[1] for b in eng.begun] == [k * steps for k in range(ran)]          # Adam step numbering
+    assert np.allclose([b[2] for b in eng.begun], [float(w0[0]) + k for k in range(ran)], atol=1e-4)   # e starts from e - 1
+    w = torch.nn.utils.parameters_to_vector(list(t.netG.parameters())).detach()
+    assert torch.allclose(w, w0 + best_epoch, atol=1e-4)                         # the weights after the best epoch are kept
+    assert t.total_iters == ran and t._adam_step == ran * steps
+    # a second fit continues the numbering
+    eng.val = [1.0, 0.5]
+    k0 = len(eng.begun)
+    t.train(x, max_iters=2, jitter=0.01)
+    assert [b[0] for b in eng.begun[k0:]] == [ran + 1, ran + 2] and eng.begun[k0][1] == ran * steps
+
+
+def test_fit_loop_recovers_from_a_non_finite_epoch_with_one_queued_behind_it(monkeypatch):
+    from nnest_b200.trainer import Trainer
+    vals = [3.0, 2.0, float('nan'), 9.0, 1.5, 1.0]       # epoch 3 diverges while epoch 4 is already queued
+    eng = _ScriptedEngine(vals)
+    monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)
+    t = Trainer(3, flow='nvp', log_dir=None, log_level=logging.ERROR, batch_size=10, engine=eng)
+    w0 = torch.nn.utils.parameters_to_vector(list(t.netG.parameters())).detach().clone()
+    t.train(np.random.RandomState(0).uniform(-1, 1, size=(50, 3)), max_iters=5, jitter=0.01)
+    # queued: 1, 2, 3, 4 (dropped: it started from the diverged weights), then 4 again from the restored weights, 5
+    assert [b[0] for b in eng.begun] == [1, 2, 3, 4, 4, 5]
+    assert eng.begun[4][1] == 0 and abs(eng.begun[4][2] - float(w0[0]) - 2) < 1e-4    # Adam restarted, best weights restored
+    assert t.best_validation_epoch == 5 and not eng.pending
+    w = torch.nn.utils.parameters_to_vector(list(t.netG.parameters())).detach()
+    assert torch.allclose(w, w0 + 2 + 2, atol=1e-4)                              # epochs 4 and 5 on top of the restored weights
