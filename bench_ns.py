@@ -57,7 +57,7 @@ def main(args):
             return r
         setattr(obj, name, wrap)
 
-    epoch_ms, epoch_n = [], []
+    epoch_ms, epoch_n, epoch_ev = [], [], []
 
     def one_run(seed):
         np.random.seed(seed)
@@ -72,18 +72,18 @@ def main(args):
         timed(s, '_save_samples', 'chain_file_s', sync=False)
         timed(s, '_write_checkpoint', 'checkpoint_s', sync=False)
         eng = s.engine
-        orig_epoch = eng.train_epoch
+        orig_begin = eng.train_epoch_begin
 
-        def train_epoch(arch, params, m, v, step0, x_train, x_valid, *a, **k):
+        def train_epoch_begin(arch, params, m, v, step0, x_train, x_valid, *a, **k):
+            # the fit queues epochs ahead of the host: the event pairs are read after the run
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            r = orig_epoch(arch, params, m, v, step0, x_train, x_valid, *a, **k)
+            r = orig_begin(arch, params, m, v, step0, x_train, x_valid, *a, **k)
             e1.record()
-            e1.synchronize()
-            epoch_ms.append(e0.elapsed_time(e1))
+            epoch_ev.append((e0, e1))
             epoch_n.append((0 if x_train is None else x_train.shape[0], 0 if x_valid is None else x_valid.shape[0]))
             return r
-        eng.train_epoch = train_epoch
+        eng.train_epoch_begin = train_epoch_begin
         orig_bulk = NSBook.bulk
 
         def bulk(self, *a, **k):
@@ -99,6 +99,8 @@ def main(args):
                   log_interval=10 ** 9, chain_stats=False)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            epoch_ms.extend(e0.elapsed_time(e1) for e0, e1 in epoch_ev)
+            del epoch_ev[:]
         finally:
             NSBook.bulk = orig_bulk
         return dt, s

@@ -203,8 +203,10 @@ class NestedSampler(Sampler):
                 return
             slots = np.concatenate(pend_slots)
             chains_ = np.concatenate(pend_chains)
-            _, first_rev = np.unique(slots[::-1], return_index=True)          # last write to a slot wins
-            keep = len(slots) - 1 - first_rev
+            # last write to a slot wins: NumPy's indexed assignment keeps the last value of a repeated index
+            last = np.full(nlive, -1, dtype=np.int64)
+            last[slots] = np.arange(len(slots), dtype=np.int64)
+            keep = last[last >= 0]
             sl = torch.from_numpy(np.ascontiguousarray(slots[keep])).to(self.device)
             ch = torch.from_numpy(np.ascontiguousarray(chains_[keep])).to(self.device)
             g = self._gathered_dev
@@ -346,11 +348,13 @@ class NestedSampler(Sampler):
                     total_calls = dist.allreduce_sum_int(self.total_calls, self.device) if self.use_mpi \
                         else self.total_calls
                     scale = batch['scale']
-                    # run diagnostics (not in the reference): one record per refill -- iteration, constraint, this rank's
-                    # acceptance, fraction of chains that moved in every coordinate and beat the constraint, final scale
-                    moved = np.all(b_first != b_last, axis=1) & (b_logl > loglstar)
-                    self.refill_log.append((it, float(loglstar), float(batch.get('acceptance', np.nan)),
-                                            float(moved.mean()), float(scale)))
+                    if diagnostics:
+                        # run diagnostics (not in the reference, only on request): one record per refill -- iteration,
+                        # constraint, this rank's acceptance, fraction of chains that moved in every coordinate and beat
+                        # the constraint, final scale
+                        moved = np.all(b_first != b_last, axis=1) & (b_logl > loglstar)
+                        self.refill_log.append((it, float(loglstar), float(batch.get('acceptance', np.nan)),
+                                                float(moved.mean()), float(scale)))
 
                 c_nb = ctypes.c_int64(nb)                       # nested.py:429-439
                 fp = ctypes.POINTER(ctypes.c_float)

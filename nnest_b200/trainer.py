@@ -276,7 +276,7 @@ class Trainer(object):
                 if queued < epoch:
                     begin(epoch)
                     queued = epoch
-                if epoch < max_iters and counter + 1 <= patience:
+                if self._lookahead and epoch < max_iters and counter + 1 <= patience:
                     begin(epoch + 1)
                     queued = epoch + 1
                 train_loss, validation_loss = self._fused_end(x_train.shape[0], x_valid.shape[0])
@@ -342,6 +342,8 @@ class Trainer(object):
         if getattr(self, '_originals_writer', None) is not None:      # originals.npy is complete when train() returns
             self._originals_writer.join()
             self._originals_writer = None
+
+    _lookahead = True      # queue epoch e + 1 before the losses of epoch e are read (False: one epoch at a time; same results)
 
     def _fused_begin(self, flat, x_train, x_valid, jitter, l2_norm, epoch_id):
         """Trainer._train + Trainer._validate (trainer.py:384-418) as one launch of the fused fitting kernel, queued without

@@ -53,7 +53,8 @@ def main():
                           hidden_dim=16, num_layers=1, num_blocks=3, flow=args.flow, batch_size=args.batch_size,
                           log_level=logging.WARNING, seed=seed)
         s.run(strategy=args.strategy.split(','), train_iters=args.train_iters, mcmc_steps=args.mcmc_steps,
-              mcmc_num_chains=args.mcmc_num_chains, max_iters=args.max_iters, log_interval=10 ** 9, chain_stats=False)
+              mcmc_num_chains=args.mcmc_num_chains, max_iters=args.max_iters, log_interval=10 ** 9, chain_stats=False,
+              diagnostics=True)
         rec = dict(impl='nnest_b200', seed=seed, x_dim=d, likelihood=args.likelihood, niter=int(s.niter),
                    ncall=int(s.total_calls), logz=float(s.logz), logzerr=float(s.logzerr), h=float(s.h),
                    logz_hex=float(s.logz).hex(), num_live_points=args.num_live_points,

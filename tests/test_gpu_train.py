@@ -221,6 +221,29 @@ def test_ragged_and_degenerate_sizes(engine):
     assert tl == 0.0 and vs > 0.0 and np.array_equal(w.cpu().numpy(), w0) and float(m.abs().max()) == 0.0
 
 
+def test_queueing_epochs_ahead_does_not_change_the_fit(tmp_path):
+    """Trainer.train queues epoch e + 1 before it reads the losses of epoch e (nnb_train_epoch_begin / _end).  With the same
+    seeds the weights, the best epoch and the losses are bit-identical to the one-epoch-at-a-time loop -- also when patience
+    runs out and when the fit is called again."""
+    from nnest_b200 import Trainer
+    x = np.random.RandomState(4).normal(size=(3000, 4)) * np.array([1.0, 0.5, 2.0, 0.1])
+    out = []
+    for lookahead in (True, False):
+        np.random.seed(7)
+        torch.manual_seed(7)
+        t = Trainer(4, flow='nvp', log_dir=str(tmp_path / str(lookahead)), log_level=logging.ERROR, batch_size=256,
+                    learning_rate=0.01)
+        t._lookahead = lookahead
+        t.train(x, max_iters=40, jitter=-1, patience=3)
+        first = (t.best_validation_epoch, t.best_validation_loss, t.total_iters)
+        t.train(x[:2000], max_iters=12, jitter=0.02)
+        w = torch.nn.utils.parameters_to_vector(list(t.netG.parameters())).detach().cpu().numpy()
+        out.append((first, t.best_validation_epoch, t.best_validation_loss, t.total_iters, t._adam_step, w))
+    a, b = out
+    assert a[:5] == b[:5], (a[:5], b[:5])
+    assert np.array_equal(a[5], b[5])
+
+
 def test_trainer_tiny_dataset_and_large_batch(tmp_path):
     """Trainer.train with fewer samples than batch_size and with a validation split of one sample."""
     from nnest_b200 import Trainer
