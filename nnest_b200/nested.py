@@ -30,6 +30,7 @@ from . import dist
 from .bookkeeping import NSBook
 from .priors import UniformPrior
 from .sampler import Sampler
+from .trainer import Trainer
 
 
 class NestedSampler(Sampler):
@@ -272,7 +273,15 @@ class NestedSampler(Sampler):
                 get_samples = True
 
             if not current_method == 'rejection_prior' and (first_time or it % update_interval == 0):   # nested.py:311
-                self.trainer.train(active_u, max_iters=train_iters, jitter=jitter)     # nested.py:311-314
+                kw = {}
+                if live_dev is not None and isinstance(self.trainer, Trainer):
+                    flush_live()                                # the device copy of the live set == active_u: no upload
+                    kw['device_samples'] = live_dev[0]
+                    if os.environ.get('NNB_CHECK_LIVE_DEV'):    # tests: the invariant this relies on
+                        assert np.array_equal(live_dev[0].cpu().numpy(), active_u)
+                        assert np.array_equal(live_dev[1].cpu().numpy(), active_logl)
+                        self._live_dev_checks = getattr(self, '_live_dev_checks', 0) + 1
+                self.trainer.train(active_u, max_iters=train_iters, jitter=jitter, **kw)     # nested.py:311-314
                 first_time = False
 
             if current_method in ('rejection_prior', 'rejection_flow', 'density_flow'):
@@ -321,6 +330,7 @@ class NestedSampler(Sampler):
                         active_u[worst] = samples[nb - 1, :]
                         active_v[worst] = self.transform(active_u[worst])
                         active_logl[worst] = loglikes[nb - 1]
+                        live_dev = None                  # replaced on the host only: the device copy is rebuilt when needed
                         accept_point = True
                         break
 

@@ -190,7 +190,13 @@ class Trainer(object):
             self.engine.set_flow_spline(g.packed_for_kernel(), self.x_dim, g.num_hidden, g.num_blocks, g.num_bins,
                                         g.tail_bound)
             return
-        self.engine.set_flow_from_state_dict(self.netG.state_dict(), scale=self.scale)
+        if self.scale == '':
+            # the parameters in registration order ARE the nnb_set_flow layout (tests/test_host_logic.py): one device->host
+            # copy of the flat vector instead of one per weight / bias tensor
+            flat = torch.nn.utils.parameters_to_vector([p.detach() for p in self.netG.parameters()])
+            self.engine.set_flow(flat.cpu().numpy(), *self._arch)
+        else:
+            self.engine.set_flow_from_state_dict(self.netG.state_dict(), scale=self.scale)
 
     def load_state_dict(self, sd, permutations=None):
         """netG.load_state_dict + export to the kernels.  flow='spline': `permutations` = the fixed P matrices of the 1x1
@@ -212,14 +218,34 @@ class Trainer(object):
               jitter=0.0,
               validation_fraction=0.1,
               patience=50,
-              l2_norm=0.0):
+              l2_norm=0.0,
+              device_samples=None):
+        """Trainer.train of the reference (trainer.py:134-245).  device_samples (not in the reference): the same rows as
+        `samples`, float64, already on the device -- NestedSampler keeps its live set there -- which saves the upload."""
+        try:
+            return self._fit(samples, max_iters, log_interval, save_interval, jitter, validation_fraction, patience,
+                             l2_norm, device_samples)
+        finally:
+            # data/originals.npy is written from `samples` itself by a background thread: it is complete (and `samples` free
+            # to change) when train() returns, however it returns
+            writer = getattr(self, '_originals_writer', None)
+            if writer is not None:
+                writer.join()
+                self._originals_writer = None
+
+    def _fit(self, samples, max_iters, log_interval, save_interval, jitter, validation_fraction, patience, l2_norm,
+             device_samples):
         start_time = time.time()
         samples = np.asarray(samples)
 
         if self.path:
             self._save_originals(samples)
         # one upload of the (float64) samples serves the jitter search and the train / validation split
-        x64 = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)).to(self.device)
+        if device_samples is not None:
+            assert device_samples.dtype == torch.float64 and tuple(device_samples.shape) == tuple(samples.shape)
+            x64 = device_samples
+        else:
+            x64 = torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)).to(self.device)
 
         if jitter < 0:
             # trainer.py:147-150: 0.2 x the mean of the two nearest "neighbour" distances of every sample, the first
@@ -266,8 +292,27 @@ class Trainer(object):
             queued = 0                          # last epoch of this fit that has been queued
             total0 = self.total_iters
 
+            perms = {'first': 1, 'block': None}
+
+            def perm_of(e):
+                """DataLoader(shuffle=True): a fresh uniformly random order of the training rows for every epoch.  The
+                orders of up to 64 epochs come from ONE device sort of (epoch << 48 | 48 random bits) keys: torch.randperm
+                is a sort per call (and a host round trip below 30 000 rows), which at 50 epochs x 59 000 rows per fit
+                was several milliseconds of device time between the epoch kernels."""
+                n = x_train.shape[0]
+                if n == 0:
+                    return None
+                if perms['block'] is None or e - perms['first'] >= perms['block'].shape[0]:
+                    count = max(1, min(64, max_iters - e + 1, (1 << 25) // n))
+                    keys = torch.randint(0, 1 << 48, (count, n), device=x_train.device, dtype=torch.int64)
+                    keys += (torch.arange(count, device=x_train.device, dtype=torch.int64) << 48)[:, None]
+                    order = torch.argsort(keys.view(-1))               # segment e of the result = flat indices of epoch e
+                    perms['block'] = (order % n).view(count, n)
+                    perms['first'] = e
+                return perms['block'][e - perms['first']]
+
             def begin(e):
-                self._fused_begin(flat, x_train, x_valid, training_jitter, l2_norm, total0 + e)
+                self._fused_begin(flat, x_train, x_valid, training_jitter, l2_norm, total0 + e, perm_of(e))
                 snap[e % 2].copy_(flat)
 
         for epoch in range(1, max_iters + 1):
@@ -339,18 +384,14 @@ class Trainer(object):
                              float(best_validation_loss)))
         _copy_into_params(params, best_state)
         self._sync_device()
-        if getattr(self, '_originals_writer', None) is not None:      # originals.npy is complete when train() returns
-            self._originals_writer.join()
-            self._originals_writer = None
 
     _lookahead = True      # queue epoch e + 1 before the losses of epoch e are read (False: one epoch at a time; same results)
 
-    def _fused_begin(self, flat, x_train, x_valid, jitter, l2_norm, epoch_id):
+    def _fused_begin(self, flat, x_train, x_valid, jitter, l2_norm, epoch_id, perm):
         """Trainer._train + Trainer._validate (trainer.py:384-418) as one launch of the fused fitting kernel, queued without
         waiting (nnb_train_epoch_begin).  The l2 penalty's gradient 2 * l2_norm * w is folded into the weight-decay term
         (identical update; the reported loss excludes the penalty in the reference too, trainer.py:396-397)."""
         n, n_valid = x_train.shape[0], x_valid.shape[0]
-        perm = torch.randperm(n, device=x_train.device) if n else None     # DataLoader(shuffle=True)
         self.engine.train_epoch_begin(
             self._arch, flat, self._adam_m, self._adam_v, self._adam_step, x_train if n else None,
             x_valid if n_valid else None, self.batch_size, perm=perm, jitter=jitter, lr=self._lr,
@@ -377,9 +418,9 @@ class Trainer(object):
         prev = getattr(self, '_originals_writer', None)
         if prev is not None:
             prev.join()
-        data = np.array(samples, copy=True)
+        # no private copy: train() joins the writer before it returns, and nobody touches `samples` in between
         path = os.path.join(self.path, 'data', 'originals.npy')
-        self._originals_writer = threading.Thread(target=np.save, args=(path, data), daemon=False)
+        self._originals_writer = threading.Thread(target=np.save, args=(path, samples), daemon=False)
         self._originals_writer.start()
 
     def _train(self, epoch, x_train, jitter=0.0, l2_norm=0.0):

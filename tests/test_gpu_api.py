@@ -243,6 +243,22 @@ def test_run_diagnostics_are_recorded(tmp_path):
     assert len(rows) == len(s.trainer.fit_log) + 1
 
 
+def test_device_live_set_mirrors_the_host_live_set_at_every_retrain(tmp_path, monkeypatch):
+    """NestedSampler hands the flow fit its DEVICE copy of the live set (no upload per retrain).  That copy is maintained by
+    scatters from the gathered end states; it must equal active_u / active_logl bit for bit whenever a retrain happens --
+    after bulk runs of iterations, after single iterations, after the rejection phase."""
+    from nnest_b200 import NestedSampler
+    from nnest_b200.likelihoods import Rosenbrock
+    monkeypatch.setenv('NNB_CHECK_LIVE_DEV', '1')
+    np.random.seed(3)
+    torch.manual_seed(3)
+    s = NestedSampler(3, Rosenbrock(3), transform=lambda x: 5 * x, num_live_points=400, flow='nvp',
+                      log_dir=str(tmp_path), log_level=logging.WARNING)
+    s.run(mcmc_num_chains=150, train_iters=10, max_iters=4000, update_interval=130, chain_stats=False)
+    assert s._live_dev_checks >= 5
+    assert np.isfinite(s.logz)
+
+
 def test_trainer_injection_b1(tmp_path):
     """Sampler(trainer=obj).  (i) a separately built nnest_b200.Trainer; (ii) a foreign object that only
     honours the reference's contract (netG with the reference's state_dict keys + forward / inverse / train) -- it has

@@ -79,6 +79,19 @@ def test_samplers_and_trainer_refuse_to_run_without_a_gpu(tmp_path):
         Trainer(2, flow='spline', num_slow=1, log_dir=None)
 
 
+@pytest.mark.parametrize('arch', [(30, 16, 3, 1), (5, 32, 5, 2), (2, 16, 1, 1)])
+def test_parameter_order_is_the_set_flow_layout(arch):
+    """Trainer._sync_device hands the flat parameter vector (registration order) to nnb_set_flow: it must be the layout
+    flatten_state_dict builds key by key from the state_dict (networks.py:262-282)."""
+    from nnest_b200.networks import SingleSpeedNVP
+    from nnest_b200.engine import flatten_state_dict
+    d, h, b, l = arch
+    g = SingleSpeedNVP(d, h, b, l, scale='', device=torch.device('cpu'))
+    flat = torch.nn.utils.parameters_to_vector([p.detach() for p in g.parameters()]).numpy()
+    want, dd, hh, ll, bb, flags = flatten_state_dict(g.state_dict(), '')
+    assert (dd, hh, ll, bb, flags) == (d, h, l, b, 0) and np.array_equal(flat, want)
+
+
 class _ScriptedEngine(object):
     """Stands in for the device in the test of the fit loop's HOST logic: an epoch adds 1 to every weight when it is queued
     and reports the scripted validation loss when it is collected.  Records what was queued and how many epochs were in
@@ -93,8 +106,8 @@ class _ScriptedEngine(object):
     def train_supported(self, *arch):
         return True
 
-    def set_flow_from_state_dict(self, sd, scale=''):
-        self.installed = {k: v.clone() for k, v in sd.items()}
+    def set_flow(self, flat, d, hidden, num_layers, num_blocks, flags=0):
+        self.installed = np.array(flat, copy=True)
 
     def mean_nn_distance(self, x):
         return 0.0
@@ -166,6 +179,7 @@ def test_fit_loop_queues_epochs_ahead_without_changing_the_decisions(case, monke
     assert np.allclose([b[2] for b in eng.begun], [float(w0[0]) + k for k in range(ran)], atol=1e-4)   # e starts from e - 1
     w = torch.nn.utils.parameters_to_vector(list(t.netG.parameters())).detach()
     assert torch.allclose(w, w0 + best_epoch, atol=1e-4)                         # the weights after the best epoch are kept
+    assert np.allclose(eng.installed, w.numpy())                                 # ... and installed in the sampling kernels
     assert t.total_iters == ran and t._adam_step == ran * steps
     # a second fit continues the numbering
     eng.val = [1.0, 0.5]
