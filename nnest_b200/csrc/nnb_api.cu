@@ -432,41 +432,78 @@ extern "C" int64_t nnb_consume_scan(const float* first, const float* last, const
   return -1;
 }
 
-// Min-heap over (logl, index): the top is np.argmin's answer (first index among equal minima).  The key travels with the
-// slot index in the heap node: a sift-down step reads the two children from ONE cache line instead of chasing
-// heap[] -> key[] twice per level (65 536 live points: 2.4x faster per replacement).
+// Which point is the worst, iteration after iteration (np.argmin(active_logl): first index among equal minima), without
+// an O(nlive) pass -- or a 16-level heap walk -- per iteration.  A replacement always takes the place of the current minimum,
+// so the points present at the start leave in sorted order: they are sorted ONCE per call, and the points that came in during the call wait in a small min-heap.  The worst is the smaller of the two fronts under
+// the total order (logl, slot).
 namespace {
-struct LiveHeap {
-  struct Node { double key; int64_t slot; };
-  std::vector<Node> heap;
-  explicit LiveHeap(const double* logl, int64_t n) : heap((size_t)n) {
-    for (int64_t i = 0; i < n; ++i) heap[(size_t)i] = Node{logl[i], i};
-    for (int64_t i = n / 2 - 1; i >= 0; --i) sift_down(i);
+struct LiveNode { double key; int64_t slot; };
+inline bool live_less(const LiveNode& a, const LiveNode& b) { return a.key < b.key || (a.key == b.key && a.slot < b.slot); }
+
+// (logl, slot) ascending: stable byte-wise radix sort on an order-preserving integer image of the key (slots enter in
+// increasing order, so equal keys stay in slot order); passes whose byte is the same for every point are skipped.  Ten times
+// faster than std::sort with the pair comparator at 65 536 live points.
+void sort_live(const double* logl, int64_t n, std::vector<LiveNode>& out) {
+  struct Img { uint64_t k; int64_t slot; };
+  // scratch kept between calls (a run makes hundreds of them; fresh megabyte-sized vectors are page faults every time)
+  static thread_local std::vector<Img> a, b;
+  a.resize((size_t)n);
+  b.resize((size_t)n);
+  size_t hist[8][256] = {};
+  for (int64_t i = 0; i < n; ++i) {
+    const double v = logl[i] + 0.0;               // -0.0 == +0.0 for np.argmin: one image for both
+    uint64_t u;
+    memcpy(&u, &v, 8);
+    u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+    a[(size_t)i] = Img{u, i};
+    for (int p = 0; p < 8; ++p) ++hist[p][(u >> (8 * p)) & 255];
   }
-  static bool less(const Node& a, const Node& b) { return a.key < b.key || (a.key == b.key && a.slot < b.slot); }
-  void sift_down(int64_t i) {
-    const int64_t n = (int64_t)heap.size();
-    const Node x = heap[(size_t)i];
+  Img* src = a.data();
+  Img* dst = b.data();
+  for (int p = 0; p < 8; ++p) {
+    size_t* h = hist[p];
+    bool single = false;
+    for (int j = 0; j < 256; ++j) single |= (h[j] == (size_t)n);
+    if (single) continue;
+    size_t sum = 0;
+    for (int j = 0; j < 256; ++j) { const size_t c = h[j]; h[j] = sum; sum += c; }
+    for (int64_t i = 0; i < n; ++i) dst[h[(src[i].k >> (8 * p)) & 255]++] = src[i];
+    std::swap(src, dst);
+  }
+  out.resize((size_t)n);
+  for (int64_t i = 0; i < n; ++i) out[(size_t)i] = LiveNode{logl[src[i].slot], src[i].slot};
+}
+
+struct NewHeap {   // binary min-heap of the replacements, key stored with the slot
+  std::vector<LiveNode> h;
+  bool empty() const { return h.empty(); }
+  const LiveNode& top() const { return h[0]; }
+  void push(LiveNode x) {
+    size_t i = h.size();
+    h.push_back(x);
+    while (i > 0) {
+      const size_t p = (i - 1) / 2;
+      if (!live_less(x, h[p])) break;
+      h[i] = h[p];
+      i = p;
+    }
+    h[i] = x;
+  }
+  void pop() {
+    const LiveNode x = h.back();
+    h.pop_back();
+    const size_t n = h.size();
+    if (!n) return;
+    size_t i = 0;
     for (;;) {
-      int64_t c = 2 * i + 1;
+      size_t c = 2 * i + 1;
       if (c >= n) break;
-      if (c + 1 < n && less(heap[(size_t)c + 1], heap[(size_t)c])) ++c;
-      if (!less(heap[(size_t)c], x)) break;
-      heap[(size_t)i] = heap[(size_t)c];
+      if (c + 1 < n && live_less(h[c + 1], h[c])) ++c;
+      if (!live_less(h[c], x)) break;
+      h[i] = h[c];
       i = c;
     }
-    heap[(size_t)i] = x;
-  }
-  int64_t top() const { return heap[0].slot; }
-  double top_key() const { return heap[0].key; }
-  void replace_top(double v) {   // the slot at the top takes a new (larger) key
-    heap[0].key = v;
-    sift_down(0);
-  }
-  double max_key() const {
-    double m = heap[0].key;
-    for (const Node& nd : heap) m = nd.key > m ? nd.key : m;
-    return m;
+    h[i] = x;
   }
 };
 }  // namespace
@@ -480,19 +517,66 @@ extern "C" int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, cons
     return NNB_ERR_ARG;
   for (int64_t i = 0; i < nlive; ++i)
     if (active_logl[i] != active_logl[i]) return NNB_ERR_ARG;   // NaN has no place in the ordering
-  LiveHeap hp(active_logl, nlive);
-  std::vector<int64_t> writer((size_t)nlive, -1);
+  *exhausted = 0;
+  if (max_iters == 0) return 0;
+  const int64_t nb0 = *nb < 0 ? 0 : *nb;
+  const int64_t left = n_chains > nb0 ? n_chains - nb0 : 0;
+  // np.all(first != last, axis=1) of the chains not yet consumed does not depend on the constraint: evaluated once, by a few
+  // threads (two 8 MB arrays at config-4 size); the per-iteration scan then reads one byte and one double per chain
+  static thread_local std::vector<unsigned char> moved;
+  static thread_local std::vector<LiveNode> init;
+  static thread_local NewHeap fresh;
+  static thread_local std::vector<double> cur;
+  static thread_local std::vector<int64_t> writer;
+  moved.resize((size_t)left);
+  {
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(hw ? hw : 1u, 8u), left * d / 65536));
+    unsigned char* flags = moved.data();          // (the vector itself is thread_local: the workers must not name it)
+    auto work = [=](int64_t a, int64_t b) {
+      for (int64_t c = a; c < b; ++c) {
+        const float* x = first + (nb0 + c) * d;
+        const float* y = last + (nb0 + c) * d;
+        bool all_differ = true;
+        for (int i = 0; i < d; ++i) all_differ &= (x[i] != y[i]);
+        flags[c] = all_differ ? 1 : 0;
+      }
+    };
+    if (nt <= 1) {
+      work(0, left);
+    } else {
+      std::vector<std::thread> th;
+      const int64_t per = (left + nt - 1) / nt;
+      for (int t = 0; t < nt; ++t) th.emplace_back(work, std::min(left, t * per), std::min(left, (t + 1) * per));
+      for (auto& x : th) x.join();
+    }
+  }
+  // every iteration consumes at least one chain, the last one started may find none: at most `pops` minima are needed
+  const int64_t pops = std::min<int64_t>(std::min(max_iters, left + 1), nlive);
+  sort_live(active_logl, nlive, init);
+  int64_t front = 0;   // next of the initial points to leave
+  fresh.h.clear();
+  fresh.h.reserve((size_t)pops);
+  cur.assign(active_logl, active_logl + nlive);   // current value of every slot
+  writer.assign((size_t)nlive, -1);
   double maxl = active_logl[0];
   for (int64_t i = 1; i < nlive; ++i) maxl = active_logl[i] > maxl ? active_logl[i] : maxl;
-  *exhausted = 0;
   int64_t k = 0;
   for (; k < max_iters; ++k) {
-    const int64_t worst = hp.top();
-    const double loglstar = hp.top_key();
+    // front < pops here: at most one initial point leaves per iteration, and k < pops unless the live set was consumed
+    // entirely (pops == nlive), in which case the heap holds every live point
+    const bool from_init = front < pops && (fresh.empty() || live_less(init[(size_t)front], fresh.top()));
+    if (!from_init && fresh.empty()) return NNB_ERR_STATE;   // cannot happen (see above)
+    const int64_t worst = from_init ? init[(size_t)front].slot : fresh.top().slot;
+    const double loglstar = cur[(size_t)worst];
     worst_out[k] = worst;
     loglstar_out[k] = loglstar;
     prev_out[k] = writer[(size_t)worst];
-    const int64_t ib = nnb_consume_scan(first, last, logl_last, n_chains, d, loglstar, nb);
+    int64_t ib = -1;
+    for (int64_t c = (*nb < 0 ? 0 : *nb); c < n_chains; ++c) {        // nnb_consume_scan with the precomputed flags
+      *nb = c + 1;
+      if (moved[(size_t)(c - nb0)] && logl_last[c] > loglstar) { ib = c; break; }
+    }
     if (ib < 0) {
       *exhausted = 1;
       return k;
@@ -500,9 +584,12 @@ extern "C" int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, cons
     const double nl = logl_last[ib];
     chain_out[k] = ib;
     writer[(size_t)worst] = k;
-    hp.replace_top(nl);
+    if (from_init) ++front; else fresh.pop();
+    fresh.push(LiveNode{nl, worst});
+    cur[(size_t)worst] = nl;
     if (loglstar == maxl) {   // every live point was equal: recompute (np.max after the replacement)
-      maxl = hp.max_key();
+      maxl = cur[0];
+      for (int64_t i = 1; i < nlive; ++i) maxl = cur[(size_t)i] > maxl ? cur[(size_t)i] : maxl;
     } else if (nl > maxl) {
       maxl = nl;
     }

@@ -112,6 +112,45 @@ def test_bulk_bookkeeping_bit_exact(lib, seed, nlive, n, ties, chunk):
     assert np.array_equal(bu, au) and np.array_equal(bv, av) and np.array_equal(bl, al)
 
 
+def test_consume_large_batch_matches_the_single_iteration_scan(lib):
+    """nnb_ns_consume at a size where its helpers run on several threads (flags of 20 000 chains) and the live set is
+    radix-sorted with ties and signed zeros: the worst slots, constraints and chains it selects are those of the
+    one-iteration-at-a-time loop (np.argmin + nnb_consume_scan, nested.py:272,429-439)."""
+    import ctypes as C
+    rng = np.random.RandomState(11)
+    nlive, n, d = 3000, 20000, 8
+    logl = np.round(rng.uniform(-6, 6, size=nlive), 1)
+    logl[rng.randint(0, nlive, 40)] = 0.0
+    logl[rng.randint(0, nlive, 40)] = -0.0
+    first = rng.uniform(-1, 1, size=(n, d)).astype(np.float32)
+    last = rng.uniform(-1, 1, size=(n, d)).astype(np.float32)
+    stuck = rng.uniform(size=n) < 0.2
+    last[stuck, 2] = first[stuck, 2]
+    ll = np.round(rng.uniform(-6, 12, size=n), 1)
+    ip, dp, fp = C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_float)
+    P = lambda a, t: a.ctypes.data_as(t)
+    for max_iters in (5000, 100000):
+        worst, chain, prev = (np.empty(max_iters + 1, dtype=np.int64) for _ in range(3))
+        lstar, maxl = np.empty(max_iters + 1), np.empty(max_iters + 1)
+        nb, exh = C.c_int64(0), C.c_int(0)
+        k = lib.nnb_ns_consume(P(logl, dp), nlive, P(first, fp), P(last, fp), P(ll, dp), n, d, C.byref(nb), max_iters,
+                               P(worst, ip), P(chain, ip), P(prev, ip), P(lstar, dp), P(maxl, dp), C.byref(exh))
+        # the reference loop
+        cur, pos, j, writer = logl.copy(), C.c_int64(0), 0, {}
+        while j < max_iters:
+            w = int(np.argmin(cur))
+            assert worst[j] == w and lstar[j].tobytes() == cur[w].tobytes() and prev[j] == writer.get(w, -1), j
+            ib = lib.nnb_consume_scan(P(first, fp), P(last, fp), P(ll, dp), n, d, float(cur[w]), C.byref(pos))
+            if ib < 0:
+                break
+            assert chain[j] == ib
+            cur[w] = ll[ib]
+            writer[w] = j
+            assert maxl[j] == cur.max()
+            j += 1
+        assert k == j and nb.value == pos.value and bool(exh.value) == (j < max_iters)
+
+
 def test_bulk_respects_iteration_limit(lib):
     rng = np.random.RandomState(9)
     tr = lambda x: 5 * x
