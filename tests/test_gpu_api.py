@@ -162,7 +162,9 @@ def test_nested_run_bookkeeping_bit_exact_and_layout(tmp_path):
 
 def test_reference_evidence_test_rosenbrock(tmp_path):
     """The reference's only integration test (tests/test_nested.py:10-19): Rosenbrock-2D, 1000 live points,
-    |logz + 5.80| <= 0.2 -- here with flow='nvp' (the accelerated flow), default strategy, 1000 GPU chains."""
+    |logz + 5.80| <= 0.2 -- here with flow='nvp' (the accelerated flow), default strategy, 1000 GPU chains.  The reference's
+    own band, not a widened one: seeds 0..7 give |logz + 5.80| = 0.05 .. 0.14 (profiles/r2_data/r2_late_rosen2_band.txt), and
+    a seed reproduces bit for bit."""
     from nnest_b200 import NestedSampler
     from nnest_b200.likelihoods import Rosenbrock
     np.random.seed(0)
@@ -171,7 +173,7 @@ def test_reference_evidence_test_rosenbrock(tmp_path):
                             num_layers=1, num_blocks=3, num_slow=0, flow='nvp', log_dir=str(tmp_path),
                             log_level=logging.WARNING)
     sampler.run(mcmc_num_chains=1000, mcmc_dynamic_step_size=False, train_iters=200)
-    assert np.abs(sampler.logz + 5.80) <= 0.2 + 2 * sampler.logzerr
+    assert np.abs(sampler.logz + 5.80) <= 0.2
 
 
 def test_mcmc_sampler_gaussian_posterior(tmp_path):
