@@ -108,6 +108,39 @@ def test_chain_text_writer_matches_reference_format(lib, tmp_path):
     assert n2 > 0 and len(open(path).read().splitlines()) == table.shape[0] + 4
 
 
+def test_chain_text_fast_formatter_is_exact(lib, tmp_path):
+    """The '%.5E' spelling of nnb_write_chain_text / _rows takes a fast path (six digits from a double-double product) and
+    hands anything within 1e-6 of a rounding tie to std::to_chars.  Against Python's own '%.5E' on the cases that could go
+    wrong: magnitudes over the whole double range, decimal near-ties d.ddddd5e+k nudged by a few ulps, decade boundaries,
+    exactly representable ties, values with few mantissa bits, zeros, subnormals, the largest double."""
+    import numpy as np
+    from nnest_b200 import _lib
+    rng = np.random.RandomState(5)
+    n = 300000
+    parts = [rng.choice([-1, 1], n) * 10.0 ** rng.uniform(-307, 308, n), rng.normal(size=n) * 10.0 ** rng.randint(-3, 4, n)]
+    ties = np.array([float('%d5e%d' % (m, k - 6)) for m, k in zip(rng.randint(100000, 1000000, 60000),
+                                                                 rng.randint(-290, 290, 60000))])
+    decades = np.array([float('1e%d' % k) for k in range(-300, 301)] + [float('9.999995e%d' % k) for k in range(-300, 300)])
+    for base in (ties, decades):
+        for ulps in range(-2, 3):
+            x = base.copy()
+            for _ in range(abs(ulps)):
+                x = np.nextafter(x, np.inf if ulps > 0 else -np.inf)
+            parts.append(x)
+    parts.append(np.array([100000.5, 100001.5, 999999.5, 0.5, 0.25, 1.5, 2.5, 1048576.5, 3.0, 1e22, 1e23, 5e-324, 1e-290,
+                           1e290, 1.7976931348623157e308, 2.2250738585072014e-308, 0.0, -0.0, 123456.5, 1234565.0]))
+    parts.append(rng.randint(-10 ** 7, 10 ** 7, n // 4).astype(np.float64) / 2.0)
+    parts.append(rng.randint(0, 2 ** 53, n // 4).astype(np.float64) * 2.0 ** rng.randint(-80, 80, n // 4))
+    x = np.concatenate(parts)
+    x = np.ascontiguousarray(np.concatenate((x, np.ones((-len(x)) % 4))).reshape(-1, 4))
+    path = str(tmp_path / 'f.txt')
+    assert lib.nnb_write_chain_text(path.encode(), None, x.ctypes.data_as(_lib._dp), x.shape[0], 4, 0) > 0
+    with open(path) as f:
+        for i, line in enumerate(f):
+            assert line[:-1] == ' '.join('%.5E' % v for v in x[i]), (i, [v.hex() for v in x[i]])
+    assert i + 1 == x.shape[0]
+
+
 def test_save_samples_writes_the_reference_bytes(tmp_path):
     """Sampler._save_samples hands the arrays to nnb_write_chain_rows (no staging table; rows formatted in batches while the
     previous batch is written): the file is byte for byte what the reference's '%.5E' loop writes (nnest/sampler.py:
