@@ -2,6 +2,8 @@
 // dispatch to the per-hidden-size kernels, the likelihood kernel launch and the host-side
 // live-point scan.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdio>
@@ -728,18 +730,36 @@ inline char* format_5e(char* w, double v) {
 }
 
 // fill(r, out): the `cols` values of row r.
+// Batches of rows are formatted by all host threads into private buffers; while batch k + 1 is being formatted, the buffers
+// of batch k go to the file through a few concurrent pwrite()s at their final offsets (the page-cache copy of one writer is
+// the bottleneck of a 3.6 GB chain file: 1.8 GB/s with one writer, ~3 GB/s with two to four).
 template <typename Fill>
 int64_t write_chain(const char* path, const char* header, int64_t rows, int cols, int append, Fill fill) {
-  FILE* f = fopen(path, append ? "a" : "w");
-  if (!f) return NNB_ERR_ARG;
-  int64_t written = 0;
-  if (header && header[0]) written += fprintf(f, "%s\n", header);
-  const int64_t chunk = 1 << 15;   // rows per work item
+  const int fd = open(path, O_WRONLY | O_CREAT | (append ? 0 : O_TRUNC), 0644);
+  if (fd < 0) return NNB_ERR_ARG;
+  bool ok = true;
+  auto write_all = [fd](const char* p, size_t n, int64_t off) {
+    while (n > 0) {
+      const ssize_t w = pwrite(fd, p, n, (off_t)off);
+      if (w <= 0) return false;
+      p += w; n -= (size_t)w; off += w;
+    }
+    return true;
+  };
+  int64_t pos = append ? (int64_t)lseek(fd, 0, SEEK_END) : 0;
+  if (pos < 0) { close(fd); return NNB_ERR_ARG; }
+  const int64_t pos0 = pos;
+  if (header && header[0]) {
+    std::string hline = std::string(header) + "\n";
+    ok = write_all(hline.data(), hline.size(), pos);
+    pos += (int64_t)hline.size();
+  }
+  const int64_t chunk = 1 << 14;   // rows per work item
   unsigned hw = std::thread::hardware_concurrency();
   const int nthreads = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
+  const int nwriters = std::min(4, nthreads);
   const size_t per_row = (size_t)cols * 14 + 2;   // "-1.23456E+308 " is 14 characters at most
   std::vector<std::string> bufs[2] = {std::vector<std::string>((size_t)nthreads), std::vector<std::string>((size_t)nthreads)};
-  bool ok = true;
   auto format_batch = [&](int64_t r0, std::vector<std::string>& set) {
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; ++t) {
@@ -769,18 +789,25 @@ int64_t write_chain(const char* path, const char* header, int64_t rows, int cols
   for (int64_t r0 = 0; r0 < rows && ok; r0 += batch) {
     std::thread next;
     if (r0 + batch < rows) next = std::thread([&, r0, cur] { format_batch(r0 + batch, bufs[cur ^ 1]); });
-    for (int t = 0; t < nthreads; ++t) {
-      const std::string& o = bufs[cur][(size_t)t];
-      if (!o.empty()) {
-        if (ok && fwrite(o.data(), 1, o.size(), f) != o.size()) ok = false;
-        written += (int64_t)o.size();
-      }
-    }
+    // final offsets of this batch's buffers, then a few writers take them round robin
+    std::vector<int64_t> off((size_t)nthreads);
+    for (int t = 0; t < nthreads; ++t) { off[(size_t)t] = pos; pos += (int64_t)bufs[cur][(size_t)t].size(); }
+    std::vector<std::thread> wr;
+    std::vector<char> good((size_t)nwriters, 1);
+    for (int wi = 0; wi < nwriters; ++wi)
+      wr.emplace_back([&, wi, cur] {
+        for (int t = wi; t < nthreads; t += nwriters) {
+          const std::string& o = bufs[cur][(size_t)t];
+          if (!o.empty() && !write_all(o.data(), o.size(), off[(size_t)t])) good[(size_t)wi] = 0;
+        }
+      });
+    for (auto& x : wr) x.join();
+    for (char g : good) ok = ok && g;
     if (next.joinable()) next.join();
     cur ^= 1;
   }
-  if (fclose(f) != 0) ok = false;
-  return ok ? written : (int64_t)NNB_ERR_ARG;
+  if (close(fd) != 0) ok = false;
+  return ok ? pos - pos0 : (int64_t)NNB_ERR_ARG;
 }
 }  // namespace
 
