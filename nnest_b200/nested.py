@@ -2,7 +2,8 @@
 
 The MCMC refill (nested.py:398-427) runs in the fused CUDA kernels (Sampler._mcmc_refill); live-point
 replacement (nested.py:429-439) uses the exact host routines exported by the C ABI (nnb_consume_scan for a single
-iteration, nnb_ns_consume for a run of iterations with a heap instead of an O(nlive) argmin per iteration);
+iteration, nnb_ns_consume for a run of iterations: the live set sorted once + a heap of the replacements instead of an
+O(nlive) argmin per iteration);
 evidence bookkeeping (nested.py:272-293,458-464,487-500) is the reference's float64 arithmetic in the reference's
 order (bookkeeping.NSBook: sequential NumPy accumulations between refills / retrains / checkpoints, the scalar code
 around them), so that logZ, H and the posterior arrays are bit-identical given identical likelihood values
