@@ -442,38 +442,56 @@ namespace {
 struct LiveNode { double key; int64_t slot; };
 inline bool live_less(const LiveNode& a, const LiveNode& b) { return a.key < b.key || (a.key == b.key && a.slot < b.slot); }
 
-// (logl, slot) ascending: stable byte-wise radix sort on an order-preserving integer image of the key (slots enter in
-// increasing order, so equal keys stay in slot order); passes whose byte is the same for every point are skipped.  Ten times
-// faster than std::sort with the pair comparator at 65 536 live points.
-void sort_live(const double* logl, int64_t n, std::vector<LiveNode>& out) {
+// The `need` smallest live points (and every tie of the largest of them) in (logl, slot) order: the points are reduced
+// to an order-preserving integer image of the key, the need-th smallest image is found by selection, and only the points at
+// or below it go through a stable byte-wise radix sort (slots enter in increasing order, so equal keys stay in slot order;
+// passes whose byte is the same for every point are skipped).  A call consumes at most as many points as it has chains left
+// and iterations allowed -- on average a third of a 65 536-point live set -- and std::sort with the pair comparator would
+// cost ten times the radix passes.
+void sort_live(const double* logl, int64_t n, int64_t need, std::vector<LiveNode>& out) {
   struct Img { uint64_t k; int64_t slot; };
   // scratch kept between calls (a run makes hundreds of them; fresh megabyte-sized vectors are page faults every time)
   static thread_local std::vector<Img> a, b;
-  a.resize((size_t)n);
-  b.resize((size_t)n);
-  size_t hist[8][256] = {};
+  static thread_local std::vector<uint64_t> keys;
+  keys.resize((size_t)n);
   for (int64_t i = 0; i < n; ++i) {
     const double v = logl[i] + 0.0;               // -0.0 == +0.0 for np.argmin: one image for both
     uint64_t u;
     memcpy(&u, &v, 8);
-    u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-    a[(size_t)i] = Img{u, i};
+    keys[(size_t)i] = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+  }
+  uint64_t thr = ~0ull;
+  if (need < n) {
+    static thread_local std::vector<uint64_t> sel;
+    sel = keys;
+    std::nth_element(sel.begin(), sel.begin() + (need - 1), sel.end());
+    thr = sel[(size_t)(need - 1)];
+  }
+  a.clear();
+  a.reserve((size_t)n);
+  size_t hist[8][256] = {};
+  for (int64_t i = 0; i < n; ++i) {
+    const uint64_t u = keys[(size_t)i];
+    if (u > thr) continue;
+    a.push_back(Img{u, i});
     for (int p = 0; p < 8; ++p) ++hist[p][(u >> (8 * p)) & 255];
   }
+  const size_t m = a.size();
+  b.resize(m);
   Img* src = a.data();
   Img* dst = b.data();
   for (int p = 0; p < 8; ++p) {
     size_t* h = hist[p];
     bool single = false;
-    for (int j = 0; j < 256; ++j) single |= (h[j] == (size_t)n);
+    for (int j = 0; j < 256; ++j) single |= (h[j] == m);
     if (single) continue;
     size_t sum = 0;
     for (int j = 0; j < 256; ++j) { const size_t c = h[j]; h[j] = sum; sum += c; }
-    for (int64_t i = 0; i < n; ++i) dst[h[(src[i].k >> (8 * p)) & 255]++] = src[i];
+    for (size_t i = 0; i < m; ++i) dst[h[(src[i].k >> (8 * p)) & 255]++] = src[i];
     std::swap(src, dst);
   }
-  out.resize((size_t)n);
-  for (int64_t i = 0; i < n; ++i) out[(size_t)i] = LiveNode{logl[src[i].slot], src[i].slot};
+  out.resize(m);
+  for (size_t i = 0; i < m; ++i) out[i] = LiveNode{logl[src[i].slot], src[i].slot};
 }
 
 struct NewHeap {   // binary min-heap of the replacements, key stored with the slot
@@ -555,7 +573,8 @@ extern "C" int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, cons
   }
   // every iteration consumes at least one chain, the last one started may find none: at most `pops` minima are needed
   const int64_t pops = std::min<int64_t>(std::min(max_iters, left + 1), nlive);
-  sort_live(active_logl, nlive, init);
+  sort_live(active_logl, nlive, pops, init);      // init.size() >= pops
+  const int64_t ninit = (int64_t)init.size();
   int64_t front = 0;   // next of the initial points to leave
   fresh.h.clear();
   fresh.h.reserve((size_t)pops);
@@ -565,9 +584,9 @@ extern "C" int64_t nnb_ns_consume(const double* active_logl, int64_t nlive, cons
   for (int64_t i = 1; i < nlive; ++i) maxl = active_logl[i] > maxl ? active_logl[i] : maxl;
   int64_t k = 0;
   for (; k < max_iters; ++k) {
-    // front < pops here: at most one initial point leaves per iteration, and k < pops unless the live set was consumed
-    // entirely (pops == nlive), in which case the heap holds every live point
-    const bool from_init = front < pops && (fresh.empty() || live_less(init[(size_t)front], fresh.top()));
+    // at most one initial point leaves per iteration and at most `pops` iterations take one: front < ninit here unless the
+    // whole live set has been replaced (pops == nlive), in which case the heap holds every live point
+    const bool from_init = front < ninit && (fresh.empty() || live_less(init[(size_t)front], fresh.top()));
     if (!from_init && fresh.empty()) return NNB_ERR_STATE;   // cannot happen (see above)
     const int64_t worst = from_init ? init[(size_t)front].slot : fresh.top().slot;
     const double loglstar = cur[(size_t)worst];
