@@ -173,3 +173,26 @@ def test_save_samples_writes_the_reference_bytes(tmp_path):
             want2 = ''.join(' '.join('%.5E' % v for v in [1.0, -lgl[i]] + list(smp.astype(np.float32)[i, ::-1])) + '\n'
                             for i in range(n))
             assert (out / 'c2.txt').read_bytes().decode() == '#weight minusloglike a b c\n' + want2
+
+
+def test_save_samples_reproduces_the_files_the_reference_wrote(tmp_path):
+    """tests/golden/chain_files.npz holds the bytes the REAL reference's Sampler._save_samples wrote (make_golden_chain.py):
+    single chain with header + derived columns + weights below min_weight + infinite loglikes, single chain without
+    weights, and the multi-chain layout chain_<k>.txt (nnest/sampler.py:494-527)."""
+    import os
+    import types
+    import numpy as np
+    from nnest_b200.sampler import Sampler
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'chain_files.npz'))
+    for tag in ('named', 'plain', 'multi'):
+        out = tmp_path / tag
+        out.mkdir()
+        key = lambda k: g[tag + '/' + k] if tag + '/' + k in g.files else None
+        names = key('names')
+        me = types.SimpleNamespace(param_names=None if names is None else [str(s) for s in names],
+                                   logs={'chains': str(out)})
+        Sampler._save_samples(me, key('samples'), key('loglikes'), weights=key('weights'), derived_samples=key('derived'))
+        files = sorted(k.split('/', 1)[1] for k in g.files if k.startswith(tag + '/') and k.endswith('.txt'))
+        assert sorted(os.listdir(str(out))) == files
+        for f in files:
+            assert (out / f).read_bytes() == g[tag + '/' + f].tobytes(), (tag, f)
