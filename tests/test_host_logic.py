@@ -130,57 +130,46 @@ class _ScriptedEngine(object):
         del self.pending[:]
 
 
-def _sequential_fit(val_losses, max_iters, patience):
-    """the reference's loop (nnest/trainer.py:170-207) on a list of validation losses: (best epoch, epochs run)"""
-    best, best_epoch, counter = float('inf'), 0, 0
-    for epoch in range(1, max_iters + 1):
-        v = val_losses[min(epoch, len(val_losses)) - 1]
-        if v < best:
-            best, best_epoch, counter = v, epoch, 0
-        counter += 1
-        if counter > patience:
-            return best_epoch, epoch
-    return best_epoch, max_iters
+FIT_CASES = ['improving', 'patience', 'patience_short', 'plateau', 'one_epoch', 'ties', 'patience_zero']
 
 
-@pytest.mark.parametrize('case', ['improving', 'patience', 'patience_short', 'plateau', 'one_epoch'])
-def test_fit_loop_queues_epochs_ahead_without_changing_the_decisions(case, monkeypatch):
+@pytest.mark.parametrize('lookahead', [True, False])
+@pytest.mark.parametrize('case', FIT_CASES)
+def test_fit_loop_queues_epochs_ahead_without_changing_the_decisions(case, lookahead, monkeypatch):
     """Trainer.train queues epoch e + 1 before it reads the losses of epoch e whenever epoch e cannot end the fit.  The
-    decisions (best epoch, weights kept, epoch at which patience runs out, Adam step numbering, no epoch left in flight or
-    run in excess) must be those of the sequential loop of nnest/trainer.py:170-207."""
+    decisions -- best epoch, the epoch at which patience runs out, WHICH epoch's weights are kept -- are those the REAL
+    reference's loop (nnest/trainer.py:170-244) took on the same scripted validation losses (tests/golden/fit_loop.npz,
+    make_golden_fitloop.py); no epoch is left in flight or run in excess; Adam steps and epoch ids are numbered as in the
+    sequential loop."""
     from nnest_b200.trainer import Trainer
+    g = load('fit_loop.npz')
+    vals = [float(v) for v in g[case + '/vals']]
+    max_iters, patience = int(g[case + '/max_iters']), int(g[case + '/patience'])
+    best_epoch, ran, kept = int(g[case + '/best_epoch']), int(g[case + '/epochs_run']), int(g[case + '/kept_epoch'])
     rng = np.random.RandomState(3)
-    if case == 'improving':
-        vals, max_iters, patience = list(np.linspace(5, 1, 12)), 12, 50
-    elif case == 'patience':
-        vals, max_iters, patience = [5, 4, 3] + [3.5] * 30, 30, 4
-    elif case == 'patience_short':
-        vals, max_iters, patience = [5, 6, 7, 8], 10, 1
-    elif case == 'plateau':
-        vals, max_iters, patience = list(rng.uniform(1, 2, size=40)), 40, 6
-    else:
-        vals, max_iters, patience = [2.0], 1, 50
     eng = _ScriptedEngine(vals)
     monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)     # the scripted engine stands in for the device
     t = Trainer(3, flow='nvp', log_dir=None, log_level=logging.ERROR, batch_size=10, engine=eng)
     assert t._fused
+    t._lookahead = lookahead
     w0 = torch.nn.utils.parameters_to_vector(list(t.netG.parameters())).detach().clone()
     x = rng.uniform(-1, 1, size=(50, 3))
     t.train(x, max_iters=max_iters, jitter=0.01, patience=patience)
-    best_epoch, ran = _sequential_fit(vals, max_iters, patience)
     assert t.best_validation_epoch == best_epoch
     assert len(eng.begun) == ran and not eng.pending and eng.dropped == 0       # nothing queued in excess
-    if ran > 2 and patience > 1:
+    if lookahead and ran > 2 and patience > 1:
         assert eng.max_in_flight == 2                                            # ... and epochs WERE queued ahead
+    if not lookahead:
+        assert eng.max_in_flight == 1
     n_train = 50 - 5
     steps = (n_train + 9) // 10
     assert [b[0] for b in eng.begun] == list(range(1, ran + 1))                  # epoch ids = total_iters
     assert [b[1] for b in eng.begun] == [k * steps for k in range(ran)]          # Adam step numbering
     assert np.allclose([b[2] for b in eng.begun], [float(w0[0]) + k for k in range(ran)], atol=1e-4)   # e starts from e - 1
     w = torch.nn.utils.parameters_to_vector(list(t.netG.parameters())).detach()
-    assert torch.allclose(w, w0 + best_epoch, atol=1e-4)                         # the weights after the best epoch are kept
+    assert torch.allclose(w, w0 + kept, atol=1e-4)                               # the weights the reference keeps
     assert np.allclose(eng.installed, w.numpy())                                 # ... and installed in the sampling kernels
-    assert t.total_iters == ran and t._adam_step == ran * steps
+    assert t.total_iters == ran == int(g[case + '/total_iters']) and t._adam_step == ran * steps
     # a second fit continues the numbering
     eng.val = [1.0, 0.5]
     k0 = len(eng.begun)
