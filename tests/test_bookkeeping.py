@@ -197,3 +197,48 @@ def test_samples_with_is_the_concatenation_of_dead_and_live_points():
         bk.saved_logwt.append(np.zeros(k))
     want = np.concatenate((bk.dead_points()[0].reshape(-1, 3), av))
     assert np.array_equal(bk.samples_with(av), want)
+
+
+def test_consume_is_safe_to_call_from_several_threads(lib):
+    """nnb_ns_consume keeps its scratch buffers between calls per THREAD: two samplers replaying their batches from two host
+    threads (ctypes releases the GIL) must get what each gets alone."""
+    import ctypes as C
+    import threading
+    ip, dp, fp = C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_float)
+    P = lambda a, t: a.ctypes.data_as(t)
+
+    def problem(seed, nlive, n, d):
+        rng = np.random.RandomState(seed)
+        logl = rng.uniform(-50, -10, size=nlive)
+        first = rng.uniform(-1, 1, size=(n, d)).astype(np.float32)
+        last = rng.uniform(-1, 1, size=(n, d)).astype(np.float32)
+        ll = rng.uniform(-40, 5, size=n)
+        return logl, first, last, ll
+
+    def run(prob, reps, out):
+        logl, first, last, ll = prob
+        n, d = first.shape
+        for _ in range(reps):
+            mi = n + 1
+            worst, chain, prev = (np.empty(mi + 1, dtype=np.int64) for _ in range(3))
+            lstar, maxl = np.empty(mi + 1), np.empty(mi + 1)
+            nb, exh = C.c_int64(0), C.c_int(0)
+            k = lib.nnb_ns_consume(P(logl, dp), len(logl), P(first, fp), P(last, fp), P(ll, dp), n, d, C.byref(nb), mi,
+                                   P(worst, ip), P(chain, ip), P(prev, ip), P(lstar, dp), P(maxl, dp), C.byref(exh))
+            out.append((k, nb.value, exh.value, worst[:k].copy(), chain[:k].copy(), lstar[:k + 1].copy(), maxl[:k].copy()))
+
+    probs = [problem(1, 5000, 30000, 6), problem(2, 700, 9000, 30)]
+    alone = [[], []]
+    for i in (0, 1):
+        run(probs[i], 1, alone[i])
+    together = [[], []]
+    th = [threading.Thread(target=run, args=(probs[i], 6, together[i])) for i in (0, 1)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in (0, 1):
+        want = alone[i][0]
+        assert len(together[i]) == 6
+        for got in together[i]:
+            assert got[:3] == want[:3]
+            for a, b in zip(got[3:], want[3:]):
+                assert np.array_equal(a, b)
