@@ -196,3 +196,22 @@ def test_save_samples_reproduces_the_files_the_reference_wrote(tmp_path):
         assert sorted(os.listdir(str(out))) == files
         for f in files:
             assert (out / f).read_bytes() == g[tag + '/' + f].tobytes(), (tag, f)
+
+
+def test_chain_text_formatter_on_adversarial_floats(lib, tmp_path):
+    """hypothesis picks the doubles (subnormals, signed zeros, infinities, NaN, huge and tiny magnitudes, values one ulp
+    from a power of ten): every one is spelled as Python's '%.5E' spells it."""
+    import numpy as np
+    hyp = pytest.importorskip('hypothesis')
+    from hypothesis import strategies as st
+    from nnest_b200 import _lib
+    path = str(tmp_path / 'h.txt')
+
+    @hyp.settings(max_examples=300, deadline=None)
+    @hyp.given(st.lists(st.floats(allow_nan=True, allow_infinity=True, width=64), min_size=1, max_size=64))
+    def check(vals):
+        x = np.array(vals, dtype=np.float64).reshape(1, -1)
+        assert lib.nnb_write_chain_text(path.encode(), None, x.ctypes.data_as(_lib._dp), 1, x.shape[1], 0) > 0
+        assert open(path).read() == ' '.join('%.5E' % v for v in x[0]) + '\n'
+
+    check()
